@@ -1,0 +1,77 @@
+// Internal definitions shared by the kernels of libagrs_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "agrs.h"
+
+struct agrs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  cudaMemPool_t pool = nullptr;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  std::string err;
+  int sticky = 0;  // sticky CUDA error class
+  uint64_t launches = 0;
+  int gemm_path = AGRS_GEMM_AUTO;
+  int last_gemm_path = 0;
+  int tc_bn = 256;         // tcgen05 tile width: 256 (2 smem stages) or 128 (3 stages)
+  int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
+  int64_t tc_min_flops = 1LL << 24;  // AUTO path: below this many MACs the SIMT kernel wins on launch+fill latency
+  // small scratch for reductions (block partials + completion counter), allocated once
+  float* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  unsigned int* counter = nullptr;
+  // large workspace for split-K partials, grown on demand
+  float* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  // driver entry point for TMA descriptor encoding (resolved lazily; no link-time libcuda dependency)
+  void* encode_tiled = nullptr;
+};
+
+int agrs_fail(agrs_ctx* ctx, int code, const char* fmt, ...);
+
+#define AGRS_CHECK_CTX(ctx)                 \
+  do {                                      \
+    if (!(ctx)) return AGRS_ERR_INVALID;    \
+    if ((ctx)->sticky) return (ctx)->sticky; \
+  } while (0)
+
+#define AGRS_CUDA(ctx, expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      (ctx)->sticky = AGRS_ERR_CUDA;                                                          \
+      return agrs_fail((ctx), AGRS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                       __FILE__, __LINE__);                                                   \
+    }                                                                                         \
+  } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define AGRS_LAUNCHED(ctx)                        \
+  do {                                            \
+    (ctx)->launches++;                            \
+    AGRS_CUDA((ctx), cudaPeekAtLastError());      \
+  } while (0)
+
+#define AGRS_REQUIRE(ctx, cond, code, ...)                  \
+  do {                                                      \
+    if (!(cond)) return agrs_fail((ctx), (code), __VA_ARGS__); \
+  } while (0)
+
+int agrs_ensure_workspace(agrs_ctx* ctx, size_t nbytes);
+
+// gemm back ends (gemm_simt.cu / gemm_tcgen05.cu)
+int agrs_gemm_simt(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+                   int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
+bool agrs_gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                           const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
+int agrs_gemm_tc(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+                 int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
+
+static inline bool agrs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -1,0 +1,184 @@
+// Context, stream-ordered memory pool and transfers of libagrs_b200.so.
+// Replaces CudaData{ptr} + Drop of the reference (src/tensor/storage.rs:5-14).
+#include <stdarg.h>
+#include <string.h>
+
+#include "agrs_internal.h"
+
+int agrs_fail(agrs_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    ctx->err = buf;
+  }
+  return code;
+}
+
+static int ctx_init(int device, cudaStream_t stream, bool own, agrs_ctx** out) {
+  if (!out) return AGRS_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return AGRS_ERR_NODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AGRS_ERR_NODEVICE;
+  if (prop.major != 10) return AGRS_ERR_NODEVICE;  // sm_100a code only: no fallback of any kind
+  agrs_ctx* ctx = new agrs_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }
+  if (own) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }
+    ctx->owns_stream = true;
+  } else {
+    ctx->stream = stream;
+  }
+  // the device's default pool, told to keep freed blocks (no trim at sync points): steady-state
+  // training steps then allocate without touching the driver.
+  if (cudaDeviceGetDefaultMemPool(&ctx->pool, device) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }
+  uint64_t keep = UINT64_MAX;
+  cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  ctx->scratch_bytes = 64 * 1024 * sizeof(float);
+  if (cudaMalloc(&ctx->scratch, ctx->scratch_bytes) != cudaSuccess || cudaMalloc(&ctx->counter, 64) != cudaSuccess ||
+      cudaMemsetAsync(ctx->counter, 0, 64, ctx->stream) != cudaSuccess) {
+    delete ctx;
+    return AGRS_ERR_CUDA;
+  }
+  *out = ctx;
+  return AGRS_OK;
+}
+
+extern "C" {
+
+const char* agrs_version(void) { return "agrs_b200 0.1 (sm_100a)"; }
+
+int agrs_ctx_create(int device, agrs_ctx** out) { return ctx_init(device, nullptr, true, out); }
+
+int agrs_ctx_create_on_stream(int device, void* cuda_stream, agrs_ctx** out) {
+  return ctx_init(device, static_cast<cudaStream_t>(cuda_stream), false, out);
+}
+
+int agrs_ctx_destroy(agrs_ctx* ctx) {
+  if (!ctx) return AGRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->counter) cudaFree(ctx->counter);
+  if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return AGRS_OK;
+}
+
+const char* agrs_last_error(agrs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int agrs_sync(agrs_ctx* ctx) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AGRS_OK;
+}
+
+void* agrs_stream(agrs_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+
+uint64_t agrs_launch_count(agrs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int agrs_device_info(agrs_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes) {
+  AGRS_CHECK_CTX(ctx);
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (free_bytes || total_bytes) {
+    size_t f = 0, t = 0;
+    AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    AGRS_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+  }
+  return AGRS_OK;
+}
+
+int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out != nullptr, AGRS_ERR_INVALID, "agrs_alloc: null out");
+  if (nbytes == 0) nbytes = 4;  // empty tensors still get a distinct address
+  AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  AGRS_CUDA(ctx, cudaMallocFromPoolAsync(out, nbytes, ctx->pool, ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_free(agrs_ctx* ctx, void* ptr) {
+  AGRS_CHECK_CTX(ctx);
+  if (!ptr) return AGRS_OK;
+  AGRS_CUDA(ctx, cudaFreeAsync(ptr, ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_host_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out != nullptr, AGRS_ERR_INVALID, "agrs_host_alloc: null out");
+  AGRS_CUDA(ctx, cudaMallocHost(out, nbytes ? nbytes : 4));
+  return AGRS_OK;
+}
+
+int agrs_host_free(agrs_ctx* ctx, void* ptr) {
+  AGRS_CHECK_CTX(ctx);
+  if (ptr) AGRS_CUDA(ctx, cudaFreeHost(ptr));
+  return AGRS_OK;
+}
+
+int agrs_upload(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+  AGRS_CHECK_CTX(ctx);
+  if (nbytes == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_upload: null pointer");
+  // pageable sources are staged by the runtime before the call returns; pinned ones stay async
+  AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_download(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+  AGRS_CHECK_CTX(ctx);
+  if (nbytes == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_download: null pointer");
+  AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_copy(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+  AGRS_CHECK_CTX(ctx);
+  if (nbytes == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_copy: null pointer");
+  AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_set_gemm_path(agrs_ctx* ctx, int path) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, path >= AGRS_GEMM_AUTO && path <= AGRS_GEMM_TCGEN05, AGRS_ERR_INVALID, "unknown gemm path %d", path);
+  ctx->gemm_path = path;
+  return AGRS_OK;
+}
+
+int agrs_last_gemm_path(agrs_ctx* ctx) { return ctx ? ctx->last_gemm_path : 0; }
+
+}  // extern "C"
+
+int agrs_ensure_workspace(agrs_ctx* ctx, size_t nbytes) {
+  if (ctx->workspace_bytes >= nbytes) return AGRS_OK;
+  // growing is rare (first split-K call of a given size); stream-sync so nothing in flight uses the old block
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->workspace) AGRS_CUDA(ctx, cudaFree(ctx->workspace));
+  ctx->workspace = nullptr;
+  ctx->workspace_bytes = 0;
+  size_t want = nbytes < (size_t(16) << 20) ? (size_t(16) << 20) : nbytes;
+  AGRS_CUDA(ctx, cudaMalloc(&ctx->workspace, want));
+  ctx->workspace_bytes = want;
+  return AGRS_OK;
+}

@@ -1,0 +1,305 @@
+// HBM-bound elementwise kernels: activations, MSE backward, tensor arithmetic, SGD.
+// Every kernel touches each tensor exactly once, 16 bytes per thread per access, four
+// independent accesses in flight per thread, grid = a multiple of the SM count (persistent
+// grid-stride).  Streaming cache hints: nothing here is re-read by the same kernel.
+#include "agrs_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+constexpr int kBlocksPerSM = 8;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+// ---- functors (semantics cited from the reference) ----
+struct ReluFwd {  // functional_ndarray.rs:14-22: x > 0 ? x : 0  (-0.0, NaN -> +0.0)
+  __device__ float operator()(float x) const { return x > 0.f ? x : 0.f; }
+};
+struct ReluBwd {  // functional_ndarray.rs:23-34: x <= 0 ? 0 : g  (NaN x passes g)
+  __device__ float operator()(float x, float g) const { return x <= 0.f ? 0.f : g; }
+};
+struct SigmoidFwd {  // operators.rs:190-199: 1/(1+exp(-x)) in f32 (full-precision expf, IEEE divide)
+  __device__ float operator()(float x) const { return 1.0f / (1.0f + expf(-x)); }
+};
+struct SigmoidBwd {  // operators.rs:219-223: ((1 - s) * s) * g
+  __device__ float operator()(float x, float g) const {
+    float s = 1.0f / (1.0f + expf(-x));
+    return ((1.0f - s) * s) * g;
+  }
+};
+struct MseBwd {  // operators.rs:249-253: ((p - t) * 2.0 / B) * grad
+  float batch;
+  const float* up;
+  __device__ float operator()(float p, float t) const { return (((p - t) * 2.0f) / batch) * __ldg(up); }
+};
+struct AddOp { __device__ float operator()(float a, float b) const { return a + b; } };
+struct SubOp { __device__ float operator()(float a, float b) const { return a - b; } };
+struct MulOp { __device__ float operator()(float a, float b) const { return a * b; } };
+struct SMul { float s; __device__ float operator()(float a) const { return a * s; } };
+struct SDiv { float s; __device__ float operator()(float a) const { return a / s; } };
+struct SRsub { float s; __device__ float operator()(float a) const { return s - a; } };
+struct SAdd { float s; __device__ float operator()(float a) const { return a + s; } };
+struct NegOp { __device__ float operator()(float a) const { return -a; } };
+struct PowiOp {  // f32::powi: repeated multiplication (exp >= 0) or reciprocal of it
+  int e;
+  __device__ float operator()(float a) const {
+    int n = e < 0 ? -e : e;
+    float r = 1.0f, b = a;
+    while (n) {
+      if (n & 1) r *= b;
+      b *= b;
+      n >>= 1;
+    }
+    return e < 0 ? 1.0f / r : r;
+  }
+};
+struct Sq { __device__ float operator()(float a) const { return a * a; } };
+struct FillOp { float v; };
+
+// ---- unary: out[i] = f(a[i]) ----
+template <class F>
+__global__ void __launch_bounds__(kThreads) k_unary_v4(F f, float* __restrict__ out, const float* __restrict__ a, size_t n4) {
+  size_t stride = size_t(gridDim.x) * kThreads;
+  size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = ld4(a + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float4 r = make_float4(f(v[u].x), f(v[u].y), f(v[u].z), f(v[u].w));
+      st4(out + 4 * (i + u * stride), r);
+    }
+  }
+  for (; i < n4; i += stride) {
+    float4 v = ld4(a + 4 * i);
+    st4(out + 4 * i, make_float4(f(v.x), f(v.y), f(v.z), f(v.w)));
+  }
+}
+template <class F>
+__global__ void k_unary_s(F f, float* out, const float* a, size_t begin, size_t n) {
+  size_t i = begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) out[i] = f(a[i]);
+}
+
+// ---- binary, same length: out[i] = f(a[i], b[i]) ----
+template <class F>
+__global__ void __launch_bounds__(kThreads) k_binary_v4(F f, float* out, const float* a, const float* __restrict__ b, size_t n4) {
+  size_t stride = size_t(gridDim.x) * kThreads;
+  size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+    float4 x[kUnroll], y[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      x[u] = ld4(a + 4 * (i + u * stride));
+      y[u] = ld4(b + 4 * (i + u * stride));
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      st4(out + 4 * (i + u * stride), make_float4(f(x[u].x, y[u].x), f(x[u].y, y[u].y), f(x[u].z, y[u].z), f(x[u].w, y[u].w)));
+  }
+  for (; i < n4; i += stride) {
+    float4 x = ld4(a + 4 * i), y = ld4(b + 4 * i);
+    st4(out + 4 * i, make_float4(f(x.x, y.x), f(x.y, y.y), f(x.z, y.z), f(x.w, y.w)));
+  }
+}
+template <class F>
+__global__ void k_binary_s(F f, float* out, const float* a, const float* b, size_t begin, size_t n) {
+  size_t i = begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) out[i] = f(a[i], b[i]);
+}
+
+// ---- binary with broadcast rhs ----
+// trailing: b index = i % nb.  When nb % 4 == 0 rows are float4-tiled: (row, c4) decomposition keeps
+// the rhs load a float4 that stays in L1/L2 (nb*4 bytes, re-read by every row).
+template <class F>
+__global__ void __launch_bounds__(kThreads) k_bcast_trailing_v4(F f, float* out, const float* a, const float* __restrict__ b, size_t n4,
+                                                               unsigned nb4) {
+  size_t stride = size_t(gridDim.x) * kThreads;
+  for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) {
+    unsigned c = unsigned(i % nb4);
+    float4 x = ld4(a + 4 * i);
+    float4 y = __ldg(reinterpret_cast<const float4*>(b) + c);
+    st4(out + 4 * i, make_float4(f(x.x, y.x), f(x.y, y.y), f(x.z, y.z), f(x.w, y.w)));
+  }
+}
+template <class F>
+__global__ void k_bcast_s(F f, float* out, const float* a, const float* __restrict__ b, size_t n, size_t nb, size_t rep, int leading) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    size_t j = leading ? i / rep : i % nb;
+    out[i] = f(a[i], __ldg(b + j));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill_v4(float* out, float v, size_t n4) {
+  size_t stride = size_t(gridDim.x) * kThreads;
+  float4 r = make_float4(v, v, v, v);
+  for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n4; i += stride) st4(out + 4 * i, r);
+}
+__global__ void k_fill_s(float* out, float v, size_t begin, size_t n) {
+  size_t i = begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) out[i] = v;
+}
+
+// SGD: w -= lr * g  (optim.rs:31-33: tmp = g * lr; w -= tmp -- two roundings, kept: no FMA contraction)
+struct SgdOp {
+  float lr;
+  __device__ float operator()(float w, float g) const { return __fsub_rn(w, __fmul_rn(g, lr)); }
+};
+
+int grid_for(agrs_ctx* ctx, size_t work_items, int per_thread) {
+  size_t blocks = (work_items + size_t(kThreads) * per_thread - 1) / (size_t(kThreads) * per_thread);
+  size_t cap = size_t(ctx->sm_count) * kBlocksPerSM;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return int(blocks);
+}
+
+template <class F>
+int launch_unary(agrs_ctx* ctx, F f, float* out, const float* a, size_t n) {
+  if (n == 0) return AGRS_OK;
+  size_t n4 = (agrs_aligned16(out) && agrs_aligned16(a)) ? n / 4 : 0;
+  if (n4) {
+    k_unary_v4<F><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, n4);
+    AGRS_LAUNCHED(ctx);
+  }
+  if (n4 * 4 < n) {
+    k_unary_s<F><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, n4 * 4, n);
+    AGRS_LAUNCHED(ctx);
+  }
+  return AGRS_OK;
+}
+
+template <class F>
+int launch_binary(agrs_ctx* ctx, F f, float* out, const float* a, const float* b, size_t n) {
+  if (n == 0) return AGRS_OK;
+  size_t n4 = (agrs_aligned16(out) && agrs_aligned16(a) && agrs_aligned16(b)) ? n / 4 : 0;
+  if (n4) {
+    k_binary_v4<F><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, b, n4);
+    AGRS_LAUNCHED(ctx);
+  }
+  if (n4 * 4 < n) {
+    k_binary_s<F><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, b, n4 * 4, n);
+    AGRS_LAUNCHED(ctx);
+  }
+  return AGRS_OK;
+}
+
+template <class F>
+int launch_bcast(agrs_ctx* ctx, F f, float* out, const float* a, const float* b, size_t n, size_t nb, int bmode) {
+  if (n == 0) return AGRS_OK;
+  if (nb == n) return launch_binary(ctx, f, out, a, b, n);
+  AGRS_REQUIRE(ctx, nb > 0 && n % nb == 0, AGRS_ERR_SHAPE, "cannot broadcast %zu elements onto %zu", nb, n);
+  if (bmode == AGRS_BCAST_TRAILING && nb % 4 == 0 && nb / 4 < (size_t(1) << 31) && agrs_aligned16(out) && agrs_aligned16(a) &&
+      agrs_aligned16(b)) {
+    k_bcast_trailing_v4<F><<<grid_for(ctx, n / 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, b, n / 4, unsigned(nb / 4));
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
+  k_bcast_s<F><<<grid_for(ctx, n, 1), kThreads, 0, ctx->stream>>>(f, out, a, b, n, nb, n / nb, bmode == AGRS_BCAST_LEADING);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  if (n == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, x, AGRS_ERR_INVALID, "agrs_fill_f32: null pointer");
+  if (value == 0.0f) {  // zero_grad / zeros: the copy engine's memset
+    AGRS_CUDA(ctx, cudaMemsetAsync(x, 0, n * sizeof(float), ctx->stream));
+    return AGRS_OK;
+  }
+  size_t n4 = agrs_aligned16(x) ? n / 4 : 0;
+  if (n4) {
+    k_fill_v4<<<grid_for(ctx, n4, 1), kThreads, 0, ctx->stream>>>(x, value, n4);
+    AGRS_LAUNCHED(ctx);
+  }
+  if (n4 * 4 < n) {
+    k_fill_s<<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(x, value, n4 * 4, n);
+    AGRS_LAUNCHED(ctx);
+  }
+  return AGRS_OK;
+}
+
+int agrs_relu_fwd_f32(agrs_ctx* ctx, const float* x, float* y, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (x && y), AGRS_ERR_INVALID, "agrs_relu_fwd_f32: null pointer");
+  return launch_unary(ctx, ReluFwd{}, y, x, n);
+}
+int agrs_relu_bwd_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (x && g && dx), AGRS_ERR_INVALID, "agrs_relu_bwd_f32: null pointer");
+  return launch_binary(ctx, ReluBwd{}, dx, x, g, n);
+}
+int agrs_sigmoid_fwd_f32(agrs_ctx* ctx, const float* x, float* y, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (x && y), AGRS_ERR_INVALID, "agrs_sigmoid_fwd_f32: null pointer");
+  return launch_unary(ctx, SigmoidFwd{}, y, x, n);
+}
+int agrs_sigmoid_bwd_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (x && g && dx), AGRS_ERR_INVALID, "agrs_sigmoid_bwd_f32: null pointer");
+  return launch_binary(ctx, SigmoidBwd{}, dx, x, g, n);
+}
+int agrs_mse_bwd_f32(agrs_ctx* ctx, const float* pred, const float* target, const float* upstream1, float batch, size_t n,
+                     float* out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (pred && target && upstream1 && out), AGRS_ERR_INVALID, "agrs_mse_bwd_f32: null pointer");
+  return launch_binary(ctx, MseBwd{batch, upstream1}, out, pred, target, n);
+}
+
+int agrs_binary_f32(agrs_ctx* ctx, int op, float* out, const float* a, const float* b, size_t n, size_t nb, int bmode) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (out && a && b), AGRS_ERR_INVALID, "agrs_binary_f32: null pointer");
+  AGRS_REQUIRE(ctx, bmode == AGRS_BCAST_TRAILING || bmode == AGRS_BCAST_LEADING, AGRS_ERR_INVALID, "unknown broadcast mode %d", bmode);
+  switch (op) {
+    case AGRS_ADD: return launch_bcast(ctx, AddOp{}, out, a, b, n, nb, bmode);
+    case AGRS_SUB: return launch_bcast(ctx, SubOp{}, out, a, b, n, nb, bmode);
+    case AGRS_MUL: return launch_bcast(ctx, MulOp{}, out, a, b, n, nb, bmode);
+  }
+  return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown binary op %d", op);
+}
+
+int agrs_scalar_f32(agrs_ctx* ctx, int op, float* out, const float* a, float s, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (out && a), AGRS_ERR_INVALID, "agrs_scalar_f32: null pointer");
+  switch (op) {
+    case AGRS_SMUL: return launch_unary(ctx, SMul{s}, out, a, n);
+    case AGRS_SDIV: return launch_unary(ctx, SDiv{s}, out, a, n);
+    case AGRS_SRSUB: return launch_unary(ctx, SRsub{s}, out, a, n);
+    case AGRS_SADD: return launch_unary(ctx, SAdd{s}, out, a, n);
+  }
+  return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown scalar op %d", op);
+}
+
+int agrs_neg_f32(agrs_ctx* ctx, float* out, const float* a, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (out && a), AGRS_ERR_INVALID, "agrs_neg_f32: null pointer");
+  return launch_unary(ctx, NegOp{}, out, a, n);
+}
+
+int agrs_powi_f32(agrs_ctx* ctx, float* out, const float* a, int exp, size_t n) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (out && a), AGRS_ERR_INVALID, "agrs_powi_f32: null pointer");
+  if (exp == 2) return launch_unary(ctx, Sq{}, out, a, n);
+  return launch_unary(ctx, PowiOp{exp}, out, a, n);
+}
+
+int agrs_sgd_step_f32(agrs_ctx* ctx, float* w, const float* g, float lr, size_t n, size_t ng) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, n == 0 || (w && g), AGRS_ERR_INVALID, "agrs_sgd_step_f32: null pointer");
+  return launch_bcast(ctx, SgdOp{lr}, w, w, g, n, ng, AGRS_BCAST_TRAILING);
+}
+
+}  // extern "C"

@@ -1,0 +1,49 @@
+// agrs_gemm_f32: argument checking and path selection for the two GEMM back ends.
+#include "agrs_internal.h"
+
+extern "C" {
+
+int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
+  AGRS_CHECK_CTX(ctx);
+  switch (key) {
+    case AGRS_TUNE_TC_BN:
+      AGRS_REQUIRE(ctx, value == 128 || value == 256, AGRS_ERR_INVALID, "AGRS_TUNE_TC_BN must be 128 or 256");
+      ctx->tc_bn = int(value);
+      return AGRS_OK;
+    case AGRS_TUNE_TC_EXPLICIT_HI:
+      ctx->tc_explicit_hi = value ? 1 : 0;
+      return AGRS_OK;
+    case AGRS_TUNE_TC_MIN_MACS:
+      ctx->tc_min_flops = value;
+      return AGRS_OK;
+  }
+  return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown tuning key %d", key);
+}
+
+int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                  const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, M >= 0 && N >= 0 && K >= 0, AGRS_ERR_INVALID, "agrs_gemm_f32: negative extent");
+  if (M == 0 || N == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, C && (K == 0 || (A && B)), AGRS_ERR_INVALID, "agrs_gemm_f32: null pointer");
+  AGRS_REQUIRE(ctx, lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, AGRS_ERR_SHAPE,
+               "agrs_gemm_f32: leading dimension too small (lda=%lld ldb=%lld ldc=%lld for M=%lld N=%lld K=%lld tA=%d tB=%d)",
+               (long long)lda, (long long)ldb, (long long)ldc, (long long)M, (long long)N, (long long)K, transA, transB);
+  const bool eligible = K > 0 && agrs_gemm_tc_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
+  bool use_tc;
+  if (ctx->gemm_path == AGRS_GEMM_TCGEN05) {
+    AGRS_REQUIRE(ctx, eligible, AGRS_ERR_UNSUPPORTED,
+                 "agrs_gemm_f32: tcgen05 path forced but operands are not TMA-mappable (16-byte aligned bases, leading dims %% 4 == 0)");
+    use_tc = true;
+  } else if (ctx->gemm_path == AGRS_GEMM_SIMT) {
+    use_tc = false;
+  } else {
+    // a 128xBN tile per SM: tiny or very skinny problems leave the tensor cores idle and pay the pipeline fill
+    use_tc = eligible && M >= 64 && N >= 32 && K >= 32 && (M * N) * K >= ctx->tc_min_flops;
+  }
+  ctx->last_gemm_path = use_tc ? AGRS_GEMM_TCGEN05 : AGRS_GEMM_SIMT;
+  if (use_tc) return agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
+  return agrs_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
+}
+
+}  // extern "C"

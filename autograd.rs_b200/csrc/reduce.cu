@@ -1,0 +1,291 @@
+// Reductions: sum / mean / fused MSE forward (storage.rs:91-112, operators.rs:237),
+// sum_axis (db = g.sum_axis(0), operators.rs:161; col.sum_axis(-1), operators.rs:443), equality, transpose.
+// All reductions are deterministic (fixed summation tree, no float atomics): replicas of a
+// data-parallel job stay bit-identical.
+#include "agrs_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sm) {  // sm: 32 floats
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = lane < (blockDim.x >> 5) ? sm[lane] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;  // valid in warp 0
+}
+
+struct LoadId {
+  const float* a;
+  __device__ float4 v4(size_t i) const { return __ldcs(reinterpret_cast<const float4*>(a) + i); }
+  __device__ float s(size_t i) const { return a[i]; }
+  __device__ static float f(float x) { return x; }
+};
+struct LoadSqDiff {
+  const float* p;
+  const float* t;
+  __device__ float4 v4(size_t i) const {
+    float4 a = __ldcs(reinterpret_cast<const float4*>(p) + i), b = __ldcs(reinterpret_cast<const float4*>(t) + i);
+    float4 d = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    return make_float4(d.x * d.x, d.y * d.y, d.z * d.z, d.w * d.w);
+  }
+  __device__ float s(size_t i) const {
+    float d = p[i] - t[i];
+    return d * d;
+  }
+};
+
+// One launch: every block reduces a grid-stride slice to partial[blockIdx]; the last block to
+// finish (atomic ticket) folds the partials in index order and writes out[0] * scale.
+template <class L>
+__global__ void __launch_bounds__(kThreads) k_reduce_all(L ld, size_t n4, size_t n, float scale, float* partial, unsigned* ticket,
+                                                        float* out) {
+  __shared__ float sm[32];
+  __shared__ bool last;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  size_t stride = size_t(gridDim.x) * kThreads;
+  size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    float4 v0 = ld.v4(i), v1 = ld.v4(i + stride), v2 = ld.v4(i + 2 * stride), v3 = ld.v4(i + 3 * stride);
+    acc[0] += (v0.x + v0.y) + (v0.z + v0.w);
+    acc[1] += (v1.x + v1.y) + (v1.z + v1.w);
+    acc[2] += (v2.x + v2.y) + (v2.z + v2.w);
+    acc[3] += (v3.x + v3.y) + (v3.z + v3.w);
+  }
+  for (; i < n4; i += stride) {
+    float4 v = ld.v4(i);
+    acc[0] += (v.x + v.y) + (v.z + v.w);
+  }
+  for (size_t j = n4 * 4 + size_t(blockIdx.x) * kThreads + threadIdx.x; j < n; j += stride) acc[1] += ld.s(j);
+  float v = block_sum((acc[0] + acc[1]) + (acc[2] + acc[3]), sm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = v;
+    __threadfence();
+    unsigned t = atomicInc(ticket, gridDim.x - 1);  // wraps back to 0 for the next launch
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += kThreads) s += __ldcg(partial + k);
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) out[0] = s * scale;
+  }
+}
+
+template <class L>
+int launch_reduce_all(agrs_ctx* ctx, L ld, size_t n, bool vec_ok, float scale, float* out) {
+  size_t n4 = vec_ok ? n / 4 : 0;
+  size_t work = n4 ? n4 : n;
+  size_t blocks = (work + size_t(kThreads) * 4 - 1) / (size_t(kThreads) * 4);
+  size_t cap = size_t(ctx->sm_count) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_reduce_all<L><<<int(blocks), kThreads, 0, ctx->stream>>>(ld, n4, n, scale, ctx->scratch, ctx->counter, out);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+// ---- sum over the middle axis of [outer, len, inner], inner >= 2: coalesced along inner ----
+// Block = 32 x 8 threads: x covers 128 consecutive inner elements as float4 (or 32 scalars),
+// y strides the reduced axis; grid.y splits `len` into chunks whose partials go to a
+// [chunks, outer*inner] workspace folded by k_fold_chunks (fixed order).
+template <int VEC>
+__global__ void __launch_bounds__(256) k_sum_axis_mid(const float* __restrict__ x, int64_t len, int64_t inner, int64_t chunk_len,
+                                                      float* __restrict__ part /*[chunks][outer*inner]*/, int64_t out_elems) {
+  __shared__ float sm[8][32 * VEC + 1];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int64_t col = (int64_t(blockIdx.x) * 32 + tx) * VEC;  // position inside inner
+  int64_t o = blockIdx.z;
+  int64_t l0 = int64_t(blockIdx.y) * chunk_len;
+  int64_t l1 = l0 + chunk_len < len ? l0 + chunk_len : len;
+  float acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  if (col < inner) {
+    const float* base = x + o * len * inner + col;
+    for (int64_t l = l0 + ty; l < l1; l += 8) {
+      if (VEC == 4) {
+        float4 v = __ldcs(reinterpret_cast<const float4*>(base + l * inner));
+        acc[0] += v.x;
+        acc[1 % VEC] += v.y;
+        acc[2 % VEC] += v.z;
+        acc[3 % VEC] += v.w;
+      } else {
+        acc[0] += __ldcs(base + l * inner);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) sm[ty][tx * VEC + v] = acc[v];
+  __syncthreads();
+  if (ty == 0 && col < inner) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s += sm[r][tx * VEC + v];
+      part[int64_t(blockIdx.y) * out_elems + o * inner + col + v] = s;
+    }
+  }
+}
+
+__global__ void k_fold_chunks(const float* __restrict__ part, int64_t chunks, int64_t out_elems, float* __restrict__ out) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= out_elems) return;
+  float s = 0.f;
+  for (int64_t c = 0; c < chunks; ++c) s += part[c * out_elems + i];
+  out[i] = s;
+}
+
+// ---- inner == 1 (sum over the last axis): one warp per output row for long rows, one thread for short ----
+__global__ void k_sum_last_warp(const float* __restrict__ x, int64_t rows, int64_t len, float* __restrict__ out) {
+  int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int64_t l = lane; l < len; l += 32) s += x[row * len + l];
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+__global__ void k_sum_last_thread(const float* __restrict__ x, int64_t rows, int64_t len, float* __restrict__ out) {
+  int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int64_t l = 0; l < len; ++l) s += x[row * len + l];
+  out[row] = s;
+}
+
+__global__ void __launch_bounds__(kThreads) k_not_equal(const float* __restrict__ a, const float* __restrict__ b, size_t n, unsigned* flag) {
+  size_t stride = size_t(gridDim.x) * kThreads;
+  bool ne = false;
+  for (size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += stride) ne |= (a[i] != b[i]);  // NaN != NaN, as ndarray ==
+  if (__syncthreads_or(ne) && threadIdx.x == 0) atomicOr(flag, 1u);
+}
+
+__global__ void k_transpose(const float* __restrict__ in, int64_t rows, int64_t cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  int64_t c = int64_t(blockIdx.x) * 32 + threadIdx.x, r0 = int64_t(blockIdx.y) * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (c < cols && r0 + j < rows) tile[j][threadIdx.x] = in[(r0 + j) * cols + c];
+  __syncthreads();
+  int64_t r = r0 + threadIdx.x, c0 = int64_t(blockIdx.x) * 32;
+  for (int j = threadIdx.y; j < 32; j += 8)
+    if (r < rows && c0 + j < cols) out[(c0 + j) * rows + r] = tile[threadIdx.x][j];
+}
+
+}  // namespace
+
+extern "C" {
+
+int agrs_sum_f32(agrs_ctx* ctx, const float* x, size_t n, float* out1) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out1 && (n == 0 || x), AGRS_ERR_INVALID, "agrs_sum_f32: null pointer");
+  return launch_reduce_all(ctx, LoadId{x}, n, agrs_aligned16(x), 1.0f, out1);
+}
+
+int agrs_mean_f32(agrs_ctx* ctx, const float* x, size_t n, float* out1) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out1 && x && n > 0, AGRS_ERR_INVALID, "agrs_mean_f32: empty or null input");
+  return launch_reduce_all(ctx, LoadId{x}, n, agrs_aligned16(x), 1.0f / float(n), out1);
+}
+
+int agrs_mse_fwd_f32(agrs_ctx* ctx, const float* pred, const float* target, size_t n, float* out1) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out1 && pred && target && n > 0, AGRS_ERR_INVALID, "agrs_mse_fwd_f32: empty or null input");
+  return launch_reduce_all(ctx, LoadSqDiff{pred, target}, n, agrs_aligned16(pred) && agrs_aligned16(target), 1.0f / float(n), out1);
+}
+
+int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len, int64_t inner, float* out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, outer >= 0 && len >= 0 && inner >= 0, AGRS_ERR_INVALID, "agrs_sum_axis_f32: negative extent");
+  int64_t out_elems = outer * inner;
+  if (out_elems == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, out && (len == 0 || x), AGRS_ERR_INVALID, "agrs_sum_axis_f32: null pointer");
+  if (len == 0) return agrs_fill_f32(ctx, out, 0.f, size_t(out_elems));
+  if (inner == 1) {
+    if (len >= 64) {
+      int64_t threads = outer * 32;
+      k_sum_last_warp<<<unsigned((threads + 255) / 256), 256, 0, ctx->stream>>>(x, outer, len, out);
+    } else {
+      k_sum_last_thread<<<unsigned((outer + 255) / 256), 256, 0, ctx->stream>>>(x, outer, len, out);
+    }
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
+  AGRS_REQUIRE(ctx, outer <= 65535, AGRS_ERR_UNSUPPORTED, "agrs_sum_axis_f32: outer=%lld > 65535 with inner > 1", (long long)outer);
+  bool vec = (inner % 4 == 0) && agrs_aligned16(x);
+  int per_block = vec ? 128 : 32;
+  int64_t gx = (inner + per_block - 1) / per_block;
+  // split the reduced axis so the grid fills the machine (>= ~4 blocks per SM), chunks of >= 64 rows
+  int64_t want = (int64_t(ctx->sm_count) * 4 + gx * outer - 1) / (gx * outer);
+  int64_t max_chunks = (len + 63) / 64;
+  int64_t chunks = want < 1 ? 1 : (want > max_chunks ? max_chunks : want);
+  if (chunks > 1024) chunks = 1024;
+  int64_t chunk_len = (len + chunks - 1) / chunks;
+  chunks = (len + chunk_len - 1) / chunk_len;
+  float* part = out;
+  if (chunks > 1) {
+    int rc = agrs_ensure_workspace(ctx, size_t(chunks) * size_t(out_elems) * sizeof(float));
+    if (rc) return rc;
+    part = ctx->workspace;
+  }
+  dim3 grid((unsigned)gx, (unsigned)chunks, (unsigned)outer);
+  if (vec)
+    k_sum_axis_mid<4><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems);
+  else
+    k_sum_axis_mid<1><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems);
+  AGRS_LAUNCHED(ctx);
+  if (chunks > 1) {
+    k_fold_chunks<<<unsigned((out_elems + 255) / 256), 256, 0, ctx->stream>>>(part, chunks, out_elems, out);
+    AGRS_LAUNCHED(ctx);
+  }
+  return AGRS_OK;
+}
+
+int agrs_equal_f32(agrs_ctx* ctx, const float* a, const float* b, size_t n, int* host_equal) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, host_equal && (n == 0 || (a && b)), AGRS_ERR_INVALID, "agrs_equal_f32: null pointer");
+  unsigned* flag = ctx->counter + 8;  // second cache line of the counter block
+  AGRS_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(unsigned), ctx->stream));
+  if (n) {
+    size_t blocks = (n + kThreads - 1) / kThreads;
+    size_t cap = size_t(ctx->sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    k_not_equal<<<int(blocks), kThreads, 0, ctx->stream>>>(a, b, n, flag);
+    AGRS_LAUNCHED(ctx);
+  }
+  unsigned h = 0;
+  AGRS_CUDA(ctx, cudaMemcpyAsync(&h, flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *host_equal = h ? 0 : 1;
+  return AGRS_OK;
+}
+
+int agrs_transpose_f32(agrs_ctx* ctx, const float* in, int64_t rows, int64_t cols, float* out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, rows >= 0 && cols >= 0, AGRS_ERR_INVALID, "agrs_transpose_f32: negative extent");
+  if (rows == 0 || cols == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, in && out, AGRS_ERR_INVALID, "agrs_transpose_f32: null pointer");
+  dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32));
+  AGRS_REQUIRE(ctx, grid.y <= 65535, AGRS_ERR_UNSUPPORTED, "agrs_transpose_f32: too many rows");
+  k_transpose<<<grid, dim3(32, 8), 0, ctx->stream>>>(in, rows, cols, out);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+}  // extern "C"

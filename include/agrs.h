@@ -1,0 +1,143 @@
+/*
+ * agrs.h -- C ABI of libagrs_b200.so: the B200 (sm_100a) device arm of autograd.rs.
+ *
+ * This is the surface a thin Rust `extern "C"` (-sys) crate binds.  Every entry point replaces
+ * one `StorageType::CudaData` arm that is `todo!()` in the reference (NickLucche/autograd.rs);
+ * the reference call site is cited next to each declaration (paths relative to the reference
+ * root).  Plain pointers and sizes only: no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - all tensors are f32, row-major ("standard layout"), device pointers unless named host_*;
+ *   - every function returns 0 (AGRS_OK) or an error class; the message is kept per context
+ *     (agrs_last_error).  Nothing unwinds or aborts across the boundary; the host wrapper turns
+ *     a non-zero code into the reference's panic message;
+ *   - every call is asynchronous on the context's stream; only agrs_download, agrs_sync,
+ *     agrs_equal_f32 and agrs_ctx_destroy block;
+ *   - one context per device, driven by one host thread (the reference's Tensor is Rc<RefCell>,
+ *     i.e. !Send: src/utils/mod.rs:5, src/autograd/autograd.rs:9).
+ *   - there is NO CPU fallback: on a machine without an sm_100 device agrs_ctx_create fails.
+ */
+#ifndef AGRS_H_
+#define AGRS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AGRS_API __attribute__((visibility("default")))
+#else
+#define AGRS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agrs_ctx agrs_ctx;
+
+enum agrs_status {
+  AGRS_OK = 0,
+  AGRS_ERR_INVALID = 1,     /* bad argument (null pointer, negative size, unknown enum) */
+  AGRS_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed; sticky per context */
+  AGRS_ERR_SHAPE = 3,       /* shapes do not conform / cannot broadcast */
+  AGRS_ERR_UNSUPPORTED = 4, /* valid request this build cannot serve (e.g. forced tcgen05 path on unaligned operands) */
+  AGRS_ERR_NODEVICE = 5     /* no CUDA device of compute capability 10.x */
+};
+
+/* ---- context, memory (replaces CudaData{ptr} + Drop, src/tensor/storage.rs:5-14) ---- */
+AGRS_API int agrs_ctx_create(int device, agrs_ctx** out);
+/* Same, but enqueue on an existing cudaStream_t (e.g. the one torch.distributed/NCCL uses). */
+AGRS_API int agrs_ctx_create_on_stream(int device, void* cuda_stream, agrs_ctx** out);
+AGRS_API int agrs_ctx_destroy(agrs_ctx* ctx);
+AGRS_API const char* agrs_last_error(agrs_ctx* ctx);
+AGRS_API int agrs_sync(agrs_ctx* ctx);
+AGRS_API void* agrs_stream(agrs_ctx* ctx); /* the cudaStream_t launches go to */
+AGRS_API int agrs_device_info(agrs_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+AGRS_API uint64_t agrs_launch_count(agrs_ctx* ctx);
+
+AGRS_API int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out); /* stream-ordered pool; 256-B aligned */
+AGRS_API int agrs_free(agrs_ctx* ctx, void* ptr);                  /* stream-ordered: safe with work in flight */
+AGRS_API int agrs_host_alloc(agrs_ctx* ctx, size_t nbytes, void** out); /* pinned host staging */
+AGRS_API int agrs_host_free(agrs_ctx* ctx, void* ptr);
+AGRS_API int agrs_upload(agrs_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);   /* Tensor::from, tensor.rs:37-61 */
+AGRS_API int agrs_download(agrs_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes); /* data()/Index/into_raw_vec, storage.rs:139-177; blocks */
+AGRS_API int agrs_copy(agrs_ctx* ctx, void* dst_dev, const void* src_dev, size_t nbytes);      /* to_owned() deep copy, tensor.rs:148,160 */
+AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);                     /* storage.rs:75; zeros/ones tensor.rs:67-84; zero_grad tensor.rs:135-140 */
+
+/* ---- GEMM (replaces Tensor::dot's CUDA arm, src/tensor/tensor.rs:319) ----
+ * C[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[N] broadcast over rows), row-major, leading dims in elements.
+ * transA=0: A is [M,K] (lda>=K); transA=1: A is stored [K,M] (lda>=M)   -- dW = X^T G (operators.rs:160)
+ * transB=0: B is [K,N] (ldb>=N); transB=1: B is stored [N,K] (ldb>=K)   -- dX = G W^T (operators.rs:159)
+ * so the reference's materialised t_clone() copies (storage.rs:84-88) never exist on the device.
+ * bias != NULL fuses `+ b` of Linear::forward / Conv2D::forward (operators.rs:144, :379) into the epilogue.
+ * Large aligned shapes run the TMA + tcgen05 3xTF32 kernel (f32-faithful: hi*hi + hi*lo + lo*hi);
+ * everything else runs the SIMT f32 kernel.  Both are CUDA; the choice never changes semantics. */
+AGRS_API int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
+                  const float* A, int64_t lda, const float* B, int64_t ldb,
+                  float* C, int64_t ldc, const float* bias);
+enum agrs_gemm_path { AGRS_GEMM_AUTO = 0, AGRS_GEMM_SIMT = 1, AGRS_GEMM_TCGEN05 = 2 };
+AGRS_API int agrs_set_gemm_path(agrs_ctx* ctx, int path); /* tests/bench: force one path; TCGEN05 on unaligned operands -> AGRS_ERR_UNSUPPORTED */
+AGRS_API int agrs_last_gemm_path(agrs_ctx* ctx);          /* path the most recent agrs_gemm_f32 took */
+/* kernel tuning knobs (tests, benches, profiling); never change results beyond f32 rounding */
+enum agrs_tuning_key {
+  AGRS_TUNE_TC_BN = 0,          /* tcgen05 tile width: 256 (default) or 128 */
+  AGRS_TUNE_TC_EXPLICIT_HI = 1, /* 1: write the tf32-truncated hi tile explicitly instead of relying on the MMA ignoring the low 13 bits */
+  AGRS_TUNE_TC_MIN_MACS = 2     /* AUTO path: minimum M*N*K for the tcgen05 kernel */
+};
+AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
+
+/* ---- activations / loss ---- */
+AGRS_API int agrs_relu_fwd_f32(agrs_ctx* ctx, const float* x, float* y, size_t n);                   /* operators.rs:115 -> functional_ndarray.rs:14-22 */
+AGRS_API int agrs_relu_bwd_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, size_t n);  /* operators.rs:103 -> functional_ndarray.rs:23-34 */
+AGRS_API int agrs_sigmoid_fwd_f32(agrs_ctx* ctx, const float* x, float* y, size_t n);                /* operators.rs:189-201 */
+AGRS_API int agrs_sigmoid_bwd_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, size_t n); /* operators.rs:214-224: ((1-s)*s)*g, s recomputed from x */
+/* out[0] = mean((p-t)^2)  (operators.rs:237) */
+AGRS_API int agrs_mse_fwd_f32(agrs_ctx* ctx, const float* pred, const float* target, size_t n, float* out1);
+/* out = ((p - t) * 2 / batch) * upstream[0]; upstream is a DEVICE scalar: no host round trip (operators.rs:247-253) */
+AGRS_API int agrs_mse_bwd_f32(agrs_ctx* ctx, const float* pred, const float* target, const float* upstream1,
+                     float batch, size_t n, float* out);
+
+/* ---- tensor arithmetic (src/tensor/storage_arithmetic.rs, src/tensor/utils.rs:16-75) ----
+ * out[i] = a[i] (op) b[j],  j = i            when nb == n
+ *                           j = i % nb       when bmode == AGRS_BCAST_TRAILING  ([O] or [1,O] onto [B,O]; [1,1] onto anything)
+ *                           j = i / (n / nb) when bmode == AGRS_BCAST_LEADING   ([B,1] onto [B,O])
+ * out may alias a (the reference's in-place forms A + &B, A -= &B, A * &B). */
+enum agrs_binop { AGRS_ADD = 0, AGRS_SUB = 1, AGRS_MUL = 2 };
+enum agrs_bcast { AGRS_BCAST_TRAILING = 0, AGRS_BCAST_LEADING = 1 };
+AGRS_API int agrs_binary_f32(agrs_ctx* ctx, int op, float* out, const float* a, const float* b, size_t n, size_t nb, int bmode);
+/* out[i] = a[i]*s | a[i]/s | s-a[i] | a[i]+s  (storage_arithmetic.rs:257-351) ; out may alias a */
+enum agrs_scalarop { AGRS_SMUL = 0, AGRS_SDIV = 1, AGRS_SRSUB = 2, AGRS_SADD = 3 };
+AGRS_API int agrs_scalar_f32(agrs_ctx* ctx, int op, float* out, const float* a, float s, size_t n);
+AGRS_API int agrs_neg_f32(agrs_ctx* ctx, float* out, const float* a, size_t n);            /* storage_arithmetic.rs:202-208 (todo!() even on CPU) */
+AGRS_API int agrs_powi_f32(agrs_ctx* ctx, float* out, const float* a, int exp, size_t n);  /* tensor.rs:220-236 */
+AGRS_API int agrs_equal_f32(agrs_ctx* ctx, const float* a, const float* b, size_t n, int* host_equal); /* storage_arithmetic.rs:211-253; blocks */
+AGRS_API int agrs_transpose_f32(agrs_ctx* ctx, const float* in, int64_t rows, int64_t cols, float* out); /* t_clone, storage.rs:84-88 (API completeness only) */
+
+/* ---- reductions (src/tensor/storage.rs:91-112) ---- */
+AGRS_API int agrs_sum_f32(agrs_ctx* ctx, const float* x, size_t n, float* out1);  /* storage.rs:91 */
+AGRS_API int agrs_mean_f32(agrs_ctx* ctx, const float* x, size_t n, float* out1); /* storage.rs:101 */
+/* x viewed as [outer, len, inner]; out[o, i] = sum_l x[o, l, i].
+ * db = g.sum_axis(0) (operators.rs:161, :405): outer=1, len=B, inner=O.
+ * col.sum_axis(-1)   (operators.rs:443):       outer=B*P*KK, len=C_in, inner=1. */
+AGRS_API int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len, int64_t inner, float* out);
+
+/* ---- optimiser (src/nn/optim.rs:25-34) ---- w[i] -= lr * g[i % ng]  (ng == n, or g broadcast: bias [1,O] -= [O]) */
+AGRS_API int agrs_sgd_step_f32(agrs_ctx* ctx, float* w, const float* g, float lr, size_t n, size_t ng);
+
+/* ---- Conv2D lowering (src/operators/functional_ndarray.rs:40-138, operators.rs:330,341,364-376) ---- */
+/* col[b, y*Wo+x, c*k*k+i*k+j] = im[b,c,y*s-p+i,x*s-p+j] or 0;  col is [B, Ho*Wo, C*k*k] */
+AGRS_API int agrs_im2col_f32(agrs_ctx* ctx, const float* im, int64_t B, int64_t C, int64_t H, int64_t W,
+                    int64_t k, int64_t stride, int64_t pad, float* col);
+/* overlap-add inverse; col is [B, Ho*Wo, C*k*k]; im_out is [B, C, (Ho-1)s+k, (Wo-1)s+k] (padded size, as the reference) */
+AGRS_API int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t C, int64_t Ho, int64_t Wo,
+                    int64_t k, int64_t stride, float* im_out);
+/* out[c*kk + r, o] = filt[r, o] for every c: the [k,k,Co] -> [Ci,k,k,Co] broadcast (storage.rs:114-120) */
+AGRS_API int agrs_broadcast_filter_f32(agrs_ctx* ctx, const float* filt, int64_t kk, int64_t c_out, int64_t c_in, float* out);
+
+AGRS_API const char* agrs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGRS_H_ */

@@ -1,0 +1,43 @@
+"""CPU-only: the C-ABI library builds, loads, and exports every symbol include/agrs.h declares.
+No compute is called (there is no GPU here); context creation must fail loudly, not fall back."""
+import ctypes
+import os
+
+import pytest
+
+import autograd_rs_b200  # noqa: F401
+from autograd_rs_b200 import _capi
+
+
+def test_every_declared_symbol_is_exported():
+    names = _capi.declared_symbols()
+    assert len(names) >= 40
+    L = ctypes.CDLL(_capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_binding_covers_header():
+    L = _capi.lib()
+    for n in _capi.declared_symbols():
+        assert getattr(L, n).restype is not None
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_capi.AgrsError) as e:
+        _capi.Ctx(0)
+    assert e.value.code == 5  # AGRS_ERR_NODEVICE
+
+
+def test_product_path_never_imports_oracle():
+    root = os.path.dirname(_capi.HERE)
+    pkg = _capi.HERE
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".hpp", ".h", ".cu")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)
+    assert os.path.isdir(os.path.join(root, "oracle"))

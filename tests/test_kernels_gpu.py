@@ -1,0 +1,305 @@
+"""GPU parity tests of the kernel-level C ABI (libagrs_b200.so) against the oracle.
+Bit-exact where the arithmetic is elementwise IEEE f32; tolerance (written per test) where a
+summation order or a transcendental differs.  Run with: pytest -m gpu (under gpurun)."""
+import numpy as np
+import pytest
+
+import autograd_rs_b200  # noqa: F401
+from autograd_rs_b200 import _capi as K
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 3, 4, 5, 1023, 4096, (1 << 20) + 3]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = K.Ctx(0)
+    yield c
+    c.close()
+
+
+def rnd(rng, *shape):
+    return rng.uniform(-2, 2, shape).astype(np.float32)
+
+
+def unary(ctx, name, x):
+    dx = ctx.to_device(x)
+    dy = ctx.empty(max(x.size, 1))
+    ctx.call(name, dx.ptr, dy.ptr, x.size)
+    return ctx.to_host(dy, x.shape)
+
+
+# ------------------------------------------------------------------ reference KATs through the C ABI
+def test_kat_relu_on_mat(ctx, kats):
+    k = kats["relu_on_mat"]
+    x = np.array(k["x"], np.float32)
+    assert np.array_equal(unary(ctx, "agrs_relu_fwd_f32", x), np.array(k["y"], np.float32))
+
+
+def test_kat_linear(ctx, kats):
+    k = kats["linear"]
+    y = ctx.gemm(np.array(k["x"]), np.array(k["w"]), bias=np.array(k["b"]).reshape(-1))
+    assert np.array_equal(y, np.array(k["y"], np.float32))
+
+
+@pytest.mark.parametrize("name", ["im2col_nopad", "im2col_pad"])
+def test_kat_im2col(ctx, kats, name):
+    k = kats[name]
+    im = np.arange(*k["im_range"], dtype=np.float32).reshape(k["im_shape"])
+    B, C, H, W = im.shape
+    dim = ctx.to_device(im)
+    n = int(np.prod(k["col_shape"]))
+    dcol = ctx.empty(n)
+    ctx.call("agrs_im2col_f32", dim.ptr, B, C, H, W, k["k"], k["stride"], k["pad"], dcol.ptr)
+    assert np.array_equal(ctx.to_host(dcol, k["col_shape"]), np.array(k["col"], np.float32).reshape(k["col_shape"]))
+
+
+def test_kat_conv2d_ones(ctx, kats):
+    k = kats["conv2d_ones"]
+    im = np.ones(k["im_shape"], np.float32)
+    filt = np.ones(k["filt_shape"], np.float32)
+    bias = np.ones(k["bias_shape"], np.float32)
+    B, C, H, W = im.shape
+    kk, co = k["k"] * k["k"], k["c_out"]
+    P = 9
+    dim, dfilt = ctx.to_device(im), ctx.to_device(filt)
+    dcol, dkm = ctx.empty(B * P * C * kk), ctx.empty(C * kk * co)
+    ctx.call("agrs_im2col_f32", dim.ptr, B, C, H, W, k["k"], 1, 0, dcol.ptr)
+    ctx.call("agrs_broadcast_filter_f32", dfilt.ptr, kk, co, C, dkm.ptr)
+    col = ctx.to_host(dcol, (B * P, C * kk))
+    km = ctx.to_host(dkm, (C * kk, co))
+    assert np.array_equal(km, O.conv_kernel_matrix(filt, C))
+    out = ctx.gemm(col, km, bias=bias).reshape(k["out_shape"])
+    assert np.all(out == k["out_value"])
+
+
+def test_kat_relu_backward_single_node(ctx, kats):
+    k = kats["single_node_graph"]
+    x = np.array(k["x"], np.float32)
+    g = np.ones_like(x)
+    dx, dg, do = ctx.to_device(x), ctx.to_device(g), ctx.empty(x.size)
+    ctx.call("agrs_relu_bwd_f32", dx.ptr, dg.ptr, do.ptr, x.size)
+    assert np.array_equal(ctx.to_host(do, x.shape), np.array(k["x_grad"], np.float32))
+
+
+# ------------------------------------------------------------------ elementwise: bit-exact
+@pytest.mark.parametrize("n", SIZES)
+def test_relu_fwd_bwd_exact(ctx, n):
+    rng = np.random.default_rng(n)
+    x = rnd(rng, n)
+    if n > 4:
+        x[:5] = [0.0, -0.0, np.nan, np.inf, -np.inf]
+    g = rnd(rng, n)
+    y = unary(ctx, "agrs_relu_fwd_f32", x)
+    want = O.relu_fwd(x)
+    assert np.array_equal(y, want) and np.array_equal(np.signbit(y), np.signbit(want))
+    dx, dg, do = ctx.to_device(x), ctx.to_device(g), ctx.empty(max(n, 1))
+    ctx.call("agrs_relu_bwd_f32", dx.ptr, dg.ptr, do.ptr, n)
+    assert np.array_equal(ctx.to_host(do, (n,)), O.relu_bwd(x, g))
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_sigmoid(ctx, n):
+    rng = np.random.default_rng(100 + n)
+    x = (rnd(rng, n) * 5).astype(np.float32)
+    g = rnd(rng, n)
+    y = unary(ctx, "agrs_sigmoid_fwd_f32", x)
+    # tolerance: CUDA expf is <= 2 ulp, Rust's f32::exp <= 1 ulp: 4e-7 relative on the output
+    assert np.allclose(y, O.sigmoid_fwd(x), rtol=4e-7, atol=1e-37)
+    dx, dg, do = ctx.to_device(x), ctx.to_device(g), ctx.empty(max(n, 1))
+    ctx.call("agrs_sigmoid_bwd_f32", dx.ptr, dg.ptr, do.ptr, n)
+    got = ctx.to_host(do, (n,))
+    want64 = O.sigmoid_bwd(x.astype(np.float64), g.astype(np.float64))
+    assert np.allclose(got, want64, rtol=2e-6, atol=1e-30)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_binary_scalar_exact(ctx, n):
+    rng = np.random.default_rng(200 + n)
+    a, b = rnd(rng, n), rnd(rng, n)
+    da, db, do = ctx.to_device(a), ctx.to_device(b), ctx.empty(max(n, 1))
+    for op, f in ((K.ADD, np.add), (K.SUB, np.subtract), (K.MUL, np.multiply)):
+        ctx.call("agrs_binary_f32", op, do.ptr, da.ptr, db.ptr, n, n, K.BCAST_TRAILING)
+        assert np.array_equal(ctx.to_host(do, (n,)), f(a, b))
+    s = np.float32(1.7)
+    for op, want in ((K.SMUL, a * s), (K.SDIV, a / s), (K.SRSUB, s - a), (K.SADD, a + s)):
+        ctx.call("agrs_scalar_f32", op, do.ptr, da.ptr, float(s), n)
+        assert np.array_equal(ctx.to_host(do, (n,)), want)
+    ctx.call("agrs_neg_f32", do.ptr, da.ptr, n)
+    assert np.array_equal(ctx.to_host(do, (n,)), -a)
+    ctx.call("agrs_powi_f32", do.ptr, da.ptr, 2, n)
+    assert np.array_equal(ctx.to_host(do, (n,)), a * a)
+    ctx.call("agrs_powi_f32", do.ptr, da.ptr, 3, n)
+    assert np.allclose(ctx.to_host(do, (n,)), a.astype(np.float64) ** 3, rtol=3e-7)
+    ctx.call("agrs_fill_f32", do.ptr, 2.5, n)
+    assert np.all(ctx.to_host(do, (n,)) == 2.5)
+    ctx.call("agrs_fill_f32", do.ptr, 0.0, n)
+    assert np.all(ctx.to_host(do, (n,)) == 0.0)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 5), (33, 8), (513, 1024), (64, 3)])
+def test_broadcast_exact(ctx, rows, cols):
+    rng = np.random.default_rng(rows * 31 + cols)
+    a = rnd(rng, rows, cols)
+    row, colv, sc = rnd(rng, cols), rnd(rng, rows, 1), rnd(rng, 1, 1)
+    da, do = ctx.to_device(a), ctx.empty(a.size)
+    n = a.size
+    d = ctx.to_device(row)
+    ctx.call("agrs_binary_f32", K.ADD, do.ptr, da.ptr, d.ptr, n, cols, K.BCAST_TRAILING)  # bias add / grad += [O]
+    assert np.array_equal(ctx.to_host(do, a.shape), a + row)
+    d = ctx.to_device(colv)
+    ctx.call("agrs_binary_f32", K.MUL, do.ptr, da.ptr, d.ptr, n, rows, K.BCAST_LEADING)
+    assert np.array_equal(ctx.to_host(do, a.shape), a * colv)
+    d = ctx.to_device(sc)
+    ctx.call("agrs_binary_f32", K.MUL, do.ptr, da.ptr, d.ptr, n, 1, K.BCAST_TRAILING)     # * grad[1,1]
+    assert np.array_equal(ctx.to_host(do, a.shape), a * sc)
+    # in place (out aliases a), and a shape that cannot broadcast
+    d = ctx.to_device(row)
+    ctx.call("agrs_binary_f32", K.SUB, da.ptr, da.ptr, d.ptr, n, cols, K.BCAST_TRAILING)
+    assert np.array_equal(ctx.to_host(da, a.shape), a - row)
+    if n % 7:
+        with pytest.raises(K.AgrsError) as e:
+            ctx.call("agrs_binary_f32", K.ADD, do.ptr, da.ptr, d.ptr, n, 7, K.BCAST_TRAILING)
+        assert e.value.code == 3
+
+
+@pytest.mark.parametrize("n,ng", [(1, 1), (12, 12), (12, 4), (4096 * 33, 4096), (1 << 20, 1 << 20), (1000003, 1000003)])
+def test_sgd_step_exact(ctx, n, ng):
+    rng = np.random.default_rng(n)
+    w, g = rnd(rng, n), rnd(rng, ng)
+    dw, dg = ctx.to_device(w), ctx.to_device(g)
+    ctx.call("agrs_sgd_step_f32", dw.ptr, dg.ptr, 1e-3, n, ng)
+    want = w.reshape(-1, ng).copy()
+    O.sgd_step(want, g, 1e-3)  # two roundings: tmp = g*lr; w -= tmp (optim.rs:31-33)
+    assert np.array_equal(ctx.to_host(dw, (n,)), want.reshape(-1))
+
+
+@pytest.mark.parametrize("B,D", [(1, 1), (5, 3), (2000, 1), (256, 4096), (1023, 77)])
+def test_mse_fwd_bwd(ctx, B, D):
+    rng = np.random.default_rng(B * 7 + D)
+    p, t = rnd(rng, B, D), rnd(rng, B, D)
+    dp, dt, dl = ctx.to_device(p), ctx.to_device(t), ctx.empty(1)
+    ctx.call("agrs_mse_fwd_f32", dp.ptr, dt.ptr, p.size, dl.ptr)
+    loss = ctx.to_host(dl, (1, 1))
+    want64 = O.mse_fwd(p.astype(np.float64), t.astype(np.float64))
+    # tolerance: tree vs sequential f32 summation, both within 1e-6 of the f64 value
+    assert abs(loss[0, 0] - want64[0, 0]) <= 1e-6 * want64[0, 0]
+    up = np.array([[1.0]], np.float32)
+    dup, dg = ctx.to_device(up), ctx.empty(p.size)
+    ctx.call("agrs_mse_bwd_f32", dp.ptr, dt.ptr, dup.ptr, float(B), p.size, dg.ptr)
+    assert np.array_equal(ctx.to_host(dg, p.shape), O.mse_bwd(p, t, up))  # IEEE sub/mul/div/mul: bit-exact
+    up = np.array([[0.37]], np.float32)
+    dup = ctx.to_device(up)
+    ctx.call("agrs_mse_bwd_f32", dp.ptr, dt.ptr, dup.ptr, float(B), p.size, dg.ptr)
+    assert np.array_equal(ctx.to_host(dg, p.shape), O.mse_bwd(p, t, up))
+
+
+@pytest.mark.parametrize("n", [1, 3, 1000, 4097, (1 << 22) + 5])
+def test_sum_mean(ctx, n):
+    rng = np.random.default_rng(n)
+    x = rnd(rng, n)
+    dx, do = ctx.to_device(x), ctx.empty(1)
+    ctx.call("agrs_sum_f32", dx.ptr, n, do.ptr)
+    s = float(ctx.to_host(do, (1,))[0])
+    ref = float(x.astype(np.float64).sum())
+    tol = 1e-6 * float(np.abs(x).astype(np.float64).sum()) + 1e-30  # tolerance: relative to sum|x|
+    assert abs(s - ref) <= tol
+    ctx.call("agrs_mean_f32", dx.ptr, n, do.ptr)
+    assert abs(float(ctx.to_host(do, (1,))[0]) - ref / n) <= tol / n + 1e-12
+    # deterministic: same bits on a second launch
+    ctx.call("agrs_sum_f32", dx.ptr, n, do.ptr)
+    assert float(ctx.to_host(do, (1,))[0]) == s
+
+
+@pytest.mark.parametrize("outer,length,inner", [(1, 1, 1), (1, 8192, 4096), (1, 2000, 1), (1, 1000, 10), (1, 777, 6),
+                                                (3, 50, 129), (5000, 3, 1), (37, 200, 1), (9 * 25, 3, 1), (1, 100000, 8)])
+def test_sum_axis(ctx, outer, length, inner):
+    rng = np.random.default_rng(outer + length + inner)
+    x = rnd(rng, outer, length, inner)
+    dx, do = ctx.to_device(x), ctx.empty(outer * inner)
+    ctx.call("agrs_sum_axis_f32", dx.ptr, outer, length, inner, do.ptr)
+    got = ctx.to_host(do, (outer, inner))
+    ref = x.astype(np.float64).sum(axis=1)
+    bound = np.abs(x).astype(np.float64).sum(axis=1)
+    assert np.all(np.abs(got - ref) <= 1e-6 * bound + 1e-30)  # tolerance relative to sum|x| per output
+
+
+def test_transpose_equal(ctx):
+    rng = np.random.default_rng(5)
+    for r, c in [(1, 1), (3, 5), (64, 64), (1000, 37)]:
+        x = rnd(rng, r, c)
+        dx, do = ctx.to_device(x), ctx.empty(x.size)
+        ctx.call("agrs_transpose_f32", dx.ptr, r, c, do.ptr)
+        assert np.array_equal(ctx.to_host(do, (c, r)), x.T)
+        import ctypes
+        eq = ctypes.c_int(-1)
+        ctx.call("agrs_equal_f32", dx.ptr, dx.ptr, x.size, ctypes.byref(eq))
+        assert eq.value == 1
+        if x.size > 1:
+            ctx.call("agrs_equal_f32", dx.ptr, do.ptr, x.size, ctypes.byref(eq))
+            assert eq.value == int(np.array_equal(x.reshape(-1), x.T.reshape(-1)))
+
+
+# ------------------------------------------------------------------ conv lowering
+@pytest.mark.parametrize("B,C,H,W,k,s,p", [(1, 1, 5, 5, 3, 1, 0), (2, 3, 8, 7, 3, 2, 1), (4, 1, 28, 28, 5, 1, 0), (3, 2, 9, 9, 2, 2, 0),
+                                           (2, 2, 6, 6, 3, 1, 2), (1, 3, 24, 24, 3, 1, 0)])
+def test_im2col_col2im(ctx, B, C, H, W, k, s, p):
+    rng = np.random.default_rng(B + C + H + k)
+    im = rnd(rng, B, C, H, W)
+    want = O.im2col(im, k, s, p)
+    ho, wo = O.conv_out_hw(H, W, k, s, p)
+    dim, dcol = ctx.to_device(im), ctx.empty(want.size)
+    ctx.call("agrs_im2col_f32", dim.ptr, B, C, H, W, k, s, p, dcol.ptr)
+    assert np.array_equal(ctx.to_host(dcol, want.shape), want)
+    col = rnd(rng, *want.shape)
+    want_im = O.col2im(col, ho, wo, s, k)
+    dcol, dout = ctx.to_device(col), ctx.empty(want_im.size)
+    ctx.call("agrs_col2im_f32", dcol.ptr, B, C, ho, wo, k, s, dout.ptr)
+    got = ctx.to_host(dout, want_im.shape)
+    assert np.array_equal(got, want_im)  # same patch order as the reference's overlap-add: bit-exact
+
+
+def test_im2col_bad_geometry(ctx):
+    d = ctx.empty(16)
+    with pytest.raises(K.AgrsError) as e:
+        ctx.call("agrs_im2col_f32", d.ptr, 1, 1, 2, 2, 5, 1, 0, d.ptr)
+    assert e.value.code == 3
+
+
+# ------------------------------------------------------------------ SIMT GEMM
+def gemm_case(ctx, rng, M, N, Kd, ta, tb, bias, path, tol):
+    A = rnd(rng, *((Kd, M) if ta else (M, Kd)))
+    B = rnd(rng, *((N, Kd) if tb else (Kd, N)))
+    bv = rnd(rng, N) if bias else None
+    got = ctx.gemm(A, B, ta, tb, bv, path)
+    opA, opB = (A.T if ta else A).astype(np.float64), (B.T if tb else B).astype(np.float64)
+    truth = opA @ opB + (bv if bias else 0)
+    err = O.rel_err(got, truth) if truth.size else 0.0
+    assert err <= tol, (M, N, Kd, ta, tb, bias, err)
+    return err
+
+
+@pytest.mark.parametrize("M,N,Kd", [(1, 1, 1), (2000, 1, 3), (3, 2000, 1), (65, 63, 17), (128, 128, 128), (1024, 10, 3456),
+                                   (25, 6, 100000), (300, 200, 100), (5, 7, 0)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_simt(ctx, M, N, Kd, ta, tb):
+    rng = np.random.default_rng(M * 3 + N * 5 + Kd)
+    # tolerance: f32 accumulation over K terms in [-4,4]: 1e-5 of max|C| is ~10x the observed error
+    gemm_case(ctx, rng, M, N, Kd, ta, tb, bool((M + N) % 2), K.GEMM_SIMT, 1e-5)
+    assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_SIMT
+
+
+def test_gemm_bad_args(ctx):
+    d = ctx.empty(64)
+    with pytest.raises(K.AgrsError) as e:
+        ctx.call("agrs_gemm_f32", 0, 0, 4, 4, 4, d.ptr, 2, d.ptr, 4, d.ptr, 4, None)  # lda < K
+    assert e.value.code == 3
+    ctx.call("agrs_set_gemm_path", K.GEMM_TCGEN05)
+    try:
+        with pytest.raises(K.AgrsError) as e:
+            ctx.call("agrs_gemm_f32", 0, 0, 4, 3, 3, d.ptr, 3, d.ptr, 3, d.ptr, 3, None)  # ld % 4 != 0: not TMA-mappable
+        assert e.value.code == 4
+    finally:
+        ctx.call("agrs_set_gemm_path", K.GEMM_AUTO)
