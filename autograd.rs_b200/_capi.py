@@ -19,7 +19,7 @@ ADD, SUB, MUL = 0, 1, 2
 SMUL, SDIV, SRSUB, SADD = 0, 1, 2, 3
 BCAST_TRAILING, BCAST_LEADING = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
-TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS = 0, 1, 2
+TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK = 0, 1, 2, 3
 
 _lib = None
 
@@ -62,6 +62,16 @@ def lib():
             "agrs_set_gemm_path": [vp, i32],
             "agrs_last_gemm_path": [vp],
             "agrs_set_tuning": [vp, i32, i64],
+            "agrs_timer_begin": [vp],
+            "agrs_timer_end": [vp, C.POINTER(f32)],
+            "agrs_profile_enable": [vp, i32],
+            "agrs_profile_gemm": [vp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)],
+            "agrs_comm_unique_id": [vp],
+            "agrs_comm_create": [vp, i32, i32, vp, C.POINTER(vp)],
+            "agrs_comm_destroy": [vp],
+            "agrs_comm_info": [vp, C.POINTER(i32), C.POINTER(i32)],
+            "agrs_comm_allreduce_f32": [vp, vp, sz, i32],
+            "agrs_comm_join": [vp],
             "agrs_relu_fwd_f32": [vp, vp, vp, sz],
             "agrs_relu_bwd_f32": [vp, vp, vp, vp, sz],
             "agrs_sigmoid_fwd_f32": [vp, vp, vp, sz],

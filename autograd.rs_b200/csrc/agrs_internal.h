@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "agrs.h"
 
@@ -21,6 +22,7 @@ struct agrs_ctx {
   int gemm_path = AGRS_GEMM_AUTO;
   int last_gemm_path = 0;
   int tc_bn = 256;         // tcgen05 tile width: 256 (2 smem stages) or 128 (3 stages)
+  int tc_kchunk = 1024;    // K elements accumulated inside the tensor core before an RN fold into C (0: whole K)
   int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
   int64_t tc_min_flops = 1LL << 24;  // AUTO path: below this many MACs the SIMT kernel wins on launch+fill latency
   // small scratch for reductions (block partials + completion counter), allocated once
@@ -30,6 +32,12 @@ struct agrs_ctx {
   // large workspace for split-K partials, grown on demand
   float* workspace = nullptr;
   size_t workspace_bytes = 0;
+  // live GEMM timing (agrs_profile_*): event pairs recorded around launches while enabled
+  struct ProfRec { cudaEvent_t start, stop; double flops; int path; };
+  cudaEvent_t timer_a = nullptr, timer_b = nullptr;  // agrs_timer_*
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
   // driver entry point for TMA descriptor encoding (resolved lazily; no link-time libcuda dependency)
   void* encode_tiled = nullptr;
 };

@@ -85,6 +85,25 @@ int agrs_sync(agrs_ctx* ctx) {
   return AGRS_OK;
 }
 
+int agrs_timer_begin(agrs_ctx* ctx) {
+  AGRS_CHECK_CTX(ctx);
+  if (!ctx->timer_a) {
+    AGRS_CUDA(ctx, cudaEventCreate(&ctx->timer_a));
+    AGRS_CUDA(ctx, cudaEventCreate(&ctx->timer_b));
+  }
+  AGRS_CUDA(ctx, cudaEventRecord(ctx->timer_a, ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_timer_end(agrs_ctx* ctx, float* ms) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, ms && ctx->timer_a, AGRS_ERR_INVALID, "agrs_timer_end without agrs_timer_begin");
+  AGRS_CUDA(ctx, cudaEventRecord(ctx->timer_b, ctx->stream));
+  AGRS_CUDA(ctx, cudaEventSynchronize(ctx->timer_b));
+  AGRS_CUDA(ctx, cudaEventElapsedTime(ms, ctx->timer_a, ctx->timer_b));
+  return AGRS_OK;
+}
+
 void* agrs_stream(agrs_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 
 uint64_t agrs_launch_count(agrs_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,6 +1,17 @@
 // agrs_gemm_f32: argument checking and path selection for the two GEMM back ends.
 #include "agrs_internal.h"
 
+static cudaEvent_t take_event(agrs_ctx* ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return e;
+}
+
 extern "C" {
 
 int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
@@ -12,6 +23,10 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
       return AGRS_OK;
     case AGRS_TUNE_TC_EXPLICIT_HI:
       ctx->tc_explicit_hi = value ? 1 : 0;
+      return AGRS_OK;
+    case AGRS_TUNE_TC_KCHUNK:
+      AGRS_REQUIRE(ctx, value >= 0 && value < (1LL << 30), AGRS_ERR_INVALID, "AGRS_TUNE_TC_KCHUNK out of range");
+      ctx->tc_kchunk = int(value);
       return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS:
       ctx->tc_min_flops = value;
@@ -42,8 +57,54 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
     use_tc = eligible && M >= 64 && N >= 32 && K >= 32 && (M * N) * K >= ctx->tc_min_flops;
   }
   ctx->last_gemm_path = use_tc ? AGRS_GEMM_TCGEN05 : AGRS_GEMM_SIMT;
-  if (use_tc) return agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
-  return agrs_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
+  agrs_ctx::ProfRec rec{};
+  if (ctx->profiling) {
+    rec.path = ctx->last_gemm_path;
+    rec.flops = 2.0 * double(M) * double(N) * double(K);
+    rec.start = take_event(ctx);
+    rec.stop = take_event(ctx);
+    AGRS_REQUIRE(ctx, rec.start && rec.stop, AGRS_ERR_CUDA, "agrs_gemm_f32: cannot create timing events");
+    AGRS_CUDA(ctx, cudaEventRecord(rec.start, ctx->stream));
+  }
+  int rc = use_tc ? agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
+                  : agrs_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
+  if (ctx->profiling) {
+    AGRS_CUDA(ctx, cudaEventRecord(rec.stop, ctx->stream));
+    ctx->prof.push_back(rec);
+  }
+  return rc;
+}
+
+int agrs_profile_enable(agrs_ctx* ctx, int on) {
+  AGRS_CHECK_CTX(ctx);
+  ctx->profiling = on != 0;
+  return AGRS_OK;
+}
+
+int agrs_profile_gemm(agrs_ctx* ctx, int path, uint64_t* launches, double* total_ms, double* total_flops) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  uint64_t n = 0;
+  double ms = 0.0, fl = 0.0;
+  std::vector<agrs_ctx::ProfRec> keep;
+  for (auto& r : ctx->prof) {
+    if (r.path != path) {
+      keep.push_back(r);
+      continue;
+    }
+    float t = 0.f;
+    AGRS_CUDA(ctx, cudaEventElapsedTime(&t, r.start, r.stop));
+    ms += t;
+    fl += r.flops;
+    ++n;
+    ctx->event_pool.push_back(r.start);
+    ctx->event_pool.push_back(r.stop);
+  }
+  ctx->prof.swap(keep);
+  if (launches) *launches = n;
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  return AGRS_OK;
 }
 
 }  // extern "C"

@@ -111,18 +111,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// Shared-memory matrix descriptor (SM100 UMMA), SWIZZLE_128B, version 1.
-//   K-major  tile: rows of 128 B (32 f32 of K), 8-row swizzle atoms 1024 B apart      -> SBO = 1024, LBO unused (1)
-//   MN-major tile: blocks of [32 K-rows x 128 B (32 f32 of M/N)] = 4096 B per 32 M/N  -> LBO = 4096 (next 32 of M/N),
-//                  SBO = 1024 (next 8 rows of K)
+// Shared-memory matrix descriptor (SM100 UMMA), version 1.
+//   K-major  tile: rows of 128 B (32 f32 of K), SWIZZLE_128B (16-B chunks ^ row%8), 8-row atoms 1024 B apart
+//                  -> layout type 2, SBO = 1024, LBO unused (1)
+//   MN-major tile: 32-bit operands must use SWIZZLE_128B_BASE32B (32-B chunks ^ row%4; TMA swizzle 128B_ATOM_32B):
+//                  blocks of [32 K-rows x 128 B (32 f32 of M/N)] = 4096 B per 32 of M/N -> layout type 1,
+//                  LBO = 4096 (next 32 of M/N), SBO = 512 (next 4 rows of K)
 template <bool MN_MAJOR>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3FFFF) >> 4);                    // start address, bits [0,14)
   d |= uint64_t(MN_MAJOR ? (4096u >> 4) : 1u) << 16;            // leading byte offset, bits [16,30)
-  d |= uint64_t(1024u >> 4) << 32;                              // stride byte offset, bits [32,46)
+  d |= uint64_t(MN_MAJOR ? (512u >> 4) : (1024u >> 4)) << 32;   // stride byte offset, bits [32,46)
   d |= uint64_t(1) << 46;                                       // descriptor version (Blackwell)
-  d |= uint64_t(2) << 61;                                       // layout type: SWIZZLE_128B
+  d |= uint64_t(MN_MAJOR ? 1 : 2) << 61;                        // layout type: SWIZZLE_128B_BASE32B / SWIZZLE_128B
   return d;
 }
 // bytes to advance the descriptor start address per UMMA_K (=8 f32) slice of the 32-wide k-block
@@ -161,8 +163,8 @@ __device__ __forceinline__ void tile_coords(int64_t t, int64_t m_tiles, int64_t 
 
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
-k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* __restrict__ C,
-              int64_t ldc, const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int explicit_hi) {
+k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C,
+              int64_t ldc, const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int explicit_hi, int kb_per_chunk) {
   using cfg = Cfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -179,6 +181,10 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
   const int64_t m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int64_t num_tiles = m_tiles * n_tiles;
   const int num_kb = int((K + BK - 1) / BK);
+  // The tensor core's f32 accumulator truncates on every MMA (bias ~ number of accumulation steps).  K is therefore
+  // cut into chunks: each chunk accumulates in its own TMEM stage and the epilogue warps fold it into C with
+  // round-to-nearest f32 adds (the C tile is re-read from L2).  kb_per_chunk = k-blocks (of 32) per chunk.
+  const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -245,34 +251,38 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);  // epilogue has drained this accumulator stage
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(split_bar(s), ph);  // TMA landed AND lo tiles written
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = smem_base + s * cfg::STAGE_BYTES;
-          const uint32_t a_lo = a_hi + cfg::A_BYTES;
-          const uint32_t b_hi = a_hi + 2 * cfg::A_BYTES;
-          const uint32_t b_lo = b_hi + cfg::B_BYTES;
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        const int kb_end = (ch + 1) * kb_per_chunk < num_kb ? (ch + 1) * kb_per_chunk : num_kb;
+        for (int kb = ch * kb_per_chunk; kb < kb_end; ++kb) {
+          mbar_wait(split_bar(s), ph);  // TMA landed AND lo tiles written
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_base + s * cfg::STAGE_BYTES;
+            const uint32_t a_lo = a_hi + cfg::A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * cfg::A_BYTES;
+            const uint32_t b_lo = b_hi + cfg::B_BYTES;
+            const bool first_kb = (kb == ch * kb_per_chunk);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da_hi = make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>());
-            const uint64_t da_lo = make_smem_desc<A_MN>(a_lo + k * k_slice_bytes<A_MN>());
-            const uint64_t db_hi = make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>());
-            const uint64_t db_lo = make_smem_desc<B_MN>(b_lo + k * k_slice_bytes<B_MN>());
-            umma_tf32(d_tmem, da_lo, db_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
-            umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-            umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da_hi = make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>());
+              const uint64_t da_lo = make_smem_desc<A_MN>(a_lo + k * k_slice_bytes<A_MN>());
+              const uint64_t db_hi = make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>());
+              const uint64_t db_lo = make_smem_desc<B_MN>(b_lo + k * k_slice_bytes<B_MN>());
+              umma_tf32(d_tmem, da_lo, db_hi, idesc, (first_kb && k == 0) ? 0u : 1u);  // small terms first
+              umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+              umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(s));  // fires when the MMAs above have finished reading this stage
+            if (kb == kb_end - 1) umma_commit(tfull_bar(acc));
           }
-          umma_commit(empty_bar(s));  // fires when the MMAs above have finished reading this stage
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
-      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
   } else if (warp >= kSplitWarp0) {
     // ===================== splitters: lo = tf32(x - trunc(x)) =====================
@@ -319,39 +329,52 @@ k_gemm_3xtf32(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
       int64_t mb, nb;
       tile_coords(t, m_tiles, n_tiles, mb, nb);
       const int64_t row = mb * BM + q * 32 + lane;
-      mbar_wait(tfull_bar(acc), acc_ph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_wait_ld();
-        const int64_t col0 = nb * BN + c * 32;
-        if (row < M && col0 < N) {
-          float* dst = C + row * ldc + col0;
-          if (vec_ok && col0 + 32 <= N) {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_wait_ld();
+          const int64_t col0 = nb * BN + c * 32;
+          if (row < M && col0 < N) {
+            float* dst = C + row * ldc + col0;
+            if (vec_ok && col0 + 32 <= N) {
+              float4 base[8];
+              if (ch == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                     __uint_as_float(v[4 * j + 3]));
-              if (bias) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);  // col0 % 32 == 0; bias 16-B aligned (checked on host)
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                for (int j = 0; j < 8; ++j)
+                  base[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) base[j] = *reinterpret_cast<const float4*>(dst + 4 * j);  // previous chunks (L2)
               }
-              *reinterpret_cast<float4*>(dst + 4 * j) = o;
-            }
-          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) dst[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + col0 + j) : 0.f);
+              for (int j = 0; j < 8; ++j) {
+                float4 o;
+                o.x = base[j].x + __uint_as_float(v[4 * j]);
+                o.y = base[j].y + __uint_as_float(v[4 * j + 1]);
+                o.z = base[j].z + __uint_as_float(v[4 * j + 2]);
+                o.w = base[j].w + __uint_as_float(v[4 * j + 3]);
+                *reinterpret_cast<float4*>(dst + 4 * j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) {
+                  float b = ch == 0 ? (bias ? __ldg(bias + col0 + j) : 0.f) : dst[j];
+                  dst[j] = b + __uint_as_float(v[j]);
+                }
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
   }
 
@@ -380,14 +403,15 @@ static int resolve_encode(agrs_ctx* ctx) {
 
 // 2-D f32 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements; 128-byte swizzle
 static int encode_2d(agrs_ctx* ctx, CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
-                     uint32_t box_inner, uint32_t box_outer) {
+                     uint32_t box_inner, uint32_t box_outer, bool mn_major) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * sizeof(float)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
       map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AGRS_REQUIRE(ctx, r == CUDA_SUCCESS, AGRS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu ld=%llu", int(r),
                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
   return AGRS_OK;
@@ -395,17 +419,13 @@ static int encode_2d(agrs_ctx* ctx, CUtensorMap* map, const float* base, uint64_
 
 template <bool A_MN, bool B_MN, int BN, int STAGES>
 static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
-                  int64_t N, int64_t K, int explicit_hi) {
+                  int64_t N, int64_t K, int explicit_hi, int kb_per_chunk) {
   using cfg = Cfg<BN, STAGES>;
   auto kern = k_gemm_3xtf32<A_MN, B_MN, BN, STAGES>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
-    AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg::SMEM_BYTES)));
-    configured = true;
-  }
+  AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg::SMEM_BYTES)));
   int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   int grid = int(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-  kern<<<grid, kThreads, cfg::SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, explicit_hi);
+  kern<<<grid, kThreads, cfg::SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, explicit_hi, kb_per_chunk);
   AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }
@@ -431,16 +451,18 @@ int agrs_gemm_tc(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, in
   const bool B_MN = transB == 0;   // B stored [K, N]: N contiguous
   const int BN = ctx->tc_bn;       // 256 (2 stages) or 128 (3 stages)
   CUtensorMap ta, tb;
-  if (A_MN) rc = tc::encode_2d(ctx, &ta, A, uint64_t(M), uint64_t(K), uint64_t(lda), 32, 32);
-  else      rc = tc::encode_2d(ctx, &ta, A, uint64_t(K), uint64_t(M), uint64_t(lda), 32, tc::BM);
+  if (A_MN) rc = tc::encode_2d(ctx, &ta, A, uint64_t(M), uint64_t(K), uint64_t(lda), 32, 32, true);
+  else      rc = tc::encode_2d(ctx, &ta, A, uint64_t(K), uint64_t(M), uint64_t(lda), 32, tc::BM, false);
   if (rc) return rc;
-  if (B_MN) rc = tc::encode_2d(ctx, &tb, B, uint64_t(N), uint64_t(K), uint64_t(ldb), 32, 32);
-  else      rc = tc::encode_2d(ctx, &tb, B, uint64_t(K), uint64_t(N), uint64_t(ldb), 32, uint32_t(BN));
+  if (B_MN) rc = tc::encode_2d(ctx, &tb, B, uint64_t(N), uint64_t(K), uint64_t(ldb), 32, 32, true);
+  else      rc = tc::encode_2d(ctx, &tb, B, uint64_t(K), uint64_t(N), uint64_t(ldb), 32, uint32_t(BN), false);
   if (rc) return rc;
   const int eh = ctx->tc_explicit_hi;
+  const int64_t num_kb = (K + tc::BK - 1) / tc::BK;
+  const int kpc = ctx->tc_kchunk > 0 ? int((ctx->tc_kchunk + tc::BK - 1) / tc::BK) : int(num_kb);
 #define AGRS_TC(AM, BMJ)                                                                                   \
-  (BN == 256 ? tc::launch<AM, BMJ, 256, 2>(ctx, ta, tb, C, ldc, bias, M, N, K, eh)                          \
-             : tc::launch<AM, BMJ, 128, 3>(ctx, ta, tb, C, ldc, bias, M, N, K, eh))
+  (BN == 256 ? tc::launch<AM, BMJ, 256, 2>(ctx, ta, tb, C, ldc, bias, M, N, K, eh, kpc)                       \
+             : tc::launch<AM, BMJ, 128, 3>(ctx, ta, tb, C, ldc, bias, M, N, K, eh, kpc))
   if (A_MN && B_MN) return AGRS_TC(true, true);
   if (A_MN) return AGRS_TC(true, false);
   if (B_MN) return AGRS_TC(false, true);

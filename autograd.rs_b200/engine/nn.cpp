@@ -1,0 +1,73 @@
+#include "nn.hpp"
+
+#include <cmath>
+
+namespace agrs {
+std::pair<int64_t, int64_t> calculate_fan_in_and_fan_out(const Shape& s);  // tensor.cpp (init.rs:30-45)
+namespace nn {
+
+Tensor Layer::forward_default(std::vector<Tensor> xs) const {
+  Tensor res = xs.at(0).clone();
+  for (const auto& op : get_op_subgraph()) {
+    res = agrs::forward(op, xs);
+    xs = {res.clone()};
+  }
+  return res;
+}
+
+Linear::Linear(Device* d, int64_t in_features, int64_t out_features, bool /*bias: optional bias is a TODO in the reference, layers.rs:79*/) {
+  Shape w_shape{in_features, out_features};
+  float bound = 1.0f / std::sqrt(float(calculate_fan_in_and_fan_out(w_shape).first));  // fan_in = dim 1 = out_features (layers.rs:82-84)
+  w_ = Tensor::kaiming_uniform(d, w_shape);
+  bias_ = Tensor::uniform(d, {1, out_features}, -bound, bound);
+}
+
+Tensor Linear::forward(std::vector<Tensor> xs) const {
+  if (xs.size() != 1) throw Panic("assertion failed: xs.len() == 1");
+  for (auto& p : parameters()) xs.push_back(p);
+  return forward_default(std::move(xs));
+}
+
+Conv2D::Conv2D(Device* d, int64_t in_channels, int64_t out_channels, int64_t k_size, int64_t stride, int64_t pad) {
+  Shape w_shape{k_size, k_size, out_channels};
+  float bound = 1.0f / std::sqrt(float(calculate_fan_in_and_fan_out(w_shape).first));  // layers.rs:155-157
+  kernels_ = Tensor::kaiming_uniform(d, w_shape);
+  bias_ = Tensor::uniform(d, {out_channels}, -bound, bound);
+  op_ = agrs::Conv2D{in_channels, out_channels, k_size, stride, pad};
+}
+
+Tensor Conv2D::forward(std::vector<Tensor> xs) const {
+  if (xs.size() != 1) throw Panic("assertion failed: xs.len() == 1");
+  for (auto& p : parameters()) xs.push_back(p);
+  return forward_default(std::move(xs));
+}
+
+std::vector<Tensor> NN::parameters() const {
+  std::vector<Tensor> ps;
+  for (auto& l : layers())
+    for (auto& p : l->parameters()) ps.push_back(p);
+  return ps;
+}
+
+void zero_grad(const std::vector<Tensor>& params) {
+  for (auto& p : params)
+    if (p.has_grad()) p.zero_grad();
+}
+void NN::zero_grad() const { nn::zero_grad(parameters()); }
+
+void sgd_step(const std::vector<Tensor>& params, float lr) {
+  for (auto& p : params) {
+    if (!p.has_grad()) throw Panic("called `Option::unwrap()` on a `None` value");  // w_grad.as_ref().unwrap(), optim.rs:30
+    Storage& w = *p.data;
+    const Storage& g = *p.grad->g;
+    if (w.transposed || g.transposed) throw Panic("SGD on a transposed parameter view is not supported", AGRS_ERR_UNSUPPORTED);
+    Bcast k = broadcast_kind(w.shape, g.shape);
+    if (k == Bcast::Leading) throw Panic("SGD: gradient " + shape_str(g.shape) + " broadcasts along rows of " + shape_str(w.shape), AGRS_ERR_UNSUPPORTED);
+    // tmp = grad * lr; w -= tmp fused in one pass with the same two roundings
+    w.dev()->check(agrs_sgd_step_f32(w.dev()->ctx(), w.wptr(), g.rptr(), lr, size_t(w.len()), size_t(g.len())));
+  }
+}
+void SGD::step() { sgd_step(parameters_, lr_); }
+
+}  // namespace nn
+}  // namespace agrs

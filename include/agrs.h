@@ -83,9 +83,19 @@ AGRS_API int agrs_last_gemm_path(agrs_ctx* ctx);          /* path the most recen
 enum agrs_tuning_key {
   AGRS_TUNE_TC_BN = 0,          /* tcgen05 tile width: 256 (default) or 128 */
   AGRS_TUNE_TC_EXPLICIT_HI = 1, /* 1: write the tf32-truncated hi tile explicitly instead of relying on the MMA ignoring the low 13 bits */
-  AGRS_TUNE_TC_MIN_MACS = 2     /* AUTO path: minimum M*N*K for the tcgen05 kernel */
+  AGRS_TUNE_TC_MIN_MACS = 2,    /* AUTO path: minimum M*N*K for the tcgen05 kernel */
+  AGRS_TUNE_TC_KCHUNK = 3       /* K elements accumulated in TMEM between round-to-nearest folds into C (0 = all of K; default 1024) */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
+
+/* device-side stopwatch on the context's stream (CUDA events): begin records, end records + synchronises + returns ms */
+AGRS_API int agrs_timer_begin(agrs_ctx* ctx);
+AGRS_API int agrs_timer_end(agrs_ctx* ctx, float* ms);
+/* live kernel timing for bench.py's roofline: while enabled, every agrs_gemm_f32 launch is bracketed by a CUDA-event
+ * pair on the context's stream.  agrs_profile_gemm synchronises, sums the elapsed times and algorithmic flops (2*M*N*K)
+ * of the launches that took `path` since the last call, and resets them. */
+AGRS_API int agrs_profile_enable(agrs_ctx* ctx, int on);
+AGRS_API int agrs_profile_gemm(agrs_ctx* ctx, int path, uint64_t* launches, double* total_ms, double* total_flops);
 
 /* ---- activations / loss ---- */
 AGRS_API int agrs_relu_fwd_f32(agrs_ctx* ctx, const float* x, float* y, size_t n);                   /* operators.rs:115 -> functional_ndarray.rs:14-22 */
@@ -134,6 +144,21 @@ AGRS_API int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t
                     int64_t k, int64_t stride, float* im_out);
 /* out[c*kk + r, o] = filt[r, o] for every c: the [k,k,Co] -> [Ci,k,k,Co] broadcast (storage.rs:114-120) */
 AGRS_API int agrs_broadcast_filter_f32(agrs_ctx* ctx, const float* filt, int64_t kk, int64_t c_out, int64_t c_in, float* out);
+
+/* ---- data-parallel gradient exchange (new: the reference has no multi-device concept) ----
+ * One process per GPU; NCCL (over NVLink 5 / NVSwitch) is loaded at run time (libnccl.so.2), never linked.
+ * Collectives run on a communication stream owned by the comm: each call is ordered after everything
+ * enqueued so far on the context's stream, and agrs_comm_join makes the context's stream wait for all
+ * collectives enqueued so far -- so an all-reduce of layer l's gradient overlaps the backward of layer l-1. */
+typedef struct agrs_comm agrs_comm;
+#define AGRS_COMM_ID_BYTES 128
+AGRS_API int agrs_comm_unique_id(void* out_id128);  /* rank 0 makes it, the launcher broadcasts it (ncclGetUniqueId) */
+AGRS_API int agrs_comm_create(agrs_ctx* ctx, int world, int rank, const void* id128, agrs_comm** out);
+AGRS_API int agrs_comm_destroy(agrs_comm* comm);
+AGRS_API int agrs_comm_info(agrs_comm* comm, int* world, int* rank);
+/* in place; average=0: sum over ranks, average=1: mean over ranks (ncclAvg: the sum divided by the world size) */
+AGRS_API int agrs_comm_allreduce_f32(agrs_comm* comm, float* buf, size_t n, int average);
+AGRS_API int agrs_comm_join(agrs_comm* comm);
 
 AGRS_API const char* agrs_version(void);
 

@@ -23,6 +23,27 @@ def test_binding_covers_header():
         assert getattr(L, n).restype is not None
 
 
+def test_engine_exports_every_declared_symbol():
+    from autograd_rs_b200 import frontend
+    names = frontend.declared_symbols()
+    assert len(names) >= 50
+    L = frontend.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    for n in names:
+        assert getattr(L, n).argtypes is not None or n == "agrs_eng_last_error", f"{n} is not bound in frontend.py"
+
+
+def test_engine_fails_loudly_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from autograd_rs_b200 import frontend
+    with pytest.raises(frontend.Panic) as e:
+        frontend.Device(0)
+    assert e.value.code == 5 and "no CPU fallback" in str(e.value)
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():

@@ -1,0 +1,88 @@
+"""CPU (gloo, world_size 2) tests of the data-parallel host logic: row sharding, the unique-id exchange the launcher
+does, and the numerics claim the design rests on -- the mean over ranks of the LITERAL local gradients
+(MSE backward divides by the local batch, operators.rs:247) equals the literal gradient of the global batch, so
+replicas that average their gradients track the single-device oracle step for step."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import autograd_rs_b200  # noqa: F401
+from autograd_rs_b200 import frontend as F
+from autograd_rs_b200 import workloads as W
+from oracle import oracle_np as O
+
+
+def test_shard_rows_partition():
+    for rows in (0, 1, 7, 8, 8192, 65536 + 3):
+        for world in (1, 2, 3, 8):
+            spans = [F.shard_rows(rows, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == rows
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_rank_step(layers, x, t, act):
+    X, T = O.OTensor(x), O.OTensor(t, requires_grad=False)
+    h = X.clone()
+    for i, l in enumerate(layers):
+        h = l.forward(h)
+        if i + 1 < len(layers):
+            h = act().forward([h])
+    loss = O.OpMSE().forward([h, T.clone()])
+    loss.backward()
+    return float(loss.data[0, 0])
+
+
+def _worker(rank, world, port, steps, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the launcher's id exchange (bench.py): rank 0 makes a 128-byte id, everyone receives the same bytes
+    ids = [bytes(range(128)) if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    assert ids[0] == bytes(range(128))
+    ws, bs = W.mlp_init(3, 64, seed=5)
+    x, t = W.mlp_batch(96, 64, 64, seed=6)             # the GLOBAL batch, identical on both ranks
+    b, e = F.shard_rows(96, world, rank)
+    layers = [O.OLinearLayer(w.copy(), bb.copy()) for w, bb in zip(ws, bs)]
+    params = [p for l in layers for p in l.parameters()]
+    losses = []
+    for _ in range(steps):
+        loss = _oracle_rank_step(layers, x[b:e], t[b:e], O.OpReLU)
+        lt = torch.tensor([loss], dtype=torch.float64)
+        dist.all_reduce(lt)
+        losses.append(float(lt.item()) / world)        # mean of the shard means (DataParallel.mean_scalar)
+        for p in params:                               # DataParallel.sync_grads: mean over ranks, in place
+            g = torch.from_numpy(p.cell["grad"])
+            dist.all_reduce(g)
+            g /= world
+        O.sgd(params, 1e-3)
+        O.model_zero_grad(params)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), losses=np.array(losses), **{f"p{i}": p.data for i, p in enumerate(params)})
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_tracks_single_device(tmp_path):
+    world, steps = 2, 4
+    mp.spawn(_worker, args=(world, _free_port(), steps, str(tmp_path)), nprocs=world, join=True)
+    ws, bs = W.mlp_init(3, 64, seed=5)
+    x, t = W.mlp_batch(96, 64, 64, seed=6)
+    want, layers = O.mlp_train(x, t, ws, bs, "relu", 1e-3, steps, np.float32)
+    r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in range(world))
+    assert np.allclose(r0["losses"], want, rtol=1e-5)
+    for i, p in enumerate([q for l in layers for q in l.parameters()]):
+        assert np.array_equal(r0[f"p{i}"], r1[f"p{i}"])            # replicas stay bit-identical
+        assert O.rel_err(r0[f"p{i}"], p.data) < 1e-5               # and track the single-device run

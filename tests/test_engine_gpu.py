@@ -1,0 +1,435 @@
+"""GPU parity tests of the host engine (libagrs_engine.so over libagrs_b200.so) against the oracle.
+
+The first half are the reference's own 17 unit tests, ported line by line to the front end (file:line in each
+docstring); small-integer data, so they are exact.  The second half compares whole training loops with the
+oracle on seeded inputs; tolerance: max relative error <= 1e-4 per tensor (BASELINE north star), in practice ~1e-6.
+Run with: pytest -m gpu (under gpurun)."""
+import numpy as np
+import pytest
+
+import autograd_rs_b200  # noqa: F401
+from autograd_rs_b200 import frontend as F
+from autograd_rs_b200 import workloads as W
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # BASELINE.json north star: max relative error on outputs and gradients
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = F.Device(0)
+    yield d
+    d.close()
+
+
+def T(dev, a):
+    return F.Tensor.from_numpy(dev, np.array(a, dtype=np.float32))
+
+
+# ====================================================================== the reference's unit tests
+def test_relu_on_mat(dev, kats):
+    """operators.rs:486-506"""
+    k = kats["relu_on_mat"]
+    x = T(dev, k["x"])
+    res = F.ReLU().forward([x])
+    assert res.requires_grad
+    assert np.array_equal(res.data(), np.array(k["y"], np.float32))
+
+
+def test_linear(dev, kats):
+    """operators.rs:508-521"""
+    k = kats["linear"]
+    res = F.Linear().forward([T(dev, k["x"]), T(dev, k["w"]), T(dev, k["b"])])
+    assert np.array_equal(res.data(), np.array(k["y"], np.float32))
+
+
+@pytest.mark.parametrize("name", ["im2col_nopad", "im2col_pad"])
+def test_im2col(dev, kats, name):
+    """operators.rs:523-566"""
+    k = kats[name]
+    im = T(dev, np.arange(*k["im_range"], dtype=np.float32).reshape(k["im_shape"]))
+    col = F.Conv2D.im2col(im, k["k"], k["stride"], k["pad"])
+    assert col.shape() == k["col_shape"]
+    assert np.array_equal(col.data(), np.array(k["col"], np.float32).reshape(k["col_shape"]))
+
+
+def test_im2col_rejects_non_bchw(dev):
+    """functional_ndarray.rs:100-103: Err("Expected image of shape BCHW...")"""
+    with pytest.raises(F.Panic, match="BCHW"):
+        F.Conv2D.im2col(T(dev, np.zeros((3, 4, 4))), 2, 1, 0)
+
+
+def test_conv2d(dev, kats):
+    """operators.rs:568-602: forward all 9.0 (NHWC), backward gradient shapes equal input shapes"""
+    k = kats["conv2d_ones"]
+    conv = F.Conv2D(k["c_in"], k["c_out"], k["k"], k["stride"], k["pad"])
+    xs = [F.Tensor.ones(dev, k["im_shape"]), F.Tensor.ones(dev, k["filt_shape"]), F.Tensor.ones(dev, k["bias_shape"])]
+    res = conv.forward(xs)
+    assert res.shape() == k["out_shape"]
+    assert np.all(res.data() == k["out_value"])
+    # the test calls backward with the op inputs + the cached col, which lives in the graph node
+    col = F.Conv2D.im2col(xs[0], k["k"], k["stride"], k["pad"])
+    col.reshape([col.shape()[0] * col.shape()[1], col.shape()[2]])
+    grads = conv.backward(xs + [col], F.Tensor.ones(dev, k["out_shape"]))
+    assert [g.shape() for g in grads] == k["bwd_shapes"]
+
+
+def test_single_node_graph(dev, kats):
+    """autograd.rs:94-119"""
+    k = kats["single_node_graph"]
+    x = T(dev, k["x"])
+    res = F.ReLU().forward([x.clone()])
+    assert np.array_equal(res.data(), np.array(k["y"], np.float32))
+    name, nvars, nparents = res.graph_info()
+    assert name == "ReLU" and nvars == 1 and nparents == 0
+    res.backward()
+    assert np.array_equal(x.grad().data(), np.array(k["x_grad"], np.float32))
+
+
+def test_simple_graph(dev, kats):
+    """autograd.rs:121-171: ReLU -> Linear; x.grad, W.grad, b.grad (1-D)"""
+    k = kats["simple_graph"]
+    x = T(dev, k["x"])
+    res = F.ReLU().forward([x.clone()])
+    w, b = T(dev, k["w"]), T(dev, k["b"])
+    res = F.Linear().forward([res, w.clone(), b.clone()])
+    assert np.array_equal(res.data(), np.array(k["y"], np.float32))
+    assert res.graph_info() == ("Linear", 3, 1)
+    res.backward()
+    assert np.array_equal(x.grad().data(), np.array(k["x_grad"], np.float32))
+    assert np.array_equal(w.grad().data(), np.array(k["w_grad"], np.float32))
+    assert b.grad().shape() == [2] and np.array_equal(b.grad().data(), np.array(k["b_grad"], np.float32))
+
+
+def test_basic_from(dev, kats):
+    """tensor.rs:464-472"""
+    k = kats["basic_from"]
+    t = T(dev, np.zeros(k["shape"]))
+    assert t.ndim() == k["ndim"] and t.len() == k["len"] and t.shape() == k["shape"] and not t.is_empty()
+
+
+def test_clone_tensor(dev):
+    """tensor.rs:474-492: a clone points at the same storage"""
+    a = F.Tensor.zeros(dev, (2, 2))
+    b = a.clone()
+    assert a.data_ptr() == b.data_ptr()
+    b.fill(3.0)
+    assert np.all(a.data() == 3.0)
+
+
+def test_reshape(dev, kats):
+    """tensor.rs:493-502: reshape through a clone is seen by the original"""
+    k = kats["reshape_alias"]
+    a = F.Tensor.zeros(dev, k["from"])
+    b = a.clone()
+    b.reshape(k["to"])
+    assert a.shape() == k["to"]
+    with pytest.raises(F.Panic):
+        a.reshape([5])
+
+
+def test_adds(dev, kats):
+    """tensor_arithmetic.rs:348-365"""
+    k = kats["arith_adds"]
+    a, b = T(dev, k["a"]), T(dev, k["b"])
+    a_ptr = a.data_ptr()
+    a = a.add_(b)  # a + &b: in place
+    assert np.array_equal(a.data(), np.array(k["a_plus_b"], np.float32)) and a.data_ptr() == a_ptr
+    c = a.clone()
+    c.fill(1.0)
+    assert np.all(a.data() == 1.0)  # visible through the alias
+    d = a + b  # &a + &b: new storage
+    assert d.data_ptr() != a.data_ptr() and np.all(d.data() == 2.0) and np.all(a.data() == 1.0)
+    assert d.grad() is None
+
+
+def test_subs(dev):
+    """tensor_arithmetic.rs:366-383"""
+    a, b = T(dev, [[1, 2], [3, 4]]), F.Tensor.ones(dev, (2, 2))
+    ptr = a.data_ptr()
+    a.sub_(b)
+    assert np.array_equal(a.data(), np.array([[0, 1], [2, 3]], np.float32)) and a.data_ptr() == ptr
+    d = a - b
+    assert d.data_ptr() != ptr and np.array_equal(d.data(), np.array([[-1, 0], [1, 2]], np.float32))
+    a -= b
+    assert np.array_equal(a.data(), d.data()) and a.data_ptr() == ptr
+
+
+def test_scalar_ops(dev, kats):
+    """tensor_arithmetic.rs:385-399"""
+    k = kats["arith_scalar"]
+    a = T(dev, k["a"])
+    assert np.array_equal((a * 2).data(), np.array(k["mul2"], np.float32))
+    assert np.array_equal((a / 2).data(), np.array(k["div2"], np.float32))
+    assert np.array_equal((3.0 - a).data(), np.array(k["three_minus_a"], np.float32))
+    a *= 3
+    assert np.array_equal(a.data(), np.array(k["mul_assign3"], np.float32))
+
+
+def test_mul(dev):
+    """tensor_arithmetic.rs:401-437: &a * &b is new storage; a * &b keeps a's storage address"""
+    a, b = T(dev, [[1, 2], [3, 4]]), T(dev, [[2, 2], [2, 2]])
+    c = a * b
+    assert c.data_ptr() != a.data_ptr() and np.array_equal(c.data(), np.array([[2, 4], [6, 8]], np.float32))
+    ptr = a.data_ptr()
+    a = a.mul_(b)
+    assert a.data_ptr() == ptr and np.array_equal(a.data(), c.data())
+    assert a.equals(c) and not a.equals(b)
+    assert np.array_equal((-a).data(), -c.data())  # Neg is todo!() in the reference (Q4): implemented
+
+
+def test_layers_mlp(dev):
+    """layers.rs:194-206: Linear(20,10) -> ReLU -> Linear(10,1); backward; x.grad != None"""
+    dev.seed(7)
+    x = F.Tensor.ones(dev, (1, 20))
+    l1, act, l2 = F.nn.Linear(dev, 20, 10), F.nn.ReLU(), F.nn.Linear(dev, 10, 1)
+    res = l2.forward([act.forward([l1.forward([x.clone()])])])
+    res.backward()
+    assert x.grad() is not None and x.grad().shape() == [1, 20]
+
+
+def test_layers_conv(dev):
+    """layers.rs:207-217: Conv2D(3,16,3) on 1x3x24x24 -> ReLU -> backward; x.grad != None (B=1, C_in=3)"""
+    dev.seed(8)
+    x = F.Tensor.ones(dev, (1, 3, 24, 24))
+    conv, act = F.nn.Conv2D(dev, 3, 16, 3), F.nn.ReLU()
+    res = act.forward([conv.forward([x.clone()])])
+    assert res.shape() == [1, 22, 22, 16]
+    res.backward()
+    assert x.grad() is not None and x.grad().shape() == [1, 3, 24, 24]
+
+
+def test_model_mlp_shapes(dev, kats):
+    """model.rs:31-62"""
+    k = kats["mlp_param_shapes"]
+    dev.seed(9)
+    model = F.nn.Sequential([F.nn.Linear(dev, 20, 10), F.nn.ReLU(), F.nn.Linear(dev, 10, 1)])
+    assert [p.shape() for p in model.parameters()] == k["shapes"]
+    out = model.forward([F.Tensor.ones(dev, (1, 20))])
+    assert out.shape() == k["out_shape"]
+    # init bounds (init.rs:19-49; layers.rs:82-89)
+    w = model.parameters()[0].data()
+    assert np.abs(w).max() <= W.kaiming_bound((20, 10)) and np.abs(w).max() > 0.5 * W.kaiming_bound((20, 10))
+    assert np.abs(model.parameters()[1].data()).max() <= 1 / np.sqrt(10)
+
+
+# ====================================================================== semantics the reference leaves unpinned
+def test_backward_needs_graph(dev):
+    """tensor.rs:337: expect("Variable has no attached graph")"""
+    with pytest.raises(F.Panic, match="no attached graph"):
+        F.Tensor.ones(dev, (2, 2)).backward()
+
+
+def test_dot_panics(dev):
+    """tensor.rs:303-305"""
+    with pytest.raises(F.Panic, match="1d/2d matmul"):
+        F.Tensor.ones(dev, (2, 2, 2)).dot(F.Tensor.ones(dev, (2, 2)))
+    with pytest.raises(F.Panic, match="not compatible"):
+        F.Tensor.ones(dev, (2, 3)).dot(F.Tensor.ones(dev, (2, 3)))
+
+
+def test_transpose_views_feed_gemm(dev):
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal((5, 7)).astype(np.float32), rng.standard_normal((5, 3)).astype(np.float32)
+    ta = T(dev, a)
+    ta.t()  # in place on the shared storage (tensor.rs:165-169)
+    assert ta.shape() == [7, 5] and not ta.is_contiguous()
+    assert O.rel_err(ta.dot(T(dev, b)).data(), a.T @ b) < 1e-6
+    assert np.array_equal(ta.data(), a.T)
+    tc = T(dev, b).t_clone()
+    assert tc.shape() == [3, 5] and np.array_equal(tc.data(), b.T)
+
+
+def test_accumulate_twice_and_zero_grad(dev):
+    """tensor.rs:154-163 (`+=` is todo!() at HEAD, defect D2) and model.rs:14-21"""
+    x = T(dev, [[1, -2], [3, 4]])
+    for _ in range(2):
+        F.ReLU().forward([x.clone()]).backward()
+    assert np.array_equal(x.grad().data(), np.array([[2, 0], [2, 2]], np.float32))
+    x.zero_grad()
+    assert np.all(x.grad().data() == 0)
+    # SGD broadcasts a [O] gradient onto a [1,O] bias and zero_grad then makes the grad [1,O]
+    w, b = T(dev, np.ones((2, 3))), T(dev, np.ones((1, 3)))
+    F.Linear().forward([T(dev, [[1, 2]]), w.clone(), b.clone()]).backward()
+    assert b.grad().shape() == [3]
+    F.nn.SGD([w, b], 0.5).step()
+    assert np.array_equal(b.data(), np.full((1, 3), 0.5, np.float32))
+    assert np.array_equal(w.data(), np.array([[0.5] * 3, [0.0] * 3], np.float32))
+    model = F.nn.Sequential([F.nn.Linear(dev, 2, 3, w=w, bias=b)])
+    model.zero_grad()
+    assert b.grad().shape() == [1, 3] and np.all(b.grad().data() == 0)
+    with pytest.raises(F.Panic, match="None"):
+        F.nn.SGD([T(dev, [[1.0]])], 0.1).step()  # optim.rs:30 unwrap on a None grad
+
+
+def test_matmul_backward_literal_and_fixed(dev):
+    """operators.rs:183-184 (defect D3): literal dx = g.w, dw = g^T.x; the fixed flavour behind a switch"""
+    rng = np.random.default_rng(3)
+    x, w, g = (rng.standard_normal((6, 6)).astype(np.float32) for _ in range(3))
+    for literal in (True, False):
+        dev.set_matmul_backward_literal(literal)
+        dx, dw = F.MatMul().backward([T(dev, x), T(dev, w)], T(dev, g))
+        wdx, wdw = O.matmul_bwd(x, w, g, literal=literal)
+        assert O.rel_err(dx.data(), wdx) < 1e-6 and O.rel_err(dw.data(), wdw) < 1e-6
+    dev.set_matmul_backward_literal(True)
+
+
+@pytest.mark.parametrize("op,ofwd,obwd", [("sigmoid", O.sigmoid_fwd, O.sigmoid_bwd), ("relu", O.relu_fwd, O.relu_bwd)])
+def test_activation_ops(dev, op, ofwd, obwd):
+    rng = np.random.default_rng(4)
+    x, g = rng.standard_normal((33, 17)).astype(np.float32) * 3, rng.standard_normal((33, 17)).astype(np.float32)
+    o = {"sigmoid": F.Sigmoid, "relu": F.ReLU}[op]()
+    assert O.rel_err(o.forward([T(dev, x)]).data(), ofwd(x)) < 1e-6
+    assert O.rel_err(o.backward([T(dev, x)], T(dev, g))[0].data(), obwd(x, g)) < 1e-6
+
+
+def test_mse_and_mean_ops(dev):
+    rng = np.random.default_rng(5)
+    p, t = rng.standard_normal((64, 10)).astype(np.float32), rng.standard_normal((64, 10)).astype(np.float32)
+    loss = F.MeanSquaredError().forward([T(dev, p), T(dev, t)])
+    assert loss.shape() == [1, 1] and abs(loss.item() - O.mse_fwd(p, t)[0, 0]) < 1e-6 * abs(loss.item())
+    g = F.MeanSquaredError().backward([T(dev, p), T(dev, t)], F.Tensor.ones(dev, (1, 1)))
+    assert len(g) == 1  # the target gets no gradient (autograd.rs:73 zips to the shorter list)
+    assert O.rel_err(g[0].data(), O.mse_bwd(p, t, np.ones((1, 1), np.float32))) < 1e-6  # literal 2/B scaling (D4)
+    m = F.Mean().forward([T(dev, p)])
+    assert m.shape() == [1] and abs(m.item() - p.mean()) < 1e-6
+    gm = F.Mean().backward([T(dev, p)], F.Tensor.ones(dev, (1,)))
+    assert O.rel_err(gm[0].data(), O.mean_bwd(p, np.ones(1, np.float32))) < 1e-6
+
+
+# ====================================================================== whole training loops vs the oracle
+def run_device_mlp(dev, x, t, ws, bs, act, lr, steps):
+    model = W.build_mlp(dev, ws, bs, act)
+    tr = W.Trainer(model, lr)
+    X, Tt = T(dev, x), T(dev, t)
+    Tt.requires_grad = False
+    losses = [tr.step(X, Tt).item() for _ in range(steps)]
+    return losses, [p.data() for p in model.parameters()], X
+
+
+def test_fit_sine_tracks_oracle_step_for_step(dev):
+    """C1, examples/fit_sine.rs:17-102 (2000 samples, Linear(3,1), lr 1e-3); W=b=0 init as SURVEY Appendix E"""
+    x, y = O.fit_sine_data(2000, np.float32)
+    steps = 300
+    want, layers = O.mlp_train(x, y, [np.zeros((3, 1))], [np.zeros((1, 1))], None, 1e-3, steps, np.float32)
+    got, params, _ = run_device_mlp(dev, x, y, [np.zeros((3, 1), np.float32)], [np.zeros((1, 1), np.float32)], None, 1e-3, steps)
+    assert max(abs(a - b) / abs(b) for a, b in zip(got, want)) < TOL
+    assert abs(got[0] - 0.49974999) < 1e-6 and abs(got[1] - 0.44477817) < 1e-6 and abs(got[99] - 0.31669122) < 2e-6
+    assert O.rel_err(params[0], layers[0].w.data) < TOL and O.rel_err(params[1], layers[0].b.data) < TOL
+
+
+@pytest.mark.parametrize("act,width,rows,layers", [("relu", 256, 512, 3), ("sigmoid", 128, 300, 4), ("relu", 520, 1000, 2)])
+def test_mlp_training_tracks_oracle(dev, act, width, rows, layers):
+    """C2/C5 in miniature: every loss value and every final weight within 1e-4 of the oracle, f32 vs f32;
+    the device is also no further from the f64 restatement than the f32 oracle is (x4)."""
+    ws, bs = W.mlp_init(layers, width, seed=11)
+    x, t = W.mlp_batch(rows, width, width, seed=12)
+    lr, steps = 1e-4, 5
+    want, olayers = O.mlp_train(x, t, ws, bs, act, lr, steps, np.float32)
+    want64, olayers64 = O.mlp_train(x, t, ws, bs, act, lr, steps, np.float64)
+    got, params, X = run_device_mlp(dev, x, t, ws, bs, act, lr, steps)
+    assert max(abs(a - b) / abs(b) for a, b in zip(got, want)) < TOL
+    oparams = [p.data for l in olayers for p in l.parameters()]
+    oparams64 = [p.data for l in olayers64 for p in l.parameters()]
+    for g, w32, w64 in zip(params, oparams, oparams64):
+        assert O.rel_err(g, w32) < TOL
+        assert O.rel_err(g, w64) < 4 * O.rel_err(w32, w64) + 1e-6
+    # x.grad keeps accumulating over the 5 iterations (the input handle is reused and never zeroed, fit_sine.rs:65)
+    assert X.grad() is not None and X.grad().shape() == list(x.shape)
+
+
+def test_gradients_match_oracle_one_step(dev):
+    """outputs AND gradients of one forward/backward (north star tolerance), tcgen05 GEMM shapes"""
+    ws, bs = W.mlp_init(2, 384, seed=21)
+    x, t = W.mlp_batch(640, 384, 384, seed=22)
+    model = W.build_mlp(dev, ws, bs, "relu")
+    X, Tt = T(dev, x), T(dev, t)
+    Tt.requires_grad = False
+    pred = model.forward([X.clone()])
+    loss = F.nn.MeanSquaredError().forward([pred, Tt.clone()])
+    loss.backward()
+    ol = [O.OLinearLayer(w, b) for w, b in zip(ws, bs)]
+    OX, OT = O.OTensor(x), O.OTensor(t, requires_grad=False)
+    h = O.OpReLU().forward([ol[0].forward(OX.clone())])
+    opred = ol[1].forward(h)
+    oloss = O.OpMSE().forward([opred, OT.clone()])
+    oloss.backward()
+    assert O.rel_err(pred.data(), opred.data) < TOL
+    assert O.rel_err(X.grad().data(), OX.grad) < TOL
+    for p, op in zip(model.parameters(), [q for l in ol for q in l.parameters()]):
+        assert p.grad().shape() == list(op.grad.shape)
+        assert O.rel_err(p.grad().data(), op.grad) < TOL
+
+
+def test_lenet_training_tracks_oracle(dev):
+    """C3 in miniature (B=32): Conv2D(1,6,5) -> ReLU -> Flatten -> Linear(3456,10) -> MSE; conv backward at B>1
+    is the per-sample generalisation of the literal code (defect D1)."""
+    rng = np.random.default_rng(31)
+    B = 32
+    im = rng.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32)
+    t = rng.uniform(0, 1, (B, 10)).astype(np.float32)
+    fb = W.kaiming_bound((5, 5, 6))
+    filt = rng.uniform(-fb, fb, (5, 5, 6)).astype(np.float32)
+    cbias = rng.uniform(-0.1, 0.1, (6,)).astype(np.float32)
+    w = rng.uniform(-0.05, 0.05, (3456, 10)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (1, 10)).astype(np.float32)
+    lr, steps = 1e-3, 4
+    model = W.build_lenet(dev, filt, cbias, w, b)
+    tr = W.Trainer(model, lr)
+    X, Tt = T(dev, im), T(dev, t)
+    Tt.requires_grad = False
+    got = [tr.step(X, Tt).item() for _ in range(steps)]
+    # oracle loop
+    conv, lin = O.OConvLayer(filt.copy(), cbias.copy(), 1), O.OLinearLayer(w.copy(), b.copy())
+    params = conv.parameters() + lin.parameters()
+    OX, OT = O.OTensor(im), O.OTensor(t, requires_grad=False)
+    want = []
+    for _ in range(steps):
+        h = O.OpReLU().forward([conv.forward(OX.clone())])
+        h = O.OpFlatten().forward([h])
+        loss = O.OpMSE().forward([lin.forward(h), OT.clone()])
+        want.append(float(loss.data[0, 0]))
+        loss.backward()
+        O.sgd(params, lr)
+        O.model_zero_grad(params)
+    assert max(abs(a - c) / abs(c) for a, c in zip(got, want)) < TOL
+    for p, op in zip(model.parameters(), params):
+        assert O.rel_err(p.data(), op.data) < TOL
+    assert O.rel_err(X.grad().data(), OX.grad) < TOL
+
+
+def test_no_host_sync_inside_a_step(dev):
+    """forward .. zero_grad enqueue only: the step returns while the device is still busy (no host round trip)."""
+    import time
+    ws, bs = W.mlp_init(3, 2048, seed=41)
+    x, t = W.mlp_batch(4096, 2048, 2048, seed=42)
+    model = W.build_mlp(dev, ws, bs, "relu")
+    tr = W.Trainer(model, 1e-6)
+    X, Tt = T(dev, x), T(dev, t)
+    Tt.requires_grad = False
+    tr.step(X, Tt)
+    dev.sync()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        tr.step(X, Tt)
+    t_enqueue = time.perf_counter() - t0
+    dev.sync()
+    t_total = time.perf_counter() - t0
+    assert t_enqueue < 0.5 * t_total, (t_enqueue, t_total)
+
+
+def test_data_parallel_world1_is_identity(dev):
+    """DataParallel with one rank: registration + sync are no-ops on the numbers (the N>1 path runs under torchrun)."""
+    ws, bs = W.mlp_init(2, 128, seed=51)
+    x, t = W.mlp_batch(256, 128, 128, seed=52)
+    want, _, _ = run_device_mlp(dev, x, t, ws, bs, "relu", 1e-4, 3)
+    model = W.build_mlp(dev, ws, bs, "relu")
+    dp = F.DataParallel(dev, 1, 0, F.comm_unique_id(), model.parameters(), overlap=True)
+    tr = W.Trainer(model, 1e-4, dp=dp)
+    X, Tt = T(dev, x), T(dev, t)
+    Tt.requires_grad = False
+    got = [tr.step(X, Tt).item() for _ in range(3)]
+    dp.close()
+    assert got == want
