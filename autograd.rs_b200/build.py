@@ -43,7 +43,7 @@ def _run(cmd, verbose):
 
 def build_kernels(force=False, verbose=False, extra=()):
     srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")] + [os.path.join(INC, "agrs.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [os.path.join(INC, "agrs.h")]
     if not force and not _newer(LIB_KERNELS, deps):
         return LIB_KERNELS
     objdir = os.path.join(HERE, "build")

@@ -23,6 +23,7 @@ struct agrs_ctx {
   int last_gemm_path = 0;
   int tc_bn = 256;         // tcgen05 tile width: 256 (2 smem stages) or 128 (3 stages)
   int tc_kchunk = 1024;    // K elements accumulated inside the tensor core before an RN fold into C (0: whole K)
+  int tc_2cta = 1;         // use the cta_group::2 pair kernel when the problem has more than one 128-row block
   int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
   int64_t tc_min_flops = 1LL << 24;  // AUTO path: below this many MACs the SIMT kernel wins on launch+fill latency
   // small scratch for reductions (block partials + completion counter), allocated once
@@ -81,5 +82,8 @@ bool agrs_gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t
                            const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
 int agrs_gemm_tc(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
                  int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
+
+int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+                      int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
 
 static inline bool agrs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

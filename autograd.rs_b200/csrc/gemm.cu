@@ -28,6 +28,9 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
       AGRS_REQUIRE(ctx, value >= 0 && value < (1LL << 30), AGRS_ERR_INVALID, "AGRS_TUNE_TC_KCHUNK out of range");
       ctx->tc_kchunk = int(value);
       return AGRS_OK;
+    case AGRS_TUNE_TC_2CTA:
+      ctx->tc_2cta = value ? 1 : 0;
+      return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS:
       ctx->tc_min_flops = value;
       return AGRS_OK;
@@ -66,7 +69,9 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
     AGRS_REQUIRE(ctx, rec.start && rec.stop, AGRS_ERR_CUDA, "agrs_gemm_f32: cannot create timing events");
     AGRS_CUDA(ctx, cudaEventRecord(rec.start, ctx->stream));
   }
-  int rc = use_tc ? agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
+  const bool pair = use_tc && ctx->tc_2cta && M > 128;
+  int rc = pair   ? agrs_gemm_tc_2cta(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
+         : use_tc ? agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
                   : agrs_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
   if (ctx->profiling) {
     AGRS_CUDA(ctx, cudaEventRecord(rec.stop, ctx->stream));

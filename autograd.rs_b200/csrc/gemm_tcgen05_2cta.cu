@@ -1,0 +1,349 @@
+// f32-faithful 3xTF32 GEMM, CTA-pair version: tcgen05.mma.cta_group::2 on a 256 x 256 pair tile.
+//
+// Same contract as gemm_tcgen05.cu (Tensor::dot's CUDA arm, reference src/tensor/tensor.rs:319; the three GEMMs of
+// Linear::forward/backward, operators.rs:144,159,160) and the same numerics (hi = raw f32 container read by the tensor
+// core as tf32, lo = x - hi; a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulated in TMEM; K cut into chunks that the
+// epilogue folds into C with round-to-nearest adds).  What changes is the data flow, because the one-CTA kernel is
+// bound by shared-memory bandwidth and by its two-deep pipeline (profiles/r1_gemm_v1_ncu_full_summary.txt: tensor pipe
+// 47 % active):
+//   * a cluster of two CTAs (two SMs of one TPC) owns a 256 x 256 tile; each CTA stages 128 rows of A and 128 columns
+//     of B per 32-wide k-block, so every operand byte in shared memory feeds twice the math;
+//   * raw tiles (TMA) and lo tiles (splitter warps) live in separate rings: 4 raw stages cover the TMA latency, 3 lo
+//     stages cover the split, 224 KB of shared memory per CTA in total;
+//   * 8 splitter warps per CTA (two per scheduler) instead of 4.
+// Per CTA, 16 warps: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator,
+// warps 4-7 epilogue, warps 8-15 splitters.  Cross-CTA signalling: splitters and epilogue warps of both CTAs arrive on
+// the LEADER's mbarriers (release.cluster); the leader's tcgen05.commit multicasts to the same barrier in both CTAs.
+#include "tc_common.cuh"
+
+namespace tc2 {
+using namespace tc;
+
+constexpr int kThreads = 512;
+constexpr int kEpiWarp0 = 4;
+constexpr int kSplitWarp0 = 8;
+constexpr int kSplitWarps = 8;
+constexpr int BN = 256;   // pair-tile width
+constexpr int BNH = 128;  // columns of B staged per CTA
+constexpr int R = 4;      // raw (TMA) stages
+constexpr int L = 3;      // lo (splitter) stages
+constexpr uint32_t A_BYTES = BM * BK * 4;    // 16 KB
+constexpr uint32_t B_BYTES = BNH * BK * 4;   // 16 KB
+constexpr uint32_t RAW_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t SMEM_BYTES = (R + L) * RAW_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of 256 columns
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a LOCAL barrier whose arrivals come from both CTAs of the cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (spins > (1u << 24)) mbar_timeout(bar, parity);
+  }
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(uint16_t(3))
+               : "memory");
+}
+
+__device__ __forceinline__ float lo_of(float x) {
+  const uint32_t u = __float_as_uint(x);
+  const float hi = __uint_as_float(u & 0xFFFFE000u);  // what the tensor core reads from the raw container
+  float lo = x - hi;                                  // exact; the tensor core truncates it to tf32 (2^-21 relative to x)
+  return (lo == lo) ? lo : 0.f;                       // inf - inf: keep inf/NaN in the hi term only
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C, int64_t ldc,
+                   const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t lo_base = smem_base + R * RAW_BYTES;
+  const uint32_t bar_base = lo_base + L * RAW_BYTES;
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };
+  auto raw_free = [&](int s) { return bar_base + 8u * (R + s); };
+  auto lo_free = [&](int s) { return bar_base + 8u * (2 * R + s); };
+  auto split_done = [&](int s) { return bar_base + 8u * (2 * R + L + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * R + 2 * L + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
+  const int64_t num_tiles = m_tiles * n_tiles;
+  const int num_kb = int((K + BK - 1) / BK);
+  const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < R; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(raw_free(s), 1);
+    }
+    for (int s = 0; s < L; ++s) {
+      mbar_init(lo_free(s), 1);
+      mbar_init(split_done(s), 2 * kSplitWarps);  // both CTAs' splitter warps arrive on the leader's barrier
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * 4);  // both CTAs' epilogue warps arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything is signalled across CTAs
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): my 128 rows of A, my 128 columns of B =====================
+    if (lane == 0) {
+      int r = 0;
+      uint32_t rph = 0;
+      for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+        int64_t mb, nb;
+        tile_coords(t, m_tiles, n_tiles, mb, nb);
+        const int32_t m0 = int32_t(mb * 2 * BM + rank * BM), n0 = int32_t(nb * BN + rank * BNH);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(raw_free(r), rph ^ 1u);
+          const uint32_t a_dst = smem_base + r * RAW_BYTES, b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
+          const int32_t k0 = kb * BK;
+          if (A_MN) {  // A stored [K, M]: boxes of 32 (M, contiguous) x 32 (K rows)
+#pragma unroll
+            for (int g = 0; g < BM / 32; ++g) tma_load_2d(&tmap_a, raw_full(r), a_dst + g * 4096, m0 + g * 32, k0);
+          } else {     // A stored [M, K]: one box of 32 (K, contiguous) x 128 rows
+            tma_load_2d(&tmap_a, raw_full(r), a_dst, k0, m0);
+          }
+          if (B_MN) {  // B stored [K, N]
+#pragma unroll
+            for (int g = 0; g < BNH / 32; ++g) tma_load_2d(&tmap_b, raw_full(r), b_dst + g * 4096, n0 + g * 32, k0);
+          } else {     // B stored [N, K]
+            tma_load_2d(&tmap_b, raw_full(r), b_dst, k0, n0);
+          }
+          if (++r == R) { r = 0; rph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc<A_MN, B_MN, BN, 2 * BM>();
+      int r = 0, l = 0, acc = 0;
+      uint32_t lph = 0, acc_ph = 0;
+      for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+        for (int ch = 0; ch < num_chunks; ++ch) {
+          mbar_wait_cluster(tempty_bar(acc), acc_ph ^ 1u);  // both epilogues have drained this accumulator stage
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+          const int kb_end = (ch + 1) * kb_per_chunk < num_kb ? (ch + 1) * kb_per_chunk : num_kb;
+          for (int kb = ch * kb_per_chunk; kb < kb_end; ++kb) {
+            mbar_wait_cluster(split_done(l), lph);  // both CTAs: raw tile landed and lo tile written
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_hi = smem_base + r * RAW_BYTES, b_hi = a_hi + A_BYTES;
+              const uint32_t a_lo = lo_base + l * RAW_BYTES, b_lo = a_lo + A_BYTES;
+              const bool first_kb = (kb == ch * kb_per_chunk);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t da_hi = make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>());
+                const uint64_t da_lo = make_smem_desc<A_MN>(a_lo + k * k_slice_bytes<A_MN>());
+                const uint64_t db_hi = make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>());
+                const uint64_t db_lo = make_smem_desc<B_MN>(b_lo + k * k_slice_bytes<B_MN>());
+                umma_tf32_2cta(d_tmem, da_lo, db_hi, idesc, (first_kb && k == 0) ? 0u : 1u);  // small terms first
+                umma_tf32_2cta(d_tmem, da_hi, db_lo, idesc, 1u);
+                umma_tf32_2cta(d_tmem, da_hi, db_hi, idesc, 1u);
+              }
+              umma_commit_pair(raw_free(r));  // both CTAs may refill this raw stage ...
+              umma_commit_pair(lo_free(l));   // ... and this lo stage once the MMAs above have read them
+              if (kb == kb_end - 1) umma_commit_pair(tfull_bar(acc));
+            }
+            __syncwarp();
+            if (++r == R) r = 0;
+            if (++l == L) { l = 0; lph ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= kSplitWarp0) {
+    // ===================== splitters (both CTAs): lo = x - trunc_tf32(x), same swizzled offsets as the raw tile =====================
+    const int tid = threadIdx.x - kSplitWarp0 * 32;  // 0..255
+    const uint32_t done_remote = mapa_rank(split_done(0), 0);
+    int r = 0, l = 0;
+    uint32_t rph = 0, lph = 0;
+    constexpr int kPerThread = RAW_BYTES / (kSplitWarps * 32 * 16);  // 8 float4 per thread per stage
+    for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(raw_full(r), rph);
+        mbar_wait(lo_free(l), lph ^ 1u);
+        const uint32_t src = smem_base + r * RAW_BYTES + tid * 16, dst = lo_base + l * RAW_BYTES + tid * 16;
+        float4 v[kPerThread];
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i)
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                       : "r"(src + i * (kSplitWarps * 32 * 16)));
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i)
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + i * (kSplitWarps * 32 * 16)), "f"(lo_of(v[i].x)),
+                       "f"(lo_of(v[i].y)), "f"(lo_of(v[i].z)), "f"(lo_of(v[i].w))
+                       : "memory");
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(done_remote + 8u * l);
+        if (++r == R) { r = 0; rph ^= 1u; }
+        if (++l == L) { l = 0; lph ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue (both CTAs): my 128 rows of the pair tile =====================
+    const int q = warp - kEpiWarp0;  // == warp % 4: TMEM lanes [32q, 32q+32)
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+    const uint32_t tempty_remote = mapa_rank(tempty_bar(0), 0);
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+      int64_t mb, nb;
+      tile_coords(t, m_tiles, n_tiles, mb, nb);
+      const int64_t row = mb * 2 * BM + rank * BM + q * 32 + lane;
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_wait_ld();
+          const int64_t col0 = nb * BN + c * 32;
+          if (row < M && col0 < N) {
+            float* dst = C + row * ldc + col0;
+            if (vec_ok && col0 + 32 <= N) {
+              float4 base[8];
+              if (ch == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  base[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) base[j] = *reinterpret_cast<const float4*>(dst + 4 * j);  // previous chunks (L2)
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o;
+                o.x = base[j].x + __uint_as_float(v[4 * j]);
+                o.y = base[j].y + __uint_as_float(v[4 * j + 1]);
+                o.z = base[j].z + __uint_as_float(v[4 * j + 2]);
+                o.w = base[j].w + __uint_as_float(v[4 * j + 3]);
+                *reinterpret_cast<float4*>(dst + 4 * j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) {
+                  float b = ch == 0 ? (bias ? __ldg(bias + col0 + j) : 0.f) : dst[j];
+                  dst[j] = b + __uint_as_float(v[j]);
+                }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty_remote + 8u * acc);
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still read its shared memory or signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <bool A_MN, bool B_MN>
+static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
+                  int64_t N, int64_t K, int kb_per_chunk) {
+  auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN>;
+  AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+  const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  const int64_t pairs = ctx->sm_count / 2;
+  const int grid = int(2 * (tiles < pairs ? tiles : pairs));
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+}  // namespace tc2
+
+int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                      const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias) {
+  int rc = tc::resolve_encode(ctx);
+  if (rc) return rc;
+  const bool A_MN = transA != 0;  // A stored [K, M]: M contiguous
+  const bool B_MN = transB == 0;  // B stored [K, N]: N contiguous
+  CUtensorMap ta, tb;
+  if (A_MN) rc = tc::encode_2d(ctx, &ta, A, uint64_t(M), uint64_t(K), uint64_t(lda), 32, 32, true);
+  else      rc = tc::encode_2d(ctx, &ta, A, uint64_t(K), uint64_t(M), uint64_t(lda), 32, tc::BM, false);
+  if (rc) return rc;
+  if (B_MN) rc = tc::encode_2d(ctx, &tb, B, uint64_t(N), uint64_t(K), uint64_t(ldb), 32, 32, true);
+  else      rc = tc::encode_2d(ctx, &tb, B, uint64_t(K), uint64_t(N), uint64_t(ldb), 32, uint32_t(tc2::BNH), false);
+  if (rc) return rc;
+  const int64_t num_kb = (K + tc::BK - 1) / tc::BK;
+  const int kpc = ctx->tc_kchunk > 0 ? int((ctx->tc_kchunk + tc::BK - 1) / tc::BK) : int(num_kb);
+  if (A_MN && B_MN) return tc2::launch<true, true>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
+  if (A_MN) return tc2::launch<true, false>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
+  if (B_MN) return tc2::launch<false, true>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
+  return tc2::launch<false, false>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
+}

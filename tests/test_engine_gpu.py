@@ -317,7 +317,9 @@ def test_fit_sine_tracks_oracle_step_for_step(dev):
     got, params, _ = run_device_mlp(dev, x, y, [np.zeros((3, 1), np.float32)], [np.zeros((1, 1), np.float32)], None, 1e-3, steps)
     assert max(abs(a - b) / abs(b) for a, b in zip(got, want)) < TOL
     assert abs(got[0] - 0.49974999) < 1e-6 and abs(got[1] - 0.44477817) < 1e-6 and abs(got[99] - 0.31669122) < 2e-6
-    assert O.rel_err(params[0], layers[0].w.data) < TOL and O.rel_err(params[1], layers[0].b.data) < TOL
+    # the trained bias is ~1e-10 (pure rounding residue of a symmetric problem): compare both parameters on the weights' scale
+    scale = float(np.abs(layers[0].w.data).max())
+    assert np.abs(params[0] - layers[0].w.data).max() < TOL * scale and np.abs(params[1] - layers[0].b.data).max() < TOL * scale
 
 
 @pytest.mark.parametrize("act,width,rows,layers", [("relu", 256, 512, 3), ("sigmoid", 128, 300, 4), ("relu", 520, 1000, 2)])

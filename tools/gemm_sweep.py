@@ -1,0 +1,89 @@
+"""GEMM sweep on the GPU (BASELINE config C4 and the Linear shapes of C2/C5): for every shape x operand-major combination,
+check a sample of output rows against an f64 NumPy product and time the kernel with CUDA events on its stream.
+  python tools/gemm_sweep.py [--pair 0|1|both] [--sizes 256,512,...] [--linear] [--iters N] [--kchunk K]
+One JSON line per case; the last line is a summary table."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import autograd_rs_b200  # noqa: F401,E402
+from autograd_rs_b200 import _capi  # noqa: E402
+
+
+def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias=False):
+    A = rng.uniform(-1, 1, (K, M) if ta else (M, K)).astype(np.float32)
+    B = rng.uniform(-1, 1, (N, K) if tb else (K, N)).astype(np.float32)
+    bv = rng.uniform(-1, 1, N).astype(np.float32) if bias else None
+    ctx.call("agrs_set_tuning", _capi.TUNE_TC_2CTA, pair)
+    ctx.call("agrs_set_tuning", _capi.TUNE_TC_KCHUNK, kchunk)
+    ctx.call("agrs_set_gemm_path", _capi.GEMM_TCGEN05)
+    dA, dB, dC = ctx.to_device(A), ctx.to_device(B), ctx.empty(M * N)
+    dbias = ctx.to_device(bv) if bias else None
+    args = (int(ta), int(tb), M, N, K, dA.ptr, A.shape[1], dB.ptr, B.shape[1], dC.ptr, N, dbias.ptr if bias else None)
+    ctx.call("agrs_gemm_f32", *args)
+    got = ctx.to_host(dC, (M, N))
+    rows = np.unique(np.concatenate([np.arange(min(M, 4)), np.arange(max(M - 4, 0), M), rng.integers(0, M, check_rows)]))
+    opA = (A.T if ta else A)[rows].astype(np.float64)
+    opB = (B.T if tb else B).astype(np.float64)
+    truth = opA @ opB + (bv.astype(np.float64) if bias else 0.0)
+    scale = float(np.abs(truth).max())
+    err = float(np.abs(got[rows] - truth).max() / scale)
+    f32 = ((A.T if ta else A)[rows] @ (B.T if tb else B)).astype(np.float64) + (bv if bias else 0.0)
+    err32 = float(np.abs(f32 - truth).max() / scale)
+    res = {"M": M, "N": N, "K": K, "ta": int(ta), "tb": int(tb), "pair": pair, "kchunk": kchunk, "bias": bias, "rel_err_vs_f64": err,
+           "numpy_f32_rel_err_vs_f64": err32, "finite": bool(np.isfinite(got).all())}
+    if iters:
+        for _ in range(3):
+            ctx.call("agrs_gemm_f32", *args)
+        ctx.call("agrs_timer_begin")
+        for _ in range(iters):
+            ctx.call("agrs_gemm_f32", *args)
+        import ctypes as C
+        ms = C.c_float()
+        ctx.call("agrs_timer_end", C.byref(ms))
+        res["ms"] = ms.value / iters
+        res["tflops"] = 2.0 * M * N * K / (res["ms"] * 1e-3) / 1e12
+    ctx.call("agrs_set_gemm_path", _capi.GEMM_AUTO)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--pair", default="both")
+    ap.add_argument("--sizes", default="256,512,1024,2048,4096,8192")
+    ap.add_argument("--linear", action="store_true", help="also the Linear fwd/dX/dW shapes of C2 (8192x4096x4096) and C5 (8192x8192x8192)")
+    ap.add_argument("--odd", action="store_true", help="ragged shapes (partial tiles in M, N and K)")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--kchunk", type=int, default=1024)
+    a = ap.parse_args()
+    pairs = [0, 1] if a.pair == "both" else [int(a.pair)]
+    ctx = _capi.Ctx(0)
+    rng = np.random.default_rng(0)
+    cases = []
+    for n in [int(s) for s in a.sizes.split(",") if s]:
+        for ta, tb in ((0, 0), (0, 1), (1, 0)):  # fwd X.W (NN), dX = G.W^T (NT), dW = X^T.G (TN)
+            cases.append((n, n, n, ta, tb, False))
+    if a.linear:
+        for (m, n, k) in ((8192, 4096, 4096), (8192, 8192, 8192)):
+            cases += [(m, n, k, 0, 0, True), (m, k, n, 0, 1, False), (k, n, m, 1, 0, False)]
+    if a.odd:
+        cases += [(136, 72, 40, 0, 0, True), (200, 300, 100, 1, 1, False), (1000, 520, 3000, 1, 0, True), (257, 264, 36, 0, 1, False),
+                  (129, 8, 8, 0, 0, False), (384, 1000, 520, 0, 1, True), (2048, 2048, 2048, 1, 1, False), (130, 260, 4100, 1, 1, True)]
+    out = []
+    for (M, N, K, ta, tb, bias) in cases:
+        for p in pairs:
+            r = run_case(ctx, M, N, K, ta, tb, p, a.iters, a.kchunk, rng, bias=bias)
+            print(json.dumps(r), flush=True)
+            out.append(r)
+    bad = [r for r in out if not r["finite"] or r["rel_err_vs_f64"] > 2e-5]
+    print(json.dumps({"cases": len(out), "bad": len(bad), "max_rel_err": max(r["rel_err_vs_f64"] for r in out)}))
+    ctx.close()
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
