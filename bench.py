@@ -49,23 +49,29 @@ def flops_per_sample(cfg):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md).  The sampler runs from
+    before the warm-up (nvidia-smi needs ~0.3 s to produce its first line); only samples whose timestamp falls inside a
+    timed window are used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+        self.gpu, self.proc, self.path, self.windows = gpu_index, None, None, []
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -80,6 +86,12 @@ class ClockSampler:
                 for line in f:
                     c = [x.strip() for x in line.split(",")]
                     if len(c) < 8 or not c[1].isdigit():
+                        continue
+                    try:
+                        ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    except ValueError:
+                        continue
+                    if not any(t0 - 0.03 <= ts <= t1 + 0.03 for t0, t1 in self.windows):
                         continue
                     sm.append(int(c[1]))
                     mx.append(int(c[2]))
@@ -240,23 +252,24 @@ def run_b200_arm(args, cfg):
         return float(tt.item())
 
     # ---- device-resident throughput ----
-    for _ in range(args.warmup):
-        loss = tr.step(X, T)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        loss = tr.step(X, T)
+    barrier()
     dev.profile_enable(True)
     dev.profile_gemm(_capi.GEMM_TCGEN05)
     dev.profile_gemm(_capi.GEMM_SIMT)
     n0 = dev.launches()
+    w0 = time.time()
     dev.timer_begin()
     for _ in range(args.steps):
         loss = tr.step(X, T)
     ms = dev.timer_end()
+    sampler.window(w0, time.time())
     barrier()
     launches = dev.launches() - n0
-    clocks = sampler.stop() if rank == 0 else None
     dev.profile_enable(False)
     g_n, g_ms, g_fl = dev.profile_gemm(_capi.GEMM_TCGEN05)
     s_n, s_ms, s_fl = dev.profile_gemm(_capi.GEMM_SIMT)
@@ -274,6 +287,7 @@ def run_b200_arm(args, cfg):
             tr.step(X, T).item()
         barrier()
         t0 = time.perf_counter()
+        w0 = time.time()
         dev.timer_begin()
         for _ in range(args.steps):
             X.copy_from_numpy(hx, blocking=False)   # pinned host -> device, on the compute stream
@@ -281,10 +295,13 @@ def run_b200_arm(args, cfg):
             lv = tr.step(X, T).item()               # device -> host read of the loss (4 bytes), blocks
         ms_e = dev.timer_end()
         wall_e = (time.perf_counter() - t0) * 1e3
+        sampler.window(w0, time.time())
         ms_e = max_over_ranks(max(ms_e, wall_e))
         assert np.isfinite(lv)
         e2e = {"value": cfg["rows"] * world * args.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + ht.nbytes),
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps}
+
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel ----
     peaks = load_peaks()
@@ -302,7 +319,7 @@ def run_b200_arm(args, cfg):
             except Exception:
                 traffic = None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak_alg, "unit": "TFLOP/s", "frac": ach / peak_alg, "traffic": traffic,
-                    "kernel": "tc::k_gemm_3xtf32 (tcgen05.mma kind::tf32 x3)", "launches": g_n, "avg_launch_ms": g_ms / g_n,
+                    "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2 kind::tf32 x3)", "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_tflops": 3 * ach,
                     "gemm_share_of_step": g_ms / (ms if world == 1 else ms),
                     "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / 3 (3xTF32)"}

@@ -59,20 +59,21 @@ def main():
     ap.add_argument("--odd", action="store_true", help="ragged shapes (partial tiles in M, N and K)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kchunk", type=int, default=1024)
+    ap.add_argument("--majors", default="00,01,10", help="ta tb pairs for the square sizes: 00 = X.W, 01 = G.W^T, 10 = X^T.G, 11")
     a = ap.parse_args()
     pairs = [0, 1] if a.pair == "both" else [int(a.pair)]
     ctx = _capi.Ctx(0)
     rng = np.random.default_rng(0)
     cases = []
     for n in [int(s) for s in a.sizes.split(",") if s]:
-        for ta, tb in ((0, 0), (0, 1), (1, 0)):  # fwd X.W (NN), dX = G.W^T (NT), dW = X^T.G (TN)
+        for ta, tb in [(int(m[0]), int(m[1])) for m in a.majors.split(",")]:  # fwd X.W (NN), dX = G.W^T (NT), dW = X^T.G (TN)
             cases.append((n, n, n, ta, tb, False))
     if a.linear:
         for (m, n, k) in ((8192, 4096, 4096), (8192, 8192, 8192)):
             cases += [(m, n, k, 0, 0, True), (m, k, n, 0, 1, False), (k, n, m, 1, 0, False)]
     if a.odd:
         cases += [(136, 72, 40, 0, 0, True), (200, 300, 100, 1, 1, False), (1000, 520, 3000, 1, 0, True), (257, 264, 36, 0, 1, False),
-                  (129, 8, 8, 0, 0, False), (384, 1000, 520, 0, 1, True), (2048, 2048, 2048, 1, 1, False), (130, 260, 4100, 1, 1, True)]
+                  (129, 8, 8, 0, 0, False), (384, 1000, 520, 0, 1, True), (2048, 2048, 2048, 1, 1, False), (132, 260, 4100, 1, 1, True), (4100, 132, 260, 1, 0, False)]
     out = []
     for (M, N, K, ta, tb, bias) in cases:
         for p in pairs:
