@@ -57,6 +57,8 @@ def lib():
             "agrs_upload": [vp, vp, vp, sz],
             "agrs_download": [vp, vp, vp, sz],
             "agrs_copy": [vp, vp, vp, sz],
+            "agrs_upload_prefetch": [vp, vp, vp, sz],
+            "agrs_prefetch_join": [vp],
             "agrs_fill_f32": [vp, vp, f32, sz],
             "agrs_gemm_f32": [vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp],
             "agrs_set_gemm_path": [vp, i32],

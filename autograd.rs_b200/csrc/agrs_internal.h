@@ -36,6 +36,8 @@ struct agrs_ctx {
   // live GEMM timing (agrs_profile_*): event pairs recorded around launches while enabled
   struct ProfRec { cudaEvent_t start, stop; double flops; int path; };
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;  // agrs_timer_*
+  cudaStream_t copy_stream = nullptr;                // agrs_upload_prefetch
+  cudaEvent_t copy_ready = nullptr, copy_done = nullptr;
   bool profiling = false;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;

@@ -1,6 +1,7 @@
 // Conv2D lowering kernels: im2col, col2im (gather form, no atomics), filter broadcast.
 // Index maps follow src/operators/functional_ndarray.rs:40-138 of the reference exactly;
-// both kernels are pure data movement (HBM-bound): one thread per output element, writes coalesced.
+// both are pure data movement (HBM-bound).  Samples that fit in shared memory take the staged kernels (k_*_tile);
+// the one-thread-per-output-element kernels remain for samples that do not.
 #include "agrs_internal.h"
 
 namespace {
@@ -58,6 +59,101 @@ __global__ void __launch_bounds__(256) k_col2im(const float* __restrict__ col, i
   }
 }
 
+// ---- shared-memory staged versions: one CTA per image (grid-stride over the batch) --------------------------------
+// im2col writes 18x (k*k x) more than it reads and col2im reads 18x more than it writes; what matters is that the big side
+// moves as full 16-byte coalesced vectors with no per-element 64-bit div/mod.  The image (im2col) or the col block
+// (col2im) of ONE sample is staged in shared memory; the scattered side of the index map is then a shared-memory gather
+// (row pitch K = C*k*k floats: odd for the LeNet shape, so bank-conflict free).
+__global__ void __launch_bounds__(256) k_im2col_tile(const float* __restrict__ im, int B, int C, int H, int W, int k, int s, int p, int Ho,
+                                                     int Wo, float* __restrict__ col, int vec_in, int vec_out) {
+  extern __shared__ float sm[];
+  const int n_im = C * H * W, kk = k * k, K = C * kk, P = Ho * Wo, per = P * K;
+  int* toff = reinterpret_cast<int*>(sm + ((n_im + 3) & ~3));  // per tap q: channel offset c*H*W, row i, column j
+  int* ti = toff + K;
+  int* tj = ti + K;
+  for (int q = threadIdx.x; q < K; q += blockDim.x) {
+    const int c = q / kk, r = q - c * kk, i = r / k;
+    toff[q] = c * H * W;
+    ti[q] = i;
+    tj[q] = r - i * k;
+  }
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();  // table built / previous sample fully consumed
+    const float* src = im + int64_t(b) * n_im;
+    if (vec_in) {
+      for (int t = threadIdx.x; t < n_im / 4; t += blockDim.x) reinterpret_cast<float4*>(sm)[t] = __ldg(reinterpret_cast<const float4*>(src) + t);
+    } else {
+      for (int t = threadIdx.x; t < n_im; t += blockDim.x) sm[t] = __ldg(src + t);
+    }
+    __syncthreads();
+    float* dst = col + int64_t(b) * per;
+    if (vec_out) {
+      for (int o4 = threadIdx.x; o4 < per / 4; o4 += blockDim.x) {
+        const int o = 4 * o4;
+        int pp = o / K, q = o - pp * K;
+        int y = pp / Wo, x = pp - y * Wo;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = y * s - p + ti[q], w = x * s - p + tj[q];
+          v[e] = (h >= 0 && h < H && w >= 0 && w < W) ? sm[toff[q] + h * W + w] : 0.f;
+          if (++q == K) {
+            q = 0;
+            if (++x == Wo) { x = 0; ++y; }
+          }
+        }
+        reinterpret_cast<float4*>(dst)[o4] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      for (int o = threadIdx.x; o < per; o += blockDim.x) {
+        const int pp = o / K, q = o - pp * K, y = pp / Wo, x = pp - y * Wo;
+        const int h = y * s - p + ti[q], w = x * s - p + tj[q];
+        dst[o] = (h >= 0 && h < H && w >= 0 && w < W) ? sm[toff[q] + h * W + w] : 0.f;
+      }
+    }
+  }
+}
+
+// same summation order as k_col2im (increasing patch index), reading the sample's col block from shared memory
+__global__ void __launch_bounds__(256) k_col2im_tile(const float* __restrict__ col, int B, int C, int Hi, int Wi, int k, int s, int Ho, int Wo,
+                                                     float* __restrict__ im, int vec_in) {
+  extern __shared__ float sm[];
+  const int kk = k * k, K = C * kk, P = Ho * Wo, per = P * K, n_im = C * Hi * Wi;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const float* src = col + int64_t(b) * per;
+    if (vec_in) {
+      for (int t = threadIdx.x; t < per / 4; t += blockDim.x) reinterpret_cast<float4*>(sm)[t] = __ldg(reinterpret_cast<const float4*>(src) + t);
+    } else {
+      for (int t = threadIdx.x; t < per; t += blockDim.x) sm[t] = __ldg(src + t);
+    }
+    __syncthreads();
+    float* dst = im + int64_t(b) * n_im;
+    for (int idx = threadIdx.x; idx < n_im; idx += blockDim.x) {
+      const int w = idx % Wi;
+      int t = idx / Wi;
+      const int h = t % Hi, c = t / Hi;
+      float acc = 0.f;
+      for (int i = k - 1; i >= 0; --i) {
+        const int hy = h - i;
+        if (hy < 0 || hy % s) continue;
+        const int y = hy / s;
+        if (y >= Ho) continue;
+        for (int j = k - 1; j >= 0; --j) {
+          const int wx = w - j;
+          if (wx < 0 || wx % s) continue;
+          const int x = wx / s;
+          if (x >= Wo) continue;
+          acc += sm[(y * Wo + x) * K + c * kk + i * k + j];
+        }
+      }
+      dst[idx] = acc;
+    }
+  }
+}
+
+constexpr size_t kTileSmemMax = 200 * 1024;  // leave room for a second CTA's static needs; larger samples take the generic kernels
+
 __global__ void k_broadcast_filter(const float* __restrict__ filt, int64_t per, int64_t total, float* __restrict__ out) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < total) out[i] = filt[i % per];
@@ -83,7 +179,17 @@ int agrs_im2col_f32(agrs_ctx* ctx, const float* im, int64_t B, int64_t C, int64_
   if (total == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, im && col, AGRS_ERR_INVALID, "agrs_im2col_f32: null pointer");
   AGRS_REQUIRE(ctx, C * k * k < (1LL << 31) && Ho * Wo < (1LL << 31), AGRS_ERR_UNSUPPORTED, "agrs_im2col_f32: extent overflow");
-  k_im2col<<<grid1d(ctx, total), 256, 0, ctx->stream>>>(im, total, int(C), int(H), int(W), int(k), int(stride), int(pad), int(Ho), int(Wo), col);
+  const int64_t n_im = C * H * W, per = Ho * Wo * C * k * k;
+  const size_t smem = size_t(((n_im + 3) & ~int64_t(3)) + 3 * C * k * k) * sizeof(float);
+  if (smem <= kTileSmemMax && per < (1LL << 30) && B < (1LL << 31)) {
+    AGRS_CUDA(ctx, cudaFuncSetAttribute(k_im2col_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));
+    const int vec_in = (n_im % 4 == 0) && agrs_aligned16(im), vec_out = (per % 4 == 0) && agrs_aligned16(col);
+    const int64_t cap = int64_t(ctx->sm_count) * 8;
+    k_im2col_tile<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, int(B), int(C), int(H), int(W), int(k), int(stride), int(pad),
+                                                                          int(Ho), int(Wo), col, vec_in, vec_out);
+  } else {
+    k_im2col<<<grid1d(ctx, total), 256, 0, ctx->stream>>>(im, total, int(C), int(H), int(W), int(k), int(stride), int(pad), int(Ho), int(Wo), col);
+  }
   AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }
@@ -96,7 +202,17 @@ int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t C, int64
   int64_t total = B * C * Hi * Wi;
   if (total == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, col && im_out, AGRS_ERR_INVALID, "agrs_col2im_f32: null pointer");
-  k_col2im<<<grid1d(ctx, total), 256, 0, ctx->stream>>>(col, total, int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho), int(Wo), im_out);
+  const int64_t per = Ho * Wo * C * k * k;
+  const size_t smem = size_t(per) * sizeof(float);
+  if (smem <= kTileSmemMax && C * Hi * Wi < (1LL << 30) && B < (1LL << 31)) {
+    AGRS_CUDA(ctx, cudaFuncSetAttribute(k_col2im_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));
+    const int vec_in = (per % 4 == 0) && agrs_aligned16(col);
+    const int64_t cap = int64_t(ctx->sm_count) * 8;
+    k_col2im_tile<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(col, int(B), int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho),
+                                                                          int(Wo), im_out, vec_in);
+  } else {
+    k_col2im<<<grid1d(ctx, total), 256, 0, ctx->stream>>>(col, total, int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho), int(Wo), im_out);
+  }
   AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }

@@ -72,6 +72,12 @@ int agrs_ctx_destroy(agrs_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->counter) cudaFree(ctx->counter);
   if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->copy_ready);
+    cudaEventDestroy(ctx->copy_done);
+  }
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AGRS_OK;
@@ -167,6 +173,30 @@ int agrs_download(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
   AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_download: null pointer");
   AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_upload_prefetch(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
+  AGRS_CHECK_CTX(ctx);
+  if (nbytes == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_upload_prefetch: null pointer");
+  if (!ctx->copy_stream) {
+    AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    AGRS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    AGRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ready, cudaEventDisableTiming));
+    AGRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+  }
+  AGRS_CUDA(ctx, cudaEventRecord(ctx->copy_ready, ctx->stream));
+  AGRS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ready, 0));
+  AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  AGRS_CUDA(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+  return AGRS_OK;
+}
+
+int agrs_prefetch_join(agrs_ctx* ctx) {
+  AGRS_CHECK_CTX(ctx);
+  if (!ctx->copy_stream) return AGRS_OK;
+  AGRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
   return AGRS_OK;
 }
 

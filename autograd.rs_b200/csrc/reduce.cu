@@ -118,7 +118,20 @@ __global__ void __launch_bounds__(256) k_sum_axis_mid(const float* __restrict__ 
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
   if (col < inner) {
     const float* base = x + o * len * inner + col;
-    for (int64_t l = l0 + ty; l < l1; l += 8) {
+    int64_t l = l0 + ty;
+    if (VEC == 4) {  // four independent 16-byte loads in flight per thread (rows l, l+8, l+16, l+24)
+      for (; l + 24 < l1; l += 32) {
+        float4 v0 = __ldcs(reinterpret_cast<const float4*>(base + l * inner));
+        float4 v1 = __ldcs(reinterpret_cast<const float4*>(base + (l + 8) * inner));
+        float4 v2 = __ldcs(reinterpret_cast<const float4*>(base + (l + 16) * inner));
+        float4 v3 = __ldcs(reinterpret_cast<const float4*>(base + (l + 24) * inner));
+        acc[0] += v0.x; acc[1 % VEC] += v0.y; acc[2 % VEC] += v0.z; acc[3 % VEC] += v0.w;
+        acc[0] += v1.x; acc[1 % VEC] += v1.y; acc[2 % VEC] += v1.z; acc[3 % VEC] += v1.w;
+        acc[0] += v2.x; acc[1 % VEC] += v2.y; acc[2 % VEC] += v2.z; acc[3 % VEC] += v2.w;
+        acc[0] += v3.x; acc[1 % VEC] += v3.y; acc[2 % VEC] += v3.z; acc[3 % VEC] += v3.w;
+      }
+    }
+    for (; l < l1; l += 8) {
       if (VEC == 4) {
         float4 v = __ldcs(reinterpret_cast<const float4*>(base + l * inner));
         acc[0] += v.x;

@@ -169,6 +169,23 @@ int agrs_eng_tensor_copy_from_host(agrs_tensor* t, const float* host, int64_t n,
     if (blocking) s.dev()->sync();
   });
 }
+int agrs_eng_tensor_prefetch_from_host(agrs_tensor* t, const float* host, int64_t n) {
+  return guarded([&] {
+    need(t, "tensor");
+    if (n != t->t.len()) throw Panic("prefetch_from_host: buffer holds " + std::to_string(n) + " elements, tensor has " + std::to_string(t->t.len()));
+    if (n == 0) return;
+    need(host, "host data");
+    Storage& s = *t->t.data;
+    if (s.transposed) throw Panic("prefetch_from_host into a transposed view", AGRS_ERR_UNSUPPORTED);
+    s.dev()->check(agrs_upload_prefetch(s.dev()->ctx(), s.wptr(), host, size_t(n) * sizeof(float)));
+  });
+}
+int agrs_eng_device_prefetch_join(agrs_device* d) {
+  return guarded([&] {
+    need(d, "device");
+    d->dev.check(agrs_prefetch_join(d->dev.ctx()));
+  });
+}
 int agrs_eng_tensor_clone(const agrs_tensor* t, agrs_tensor** out) {
   return guarded([&] {
     need(t, "tensor");
@@ -264,7 +281,7 @@ int agrs_eng_tensor_grad(const agrs_tensor* t, agrs_tensor** out) {
   return guarded([&] {
     need(t, "tensor");
     need(out, "out");
-    *out = t->t.has_grad() ? wrap(Tensor(t->t.grad->g)) : nullptr;
+    *out = t->t.has_grad() ? wrap(Tensor(t->t.grad->get())) : nullptr;
   });
 }
 int agrs_eng_tensor_graph_info(const agrs_tensor* t, char* op_name, int cap, int* n_variables, int* n_parents) {

@@ -31,7 +31,7 @@ void DataParallel::register_parameters(const std::vector<Tensor>& params, bool o
 
 void DataParallel::reduce(GradCell& cell) {
   if (!cell.g) throw Panic("called `Option::unwrap()` on a `None` value (DataParallel: parameter has no grad)");
-  Storage& g = *cell.g;
+  Storage& g = *cell.get();
   if (g.transposed) throw Panic("DataParallel: transposed gradient view", AGRS_ERR_UNSUPPORTED);
   // in place on the gradient buffer (un-shared first if a hand-over still aliases it); ncclAvg = sum / world
   dev_->check(agrs_comm_allreduce_f32(comm_, g.wptr(), size_t(g.len()), 1));

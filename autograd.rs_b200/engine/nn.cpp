@@ -59,7 +59,7 @@ void sgd_step(const std::vector<Tensor>& params, float lr) {
   for (auto& p : params) {
     if (!p.has_grad()) throw Panic("called `Option::unwrap()` on a `None` value");  // w_grad.as_ref().unwrap(), optim.rs:30
     Storage& w = *p.data;
-    const Storage& g = *p.grad->g;
+    const Storage& g = *p.grad->get();
     if (w.transposed || g.transposed) throw Panic("SGD on a transposed parameter view is not supported", AGRS_ERR_UNSUPPORTED);
     Bcast k = broadcast_kind(w.shape, g.shape);
     if (k == Bcast::Leading) throw Panic("SGD: gradient " + shape_str(g.shape) + " broadcasts along rows of " + shape_str(w.shape), AGRS_ERR_UNSUPPORTED);

@@ -188,7 +188,7 @@ Tensor Tensor::to_owned() const {
 
 std::vector<float> Tensor::grad_to_vec() const {
   if (!has_grad()) throw Panic("called `Option::unwrap()` on a `None` value (tensor has no grad)");
-  return grad->g->to_host();
+  return grad->get()->to_host();
 }
 
 float Tensor::item() const {
@@ -322,36 +322,49 @@ Tensor Tensor::dot(const Tensor& other) const {
 }
 
 // ------------------------------------------------------------------ autograd plumbing
+const StoragePtr& GradCell::get() {
+  if (g && zero_pending) {
+    zero_pending = false;
+    g->dev()->check(agrs_fill_f32(g->dev()->ctx(), g->wptr(), 0.0f, size_t(g->len())));
+  }
+  return g;
+}
+
 void Tensor::zero_grad() const {
-  // grad = Some(zeros(shape of DATA)) (tensor.rs:135-140); reuse the allocation when it is ours alone
+  // grad = Some(zeros(shape of DATA)) (tensor.rs:135-140).  The zeros are LAZY: the cell records "all zero" and the memset
+  // only runs if somebody reads the gradient before the next accumulation (GradCell::get); the usual next event is
+  // backward's `zeros += dW`, which then degenerates to taking dW's buffer (0 + x == x) -- no memset, no add pass.
   auto& g = grad->g;
   if (g && g->len() == data->len() && g->buf.use_count() == 1) {
     g->shape = data->shape;
     g->transposed = false;
-    dev()->check(agrs_fill_f32(dev()->ctx(), g->buf->ptr, 0.0f, size_t(g->len())));
   } else {
     g = std::make_shared<Storage>(dev(), data->shape);
-    dev()->check(agrs_fill_f32(dev()->ctx(), g->buf->ptr, 0.0f, size_t(g->len())));
   }
+  grad->zero_pending = true;
 }
 
 void Tensor::accumulate_grad_from_grad_tensor(const Tensor& gt) const {
   auto& g = grad->g;
+  auto src = contig(gt.data);
   if (!g) {
     // None => Some(grad.to_owned()).  The device buffer is handed over instead of copied; whoever
     // writes in place first (Storage::wptr) un-shares it, so the observable semantics are the copy's.
-    auto src = contig(gt.data);
     g = std::make_shared<Storage>(src->buf, src->shape, false);
+  } else if (grad->zero_pending && src->len() == g->len() && broadcast_kind(g->shape, src->shape) == Bcast::Same) {
+    // zeros(shape) += b with nothing to broadcast: the result is b's values in the zeros' shape ([1,O] += [O] keeps [1,O])
+    g = std::make_shared<Storage>(src->buf, g->shape, false);
+    grad->zero_pending = false;
   } else {
     // Some(a) => a += b with ndarray broadcasting of b onto a (todo!() at HEAD: defect D2)
-    auto src = contig(gt.data);
+    grad->get();
     storage_binary_into(AGRS_ADD, *g, *g, *src);
   }
 }
 
 void Tensor::accumulate_grad(const Tensor& other) const {
   if (!other.has_grad()) return;
-  Tensor tmp(other.grad->g);
+  Tensor tmp(other.grad->get());
   accumulate_grad_from_grad_tensor(tmp);
 }
 

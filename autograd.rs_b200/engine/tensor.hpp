@@ -93,7 +93,9 @@ struct GradHook {
 
 struct GradCell {  // Rc<RefCell<Option<StorageType<f32>>>>, tensor.rs:32
   StoragePtr g;
-  GradHook* hook = nullptr;  // not owned
+  bool zero_pending = false;   // g is logically all zeros but its buffer has not been cleared yet (lazy zero_grad)
+  GradHook* hook = nullptr;    // not owned
+  const StoragePtr& get();     // the gradient storage with any pending zero fill applied: what every reader must use
 };
 
 struct Node;

@@ -63,6 +63,8 @@ def lib():
         "agrs_eng_tensor_uniform": [vp, pi64, i32, f32, f32, pvp],
         "agrs_eng_tensor_kaiming_uniform": [vp, pi64, i32, pvp],
         "agrs_eng_tensor_copy_from_host": [vp, vp, i64, i32],
+        "agrs_eng_tensor_prefetch_from_host": [vp, vp, i64],
+        "agrs_eng_device_prefetch_join": [vp],
         "agrs_eng_tensor_clone": [vp, pvp],
         "agrs_eng_tensor_to_owned": [vp, pvp],
         "agrs_eng_tensor_free": [vp],
@@ -158,6 +160,10 @@ class Device:
 
     def seed(self, s):
         _check(lib().agrs_eng_device_seed(self._h, int(s)))
+
+    def prefetch_join(self):
+        """the compute stream waits for every Tensor.prefetch_from_numpy issued so far"""
+        _check(lib().agrs_eng_device_prefetch_join(self._h))
 
     def set_matmul_backward_literal(self, literal):
         _check(lib().agrs_eng_device_set_matmul_backward_literal(self._h, int(bool(literal))))
@@ -272,6 +278,12 @@ class Tensor:
         """Overwrite the data in place from a host array (blocking=False: `arr` must be pinned and stay alive until a sync)."""
         assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"]
         _check(lib().agrs_eng_tensor_copy_from_host(self._h, arr.ctypes.data, int(arr.size), int(blocking)))
+
+    def prefetch_from_numpy(self, arr):
+        """Same, on the device's copy stream: overlaps the step already enqueued.  `arr` must be pinned (Device.pinned_empty);
+        call Device.prefetch_join() before enqueuing work that reads this tensor."""
+        assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"]
+        _check(lib().agrs_eng_tensor_prefetch_from_host(self._h, arr.ctypes.data, int(arr.size)))
 
     def clone(self):
         return Tensor._new(self.dev, lib().agrs_eng_tensor_clone, self._h)

@@ -279,27 +279,42 @@ def run_b200_arm(args, cfg):
     value = cfg["rows"] * world * args.steps / (ms * 1e-3)
 
     # ---- end to end: host buffers in, loss out, every step ----
+    # Every step's X and T come from pinned host memory (268 MB) and its loss goes back to the host.  The copy of step i+1
+    # runs on the copy stream while step i computes (two device input slots); the loss read blocks once per step.
     e2e = None
     if not args.no_e2e:
-        for _ in range(2):
-            X.copy_from_numpy(hx, blocking=False)
-            T.copy_from_numpy(ht, blocking=False)
-            tr.step(X, T).item()
+        X2, T2 = F.Tensor.zeros(dev, hx.shape), F.Tensor.zeros(dev, ht.shape)
+        T2.requires_grad = False
+        slots = [(X, T), (X2, T2)]
+
+        def e2e_loop(n):
+            slots[0][0].prefetch_from_numpy(hx)     # step 0's inputs: pinned host -> device
+            slots[0][1].prefetch_from_numpy(ht)
+            lv = None
+            for i in range(n):
+                dev.prefetch_join()                 # step i's inputs have landed
+                xs, ts = slots[i % 2]
+                if i + 1 < n:                       # step i+1's inputs start moving now, under step i's kernels
+                    slots[(i + 1) % 2][0].prefetch_from_numpy(hx)
+                    slots[(i + 1) % 2][1].prefetch_from_numpy(ht)
+                lv = tr.step(xs, ts).item()         # device -> host read of the loss (4 bytes), blocks
+            return lv
+
+        e2e_loop(2)
         barrier()
         t0 = time.perf_counter()
         w0 = time.time()
         dev.timer_begin()
-        for _ in range(args.steps):
-            X.copy_from_numpy(hx, blocking=False)   # pinned host -> device, on the compute stream
-            T.copy_from_numpy(ht, blocking=False)
-            lv = tr.step(X, T).item()               # device -> host read of the loss (4 bytes), blocks
+        lv = e2e_loop(args.steps)
         ms_e = dev.timer_end()
         wall_e = (time.perf_counter() - t0) * 1e3
         sampler.window(w0, time.time())
         ms_e = max_over_ranks(max(ms_e, wall_e))
         assert np.isfinite(lv)
         e2e = {"value": cfg["rows"] * world * args.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + ht.nbytes),
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps}
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps,
+               "how": "X,T copied from pinned host memory every step on a copy stream (double-buffered, overlapping the previous step), loss read back every step"}
+        del X2, T2, slots
 
     clocks = sampler.stop() if rank == 0 else None
 

@@ -62,6 +62,11 @@ AGRS_API int agrs_host_alloc(agrs_ctx* ctx, size_t nbytes, void** out); /* pinne
 AGRS_API int agrs_host_free(agrs_ctx* ctx, void* ptr);
 AGRS_API int agrs_upload(agrs_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);   /* Tensor::from, tensor.rs:37-61 */
 AGRS_API int agrs_download(agrs_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes); /* data()/Index/into_raw_vec, storage.rs:139-177; blocks */
+/* Upload on a separate COPY stream so it overlaps kernels already running on the context's stream (input prefetch for the next
+ * training step).  Ordered after everything enqueued on the context's stream at call time (earlier readers of dst are safe);
+ * agrs_prefetch_join makes the context's stream wait for all prefetches issued so far.  src_host must be pinned and stay alive. */
+AGRS_API int agrs_upload_prefetch(agrs_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);
+AGRS_API int agrs_prefetch_join(agrs_ctx* ctx);
 AGRS_API int agrs_copy(agrs_ctx* ctx, void* dst_dev, const void* src_dev, size_t nbytes);      /* to_owned() deep copy, tensor.rs:148,160 */
 AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);                     /* storage.rs:75; zeros/ones tensor.rs:67-84; zero_grad tensor.rs:135-140 */
 

@@ -422,6 +422,35 @@ def test_no_host_sync_inside_a_step(dev):
     assert t_enqueue < 0.5 * t_total, (t_enqueue, t_total)
 
 
+def test_prefetch_copy_stream(dev):
+    """copy-stream upload (input prefetch of the end-to-end loop): data is what was sent once the compute stream has joined"""
+    rng = np.random.default_rng(61)
+    host = dev.pinned_empty((512, 384))
+    t = F.Tensor.zeros(dev, (512, 384))
+    for _ in range(3):
+        host[...] = rng.standard_normal((512, 384)).astype(np.float32)
+        t.prefetch_from_numpy(host)
+        dev.prefetch_join()
+        doubled = t * 2.0  # a kernel enqueued after the join sees the new data
+        assert np.array_equal(doubled.data(), host * 2.0)
+    t.copy_from_numpy(host * 0 + 1, blocking=True)
+    assert np.all(t.data() == 1.0)
+
+
+def test_data_parallel_two_gpus_tracks_oracle():
+    """N=2 on real GPUs (NCCL over NVLink): tools/dp_parity.py under torchrun; skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "dp_parity.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DP PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_data_parallel_world1_is_identity(dev):
     """DataParallel with one rank: registration + sync are no-ops on the numbers (the N>1 path runs under torchrun)."""
     ws, bs = W.mlp_init(2, 128, seed=51)

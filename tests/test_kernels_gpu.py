@@ -250,11 +250,12 @@ def test_transpose_equal(ctx):
 
 # ------------------------------------------------------------------ conv lowering
 @pytest.mark.parametrize("B,C,H,W,k,s,p", [(1, 1, 5, 5, 3, 1, 0), (2, 3, 8, 7, 3, 2, 1), (4, 1, 28, 28, 5, 1, 0), (3, 2, 9, 9, 2, 2, 0),
-                                           (2, 2, 6, 6, 3, 1, 2), (1, 3, 24, 24, 3, 1, 0)])
+                                           (2, 2, 6, 6, 3, 1, 2), (1, 3, 24, 24, 3, 1, 0), (300, 1, 28, 28, 5, 1, 0), (5, 2, 11, 13, 4, 3, 2),
+                                           (2, 1, 230, 230, 3, 1, 0)])  # the last sample does not fit in shared memory: generic kernels
 def test_im2col_col2im(ctx, B, C, H, W, k, s, p):
     rng = np.random.default_rng(B + C + H + k)
     im = rnd(rng, B, C, H, W)
-    want = O.im2col(im, k, s, p)
+    want = O.im2col(im, k, s, p) if im.size < 20000 else O.im2col_fast(im, k, s, p)
     ho, wo = O.conv_out_hw(H, W, k, s, p)
     dim, dcol = ctx.to_device(im), ctx.empty(want.size)
     ctx.call("agrs_im2col_f32", dim.ptr, B, C, H, W, k, s, p, dcol.ptr)
