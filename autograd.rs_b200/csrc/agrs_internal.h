@@ -30,6 +30,9 @@ struct agrs_ctx {
   float* scratch = nullptr;
   size_t scratch_bytes = 0;
   unsigned int* counter = nullptr;
+  // per-output-block completion counters of the one-launch column sum (zero between launches: the last block resets its own)
+  unsigned int* tickets = nullptr;
+  size_t tickets_n = 0;
   // large workspace for split-K partials, grown on demand
   float* workspace = nullptr;
   size_t workspace_bytes = 0;

@@ -64,19 +64,26 @@ __global__ void __launch_bounds__(256) k_col2im(const float* __restrict__ col, i
 // moves as full 16-byte coalesced vectors with no per-element 64-bit div/mod.  The image (im2col) or the col block
 // (col2im) of ONE sample is staged in shared memory; the scattered side of the index map is then a shared-memory gather
 // (row pitch K = C*k*k floats: odd for the LeNet shape, so bank-conflict free).
-__global__ void __launch_bounds__(256) k_im2col_tile(const float* __restrict__ im, int B, int C, int H, int W, int k, int s, int p, int Ho,
-                                                     int Wo, float* __restrict__ col, int vec_in, int vec_out) {
+// PAD = false: every tap is inside the image (pad == 0), no bounds checks.  Index arithmetic is incremental: a thread's
+// consecutive float4 are kTileThreads*4 output elements apart, so (patch row y, patch column x, tap q) advance by constant
+// steps with carries -- no division in the loop.
+constexpr int kTileThreads = 512;
+
+template <bool PAD>
+__global__ void __launch_bounds__(kTileThreads) k_im2col_tile(const float* __restrict__ im, int B, int C, int H, int W, int k, int s, int p,
+                                                              int Ho, int Wo, float* __restrict__ col, int vec_in, int vec_out) {
   extern __shared__ float sm[];
   const int n_im = C * H * W, kk = k * k, K = C * kk, P = Ho * Wo, per = P * K;
-  int* toff = reinterpret_cast<int*>(sm + ((n_im + 3) & ~3));  // per tap q: channel offset c*H*W, row i, column j
-  int* ti = toff + K;
-  int* tj = ti + K;
+  int* trel = reinterpret_cast<int*>(sm + ((n_im + 3) & ~3));  // per tap q: offset of the tap relative to the patch origin
+  int* tij = trel + K;                                         // (i << 16) | j, for the bounds checks of padded convolutions
   for (int q = threadIdx.x; q < K; q += blockDim.x) {
-    const int c = q / kk, r = q - c * kk, i = r / k;
-    toff[q] = c * H * W;
-    ti[q] = i;
-    tj[q] = r - i * k;
+    const int c = q / kk, r = q - c * kk, i = r / k, j = r - i * k;
+    trel[q] = c * H * W + i * W + j;
+    tij[q] = (i << 16) | j;
   }
+  // per-iteration step of a thread's first element: blockDim*4 elements = dP patches + dq taps; dP patches = dY rows + dX columns
+  const int step = blockDim.x * 4;
+  const int dP = step / K, dq = step - dP * K, dY = dP / Wo, dX = dP - dY * Wo;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();  // table built / previous sample fully consumed
     const float* src = im + int64_t(b) * n_im;
@@ -88,42 +95,57 @@ __global__ void __launch_bounds__(256) k_im2col_tile(const float* __restrict__ i
     __syncthreads();
     float* dst = col + int64_t(b) * per;
     if (vec_out) {
+      const int o0 = 4 * threadIdx.x;
+      int pp = o0 / K, q0 = o0 - pp * K;
+      int y0 = pp / Wo, x0 = pp - y0 * Wo;
       for (int o4 = threadIdx.x; o4 < per / 4; o4 += blockDim.x) {
-        const int o = 4 * o4;
-        int pp = o / K, q = o - pp * K;
-        int y = pp / Wo, x = pp - y * Wo;
+        int q = q0, x = x0, y = y0;
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int h = y * s - p + ti[q], w = x * s - p + tj[q];
-          v[e] = (h >= 0 && h < H && w >= 0 && w < W) ? sm[toff[q] + h * W + w] : 0.f;
+          if (PAD) {
+            const int ij = tij[q], h = y * s - p + (ij >> 16), w = x * s - p + (ij & 0xFFFF);
+            v[e] = (h >= 0 && h < H && w >= 0 && w < W) ? sm[(y * s - p) * W + (x * s - p) + trel[q]] : 0.f;
+          } else {
+            v[e] = sm[(y * W + x) * s + trel[q]];
+          }
           if (++q == K) {
             q = 0;
             if (++x == Wo) { x = 0; ++y; }
           }
         }
-        reinterpret_cast<float4*>(dst)[o4] = make_float4(v[0], v[1], v[2], v[3]);
+        __stcs(reinterpret_cast<float4*>(dst) + o4, make_float4(v[0], v[1], v[2], v[3]));
+        q0 += dq;
+        int carry = q0 >= K;
+        q0 -= carry ? K : 0;
+        x0 += dX + carry;
+        y0 += dY;
+        while (x0 >= Wo) { x0 -= Wo; ++y0; }
       }
     } else {
       for (int o = threadIdx.x; o < per; o += blockDim.x) {
         const int pp = o / K, q = o - pp * K, y = pp / Wo, x = pp - y * Wo;
-        const int h = y * s - p + ti[q], w = x * s - p + tj[q];
-        dst[o] = (h >= 0 && h < H && w >= 0 && w < W) ? sm[toff[q] + h * W + w] : 0.f;
+        const int ij = tij[q], h = y * s - p + (ij >> 16), w = x * s - p + (ij & 0xFFFF);
+        dst[o] = (h >= 0 && h < H && w >= 0 && w < W) ? sm[(y * s - p) * W + (x * s - p) + trel[q]] : 0.f;
       }
     }
   }
 }
 
-// same summation order as k_col2im (increasing patch index), reading the sample's col block from shared memory
-__global__ void __launch_bounds__(256) k_col2im_tile(const float* __restrict__ col, int B, int C, int Hi, int Wi, int k, int s, int Ho, int Wo,
-                                                     float* __restrict__ im, int vec_in) {
+// same summation order as k_col2im (increasing patch index), reading the sample's col block from shared memory.
+// The block is staged with cp.async (16-byte LDGSTS, no register round trip, every thread's copies in flight at once).
+__global__ void __launch_bounds__(kTileThreads) k_col2im_tile(const float* __restrict__ col, int B, int C, int Hi, int Wi, int k, int s, int Ho,
+                                                              int Wo, float* __restrict__ im, int vec_in) {
   extern __shared__ float sm[];
   const int kk = k * k, K = C * kk, P = Ho * Wo, per = P * K, n_im = C * Hi * Wi;
+  const uint32_t sm_addr = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
     const float* src = col + int64_t(b) * per;
     if (vec_in) {
-      for (int t = threadIdx.x; t < per / 4; t += blockDim.x) reinterpret_cast<float4*>(sm)[t] = __ldg(reinterpret_cast<const float4*>(src) + t);
+      for (int t = threadIdx.x; t < per / 4; t += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sm_addr + 16u * t), "l"(src + 4 * t) : "memory");
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     } else {
       for (int t = threadIdx.x; t < per; t += blockDim.x) sm[t] = __ldg(src + t);
     }
@@ -134,17 +156,26 @@ __global__ void __launch_bounds__(256) k_col2im_tile(const float* __restrict__ c
       int t = idx / Wi;
       const int h = t % Hi, c = t / Hi;
       float acc = 0.f;
-      for (int i = k - 1; i >= 0; --i) {
-        const int hy = h - i;
-        if (hy < 0 || hy % s) continue;
-        const int y = hy / s;
-        if (y >= Ho) continue;
-        for (int j = k - 1; j >= 0; --j) {
-          const int wx = w - j;
-          if (wx < 0 || wx % s) continue;
-          const int x = wx / s;
-          if (x >= Wo) continue;
-          acc += sm[(y * Wo + x) * K + c * kk + i * k + j];
+      if (s == 1) {  // unit stride: taps i in [h-Ho+1, h] and j in [w-Wo+1, w], clipped to the kernel
+        const int i_hi = h < k - 1 ? h : k - 1, i_lo = h - (Ho - 1) > 0 ? h - (Ho - 1) : 0;
+        const int j_hi = w < k - 1 ? w : k - 1, j_lo = w - (Wo - 1) > 0 ? w - (Wo - 1) : 0;
+        for (int i = i_hi; i >= i_lo; --i) {
+          const float* row = sm + ((h - i) * Wo + w) * K + c * kk + i * k;
+          for (int j = j_hi; j >= j_lo; --j) acc += row[j - j * K];  // patch (h-i, w-j), tap (i, j)
+        }
+      } else {
+        for (int i = k - 1; i >= 0; --i) {
+          const int hy = h - i;
+          if (hy < 0 || hy % s) continue;
+          const int y = hy / s;
+          if (y >= Ho) continue;
+          for (int j = k - 1; j >= 0; --j) {
+            const int wx = w - j;
+            if (wx < 0 || wx % s) continue;
+            const int x = wx / s;
+            if (x >= Wo) continue;
+            acc += sm[(y * Wo + x) * K + c * kk + i * k + j];
+          }
         }
       }
       dst[idx] = acc;
@@ -180,13 +211,20 @@ int agrs_im2col_f32(agrs_ctx* ctx, const float* im, int64_t B, int64_t C, int64_
   AGRS_REQUIRE(ctx, im && col, AGRS_ERR_INVALID, "agrs_im2col_f32: null pointer");
   AGRS_REQUIRE(ctx, C * k * k < (1LL << 31) && Ho * Wo < (1LL << 31), AGRS_ERR_UNSUPPORTED, "agrs_im2col_f32: extent overflow");
   const int64_t n_im = C * H * W, per = Ho * Wo * C * k * k;
-  const size_t smem = size_t(((n_im + 3) & ~int64_t(3)) + 3 * C * k * k) * sizeof(float);
+  const size_t smem = size_t(((n_im + 3) & ~int64_t(3)) + 2 * C * k * k) * sizeof(float);
   if (smem <= kTileSmemMax && per < (1LL << 30) && B < (1LL << 31)) {
-    AGRS_CUDA(ctx, cudaFuncSetAttribute(k_im2col_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));
     const int vec_in = (n_im % 4 == 0) && agrs_aligned16(im), vec_out = (per % 4 == 0) && agrs_aligned16(col);
-    const int64_t cap = int64_t(ctx->sm_count) * 8;
-    k_im2col_tile<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, int(B), int(C), int(H), int(W), int(k), int(stride), int(pad),
-                                                                          int(Ho), int(Wo), col, vec_in, vec_out);
+    const int64_t cap = int64_t(ctx->sm_count) * 4;
+    const unsigned grid = unsigned(B < cap ? B : cap);
+    if (pad > 0) {
+      AGRS_CUDA(ctx, cudaFuncSetAttribute(k_im2col_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));
+      k_im2col_tile<true><<<grid, kTileThreads, smem, ctx->stream>>>(im, int(B), int(C), int(H), int(W), int(k), int(stride), int(pad), int(Ho),
+                                                                    int(Wo), col, vec_in, vec_out);
+    } else {
+      AGRS_CUDA(ctx, cudaFuncSetAttribute(k_im2col_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));
+      k_im2col_tile<false><<<grid, kTileThreads, smem, ctx->stream>>>(im, int(B), int(C), int(H), int(W), int(k), int(stride), int(pad), int(Ho),
+                                                                     int(Wo), col, vec_in, vec_out);
+    }
   } else {
     k_im2col<<<grid1d(ctx, total), 256, 0, ctx->stream>>>(im, total, int(C), int(H), int(W), int(k), int(stride), int(pad), int(Ho), int(Wo), col);
   }
@@ -207,8 +245,8 @@ int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t C, int64
   if (smem <= kTileSmemMax && C * Hi * Wi < (1LL << 30) && B < (1LL << 31)) {
     AGRS_CUDA(ctx, cudaFuncSetAttribute(k_col2im_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));
     const int vec_in = (per % 4 == 0) && agrs_aligned16(col);
-    const int64_t cap = int64_t(ctx->sm_count) * 8;
-    k_col2im_tile<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(col, int(B), int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho),
+    const int64_t cap = int64_t(ctx->sm_count) * 4;
+    k_col2im_tile<<<unsigned(B < cap ? B : cap), kTileThreads, smem, ctx->stream>>>(col, int(B), int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho),
                                                                           int(Wo), im_out, vec_in);
   } else {
     k_col2im<<<grid1d(ctx, total), 256, 0, ctx->stream>>>(col, total, int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho), int(Wo), im_out);

@@ -72,6 +72,7 @@ int agrs_ctx_destroy(agrs_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->counter) cudaFree(ctx->counter);
   if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->tickets) cudaFree(ctx->tickets);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);

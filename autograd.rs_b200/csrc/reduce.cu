@@ -106,8 +106,10 @@ int launch_reduce_all(agrs_ctx* ctx, L ld, size_t n, bool vec_ok, float scale, f
 // [chunks, outer*inner] workspace folded by k_fold_chunks (fixed order).
 template <int VEC>
 __global__ void __launch_bounds__(256) k_sum_axis_mid(const float* __restrict__ x, int64_t len, int64_t inner, int64_t chunk_len,
-                                                      float* __restrict__ part /*[chunks][outer*inner]*/, int64_t out_elems) {
+                                                      float* __restrict__ part /*[chunks][outer*inner]*/, int64_t out_elems,
+                                                      unsigned int* __restrict__ tickets, float* __restrict__ out) {
   __shared__ float sm[8][32 * VEC + 1];
+  __shared__ unsigned int s_ticket;
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int64_t col = (int64_t(blockIdx.x) * 32 + tx) * VEC;  // position inside inner
   int64_t o = blockIdx.z;
@@ -155,14 +157,23 @@ __global__ void __launch_bounds__(256) k_sum_axis_mid(const float* __restrict__ 
       part[int64_t(blockIdx.y) * out_elems + o * inner + col + v] = s;
     }
   }
-}
-
-__global__ void k_fold_chunks(const float* __restrict__ part, int64_t chunks, int64_t out_elems, float* __restrict__ out) {
-  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= out_elems) return;
-  float s = 0.f;
-  for (int64_t c = 0; c < chunks; ++c) s += part[c * out_elems + i];
-  out[i] = s;
+  if (gridDim.y == 1) return;  // single chunk: `part` is the output
+  // One launch: the LAST chunk-block of this column group to finish folds the partials, always in chunk order
+  // (deterministic), and resets the ticket for the next launch.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[o * gridDim.x + blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
+  const int64_t c0 = int64_t(blockIdx.x) * 32 * VEC;
+  for (int t = threadIdx.x; t < 32 * VEC; t += blockDim.x) {
+    if (c0 + t >= inner) break;
+    float s = 0.f;
+    for (unsigned c = 0; c < gridDim.y; ++c) s += __ldcg(part + int64_t(c) * out_elems + o * inner + c0 + t);
+    out[o * inner + c0 + t] = s;
+  }
+  if (threadIdx.x == 0) tickets[o * gridDim.x + blockIdx.x] = 0;
 }
 
 // ---- inner == 1 (sum over the last axis): one warp per output row for long rows, one thread for short ----
@@ -257,16 +268,22 @@ int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len,
     if (rc) return rc;
     part = ctx->workspace;
   }
+  if (chunks > 1 && size_t(gx * outer) > ctx->tickets_n) {
+    AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->tickets) AGRS_CUDA(ctx, cudaFree(ctx->tickets));
+    ctx->tickets = nullptr;
+    ctx->tickets_n = 0;
+    size_t n = size_t(gx * outer) < 4096 ? 4096 : size_t(gx * outer);
+    AGRS_CUDA(ctx, cudaMalloc(&ctx->tickets, n * sizeof(unsigned int)));
+    AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, n * sizeof(unsigned int), ctx->stream));
+    ctx->tickets_n = n;
+  }
   dim3 grid((unsigned)gx, (unsigned)chunks, (unsigned)outer);
   if (vec)
-    k_sum_axis_mid<4><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems);
+    k_sum_axis_mid<4><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems, ctx->tickets, out);
   else
-    k_sum_axis_mid<1><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems);
+    k_sum_axis_mid<1><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems, ctx->tickets, out);
   AGRS_LAUNCHED(ctx);
-  if (chunks > 1) {
-    k_fold_chunks<<<unsigned((out_elems + 255) / 256), 256, 0, ctx->stream>>>(part, chunks, out_elems, out);
-    AGRS_LAUNCHED(ctx);
-  }
   return AGRS_OK;
 }
 
