@@ -18,7 +18,7 @@ OK = 0
 ADD, SUB, MUL = 0, 1, 2
 SMUL, SDIV, SRSUB, SADD = 0, 1, 2, 3
 BCAST_TRAILING, BCAST_LEADING = 0, 1
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SKINNY = 0, 1, 2, 3
 TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK, TUNE_TC_2CTA = 0, 1, 2, 3, 4
 
 _lib = None
@@ -64,6 +64,10 @@ def lib():
             "agrs_set_gemm_path": [vp, i32],
             "agrs_last_gemm_path": [vp],
             "agrs_set_tuning": [vp, i32, i64],
+            "agrs_capture_begin": [vp],
+            "agrs_capture_end": [vp, C.POINTER(vp)],
+            "agrs_graph_launch": [vp, vp, i32],
+            "agrs_graph_destroy": [vp, vp],
             "agrs_timer_begin": [vp],
             "agrs_timer_end": [vp, C.POINTER(f32)],
             "agrs_profile_enable": [vp, i32],
@@ -104,6 +108,8 @@ def lib():
         L.agrs_stream.restype = vp
         L.agrs_launch_count.argtypes = [vp]
         L.agrs_launch_count.restype = C.c_uint64
+        L.agrs_graph_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.agrs_graph_info.restype = i32
         L.agrs_version.argtypes = []
         L.agrs_version.restype = C.c_char_p
         _lib = L

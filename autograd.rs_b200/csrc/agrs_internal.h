@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "agrs.h"
@@ -39,6 +40,11 @@ struct agrs_ctx {
   // live GEMM timing (agrs_profile_*): event pairs recorded around launches while enabled
   struct ProfRec { cudaEvent_t start, stop; double flops; int path; };
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;  // agrs_timer_*
+  // agrs_capture_*: while capturing, allocations made inside the capture are tracked; frees of older buffers are deferred
+  bool capturing = false;
+  std::unordered_set<void*> capture_allocs;
+  std::vector<void*> deferred_frees;
+  uint64_t launches_at_capture = 0;
   cudaStream_t copy_stream = nullptr;                // agrs_upload_prefetch
   cudaEvent_t copy_ready = nullptr, copy_done = nullptr;
   bool profiling = false;
@@ -73,6 +79,12 @@ int agrs_fail(agrs_ctx* ctx, int code, const char* fmt, ...);
     AGRS_CUDA((ctx), cudaPeekAtLastError());      \
   } while (0)
 
+// entry points that block or touch the device outside the stream cannot run while the stream is being captured
+#define AGRS_NOT_CAPTURING(ctx, what)                                                                         \
+  do {                                                                                                        \
+    if ((ctx)->capturing) return agrs_fail((ctx), AGRS_ERR_UNSUPPORTED, "%s is not allowed while a CUDA graph is being captured", what); \
+  } while (0)
+
 #define AGRS_REQUIRE(ctx, cond, code, ...)                  \
   do {                                                      \
     if (!(cond)) return agrs_fail((ctx), (code), __VA_ARGS__); \
@@ -90,5 +102,9 @@ int agrs_gemm_tc(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, in
 
 int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
                       int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
+
+bool agrs_gemm_skinny_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K);
+int agrs_gemm_skinny(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                     const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias);
 
 static inline bool agrs_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -88,12 +88,103 @@ const char* agrs_last_error(agrs_ctx* ctx) { return ctx ? ctx->err.c_str() : "nu
 
 int agrs_sync(agrs_ctx* ctx) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_sync");
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AGRS_OK;
+}
+
+struct agrs_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t kernel_nodes = 0, total_nodes = 0;
+  uint64_t launches_per_replay = 0;  // kernels this library launched inside the capture
+};
+
+int agrs_capture_begin(agrs_ctx* ctx) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_capture_begin");
+  AGRS_REQUIRE(ctx, !ctx->profiling, AGRS_ERR_UNSUPPORTED, "agrs_capture_begin: disable agrs_profile_enable first");
+  AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  AGRS_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true;
+  ctx->capture_allocs.clear();
+  ctx->deferred_frees.clear();
+  ctx->launches_at_capture = ctx->launches;
+  return AGRS_OK;
+}
+
+int agrs_capture_end(agrs_ctx* ctx, agrs_graph** out) {
+  if (!ctx) return AGRS_ERR_INVALID;
+  AGRS_REQUIRE(ctx, ctx->capturing, AGRS_ERR_INVALID, "agrs_capture_end without agrs_capture_begin");
+  AGRS_REQUIRE(ctx, out, AGRS_ERR_INVALID, "agrs_capture_end: null out");
+  *out = nullptr;
+  ctx->capturing = false;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+  // buffers that predate the capture and were dropped inside it
+  for (void* p : ctx->deferred_frees) cudaFreeAsync(p, ctx->stream);
+  ctx->deferred_frees.clear();
+  ctx->capture_allocs.clear();
+  if (e != cudaSuccess || !g) {
+    cudaGetLastError();
+    if (ctx->sticky) return ctx->sticky;  // the capture was already broken by a failing call: keep its message
+    return agrs_fail(ctx, AGRS_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+  }
+  agrs_graph* gr = new agrs_graph();
+  gr->graph = g;
+  gr->launches_per_replay = ctx->launches - ctx->launches_at_capture;
+  size_t n = 0;
+  if (cudaGraphGetNodes(g, nullptr, &n) == cudaSuccess && n) {
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(g, nodes.data(), &n) == cudaSuccess) {
+      gr->total_nodes = n;
+      for (auto nd : nodes) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) gr->kernel_nodes++;
+      }
+    }
+  }
+  // buffers allocated in the graph and still owned by a tensor when the capture ended are released by the graph itself at
+  // the next replay (and re-allocated at the same address)
+  e = cudaGraphInstantiateWithFlags(&gr->exec, g, cudaGraphInstantiateFlagAutoFreeOnLaunch);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(g);
+    delete gr;
+    cudaGetLastError();
+    return agrs_fail(ctx, AGRS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  }
+  *out = gr;
+  return AGRS_OK;
+}
+
+int agrs_graph_launch(agrs_ctx* ctx, agrs_graph* graph, int times) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_graph_launch");
+  AGRS_REQUIRE(ctx, graph && graph->exec && times >= 0, AGRS_ERR_INVALID, "agrs_graph_launch: bad arguments");
+  for (int i = 0; i < times; ++i) AGRS_CUDA(ctx, cudaGraphLaunch(graph->exec, ctx->stream));
+  ctx->launches += graph->launches_per_replay * uint64_t(times);
+  return AGRS_OK;
+}
+
+int agrs_graph_destroy(agrs_ctx* ctx, agrs_graph* graph) {
+  if (!graph) return AGRS_OK;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (graph->exec) cudaGraphExecDestroy(graph->exec);
+  if (graph->graph) cudaGraphDestroy(graph->graph);
+  delete graph;
+  return AGRS_OK;
+}
+
+int agrs_graph_info(agrs_graph* graph, uint64_t* kernel_nodes, uint64_t* total_nodes) {
+  if (!graph) return AGRS_ERR_INVALID;
+  if (kernel_nodes) *kernel_nodes = graph->kernel_nodes;
+  if (total_nodes) *total_nodes = graph->total_nodes;
   return AGRS_OK;
 }
 
 int agrs_timer_begin(agrs_ctx* ctx) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_timer_begin");
   if (!ctx->timer_a) {
     AGRS_CUDA(ctx, cudaEventCreate(&ctx->timer_a));
     AGRS_CUDA(ctx, cudaEventCreate(&ctx->timer_b));
@@ -104,6 +195,7 @@ int agrs_timer_begin(agrs_ctx* ctx) {
 
 int agrs_timer_end(agrs_ctx* ctx, float* ms) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_timer_end");
   AGRS_REQUIRE(ctx, ms && ctx->timer_a, AGRS_ERR_INVALID, "agrs_timer_end without agrs_timer_begin");
   AGRS_CUDA(ctx, cudaEventRecord(ctx->timer_b, ctx->stream));
   AGRS_CUDA(ctx, cudaEventSynchronize(ctx->timer_b));
@@ -136,12 +228,21 @@ int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
   if (nbytes == 0) nbytes = 4;  // empty tensors still get a distinct address
   AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
   AGRS_CUDA(ctx, cudaMallocFromPoolAsync(out, nbytes, ctx->pool, ctx->stream));
+  if (ctx->capturing) ctx->capture_allocs.insert(*out);
   return AGRS_OK;
 }
 
 int agrs_free(agrs_ctx* ctx, void* ptr) {
   AGRS_CHECK_CTX(ctx);
   if (!ptr) return AGRS_OK;
+  if (ctx->capturing) {
+    auto it = ctx->capture_allocs.find(ptr);
+    if (it == ctx->capture_allocs.end()) {  // allocated before the capture: a graph cannot free it; release it when the capture ends
+      ctx->deferred_frees.push_back(ptr);
+      return AGRS_OK;
+    }
+    ctx->capture_allocs.erase(it);
+  }
   AGRS_CUDA(ctx, cudaFreeAsync(ptr, ctx->stream));
   return AGRS_OK;
 }
@@ -171,6 +272,7 @@ int agrs_upload(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
 int agrs_download(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
   AGRS_CHECK_CTX(ctx);
   if (nbytes == 0) return AGRS_OK;
+  AGRS_NOT_CAPTURING(ctx, "agrs_download");
   AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_download: null pointer");
   AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -211,7 +313,7 @@ int agrs_copy(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
 
 int agrs_set_gemm_path(agrs_ctx* ctx, int path) {
   AGRS_CHECK_CTX(ctx);
-  AGRS_REQUIRE(ctx, path >= AGRS_GEMM_AUTO && path <= AGRS_GEMM_TCGEN05, AGRS_ERR_INVALID, "unknown gemm path %d", path);
+  AGRS_REQUIRE(ctx, path >= AGRS_GEMM_AUTO && path <= AGRS_GEMM_SKINNY, AGRS_ERR_INVALID, "unknown gemm path %d", path);
   ctx->gemm_path = path;
   return AGRS_OK;
 }
@@ -222,6 +324,7 @@ int agrs_last_gemm_path(agrs_ctx* ctx) { return ctx ? ctx->last_gemm_path : 0; }
 
 int agrs_ensure_workspace(agrs_ctx* ctx, size_t nbytes) {
   if (ctx->workspace_bytes >= nbytes) return AGRS_OK;
+  AGRS_NOT_CAPTURING(ctx, "growing the split-K workspace (run one ordinary step before capturing)");
   // growing is rare (first split-K call of a given size); stream-sync so nothing in flight uses the old block
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->workspace) AGRS_CUDA(ctx, cudaFree(ctx->workspace));

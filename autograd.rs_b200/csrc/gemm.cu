@@ -59,7 +59,16 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
     // a 128xBN tile per SM: tiny or very skinny problems leave the tensor cores idle and pay the pipeline fill
     use_tc = eligible && M >= 64 && N >= 32 && K >= 32 && (M * N) * K >= ctx->tc_min_flops;
   }
-  ctx->last_gemm_path = use_tc ? AGRS_GEMM_TCGEN05 : AGRS_GEMM_SIMT;
+  const bool skinny_ok = K > 0 && agrs_gemm_skinny_eligible(transA, transB, M, N, K);
+  bool use_skinny = false;
+  if (ctx->gemm_path == AGRS_GEMM_SKINNY) {
+    AGRS_REQUIRE(ctx, skinny_ok, AGRS_ERR_UNSUPPORTED, "agrs_gemm_f32: skinny path forced but the shape is not skinny (N <= 32, see gemm_skinny.cu)");
+    use_skinny = true;
+    use_tc = false;
+  } else if (ctx->gemm_path == AGRS_GEMM_AUTO && !use_tc) {
+    use_skinny = skinny_ok;
+  }
+  ctx->last_gemm_path = use_tc ? AGRS_GEMM_TCGEN05 : (use_skinny ? AGRS_GEMM_SKINNY : AGRS_GEMM_SIMT);
   agrs_ctx::ProfRec rec{};
   if (ctx->profiling) {
     rec.path = ctx->last_gemm_path;
@@ -70,7 +79,8 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
     AGRS_CUDA(ctx, cudaEventRecord(rec.start, ctx->stream));
   }
   const bool pair = use_tc && ctx->tc_2cta && M > 128;
-  int rc = pair   ? agrs_gemm_tc_2cta(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
+  int rc = use_skinny ? agrs_gemm_skinny(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
+         : pair   ? agrs_gemm_tc_2cta(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
          : use_tc ? agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
                   : agrs_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
   if (ctx->profiling) {
@@ -82,12 +92,14 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
 
 int agrs_profile_enable(agrs_ctx* ctx, int on) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_profile_enable");
   ctx->profiling = on != 0;
   return AGRS_OK;
 }
 
 int agrs_profile_gemm(agrs_ctx* ctx, int path, uint64_t* launches, double* total_ms, double* total_flops) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_profile_gemm");
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   uint64_t n = 0;
   double ms = 0.0, fl = 0.0;

@@ -1,0 +1,276 @@
+// HBM-bound f32 GEMMs with a skinny output: the Conv2D lowering and the narrow Linear layers of the LeNet-style
+// configuration (reference operators.rs:378-379, :422, :445 and :144, :160 at N = 6, 10, 25).  The generic 64x64-tile SIMT
+// kernel wastes 90 % of its tile on them; these kernels stream the big operand once, coalesced, and keep the small one on chip.
+//   rows    C[M,N] = A[M,K] . op(B)      K <= 64, N <= 32, M large       one thread per output row      (conv forward, dxcol)
+//   dot     C[M,N] = A[M,K] . op(B)      N <= 16, K long                 one warp per output row        (Linear 3456 -> 10)
+//   tn      C[M,N] = A[K,M]^T . B[K,N]   N <= 16, any M, K               split-K over blocks, fixed-order fold   (dW: conv, Linear)
+// Plain FFMA in f32; summation order is fixed (deterministic).
+#include "agrs_internal.h"
+
+namespace {
+
+// ------------------------------------------------------------------ rows: one thread per output row
+// Block = 256 rows.  The A tile [256, K] is staged through shared memory with coalesced loads (row pitch K|1: odd, so thread t
+// reading row t is bank-conflict free); B (K x N, padded to NT columns) and the bias sit in shared memory and are read as
+// broadcasts; the C tile goes back through shared memory so the store is coalesced too.
+template <int NT>
+__global__ void __launch_bounds__(256) k_gemm_rows(int64_t M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                   int64_t ldb, int transB, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
+  extern __shared__ float sm[];
+  const int pitch = K | 1, cp = N | 1;
+  float* As = sm;                                                  // [256][pitch]; reused as Cs [256][cp]
+  float* Bs = sm + 256 * (pitch > cp ? pitch : cp);                // [K][NT]
+  float* bs = Bs + K * NT;                                         // [NT]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < K * NT; e += 256) {
+    const int k = e / NT, n = e - k * NT;
+    Bs[e] = n < N ? (transB ? B[int64_t(n) * ldb + k] : B[int64_t(k) * ldb + n]) : 0.f;
+  }
+  for (int n = tid; n < NT; n += 256) bs[n] = (bias && n < N) ? bias[n] : 0.f;
+  const int64_t tiles = (M + 255) / 256;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t m0 = tile * 256;
+    const int rows = int(M - m0 < 256 ? M - m0 : 256);
+    __syncthreads();  // Bs ready / previous tile's Cs drained
+    if (lda == K) {   // the tile is one contiguous run of rows*K floats
+      const float* src = A + m0 * K;
+      const int total = rows * K;
+      if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        for (int e4 = tid; e4 < total / 4; e4 += 256) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + e4);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = 4 * e4 + j, r = e / K;
+            As[r * pitch + (e - r * K)] = vv[j];
+          }
+        }
+        for (int e = (total / 4) * 4 + tid; e < total; e += 256) {
+          const int r = e / K;
+          As[r * pitch + (e - r * K)] = src[e];
+        }
+      } else {
+        for (int e = tid; e < total; e += 256) {
+          const int r = e / K;
+          As[r * pitch + (e - r * K)] = __ldcs(src + e);
+        }
+      }
+    } else {
+      for (int e = tid; e < rows * K; e += 256) {
+        const int r = e / K, k = e - r * K;
+        As[r * pitch + k] = A[(m0 + r) * lda + k];
+      }
+    }
+    __syncthreads();
+    float acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    if (tid < rows) {
+      const float* a = As + tid * pitch;
+      for (int k = 0; k < K; ++k) {
+        const float av = a[k];
+        const float4* b4 = reinterpret_cast<const float4*>(Bs + k * NT);
+#pragma unroll
+        for (int n4 = 0; n4 < NT / 4; ++n4) {
+          const float4 b = b4[n4];
+          acc[4 * n4] = fmaf(av, b.x, acc[4 * n4]);
+          acc[4 * n4 + 1] = fmaf(av, b.y, acc[4 * n4 + 1]);
+          acc[4 * n4 + 2] = fmaf(av, b.z, acc[4 * n4 + 2]);
+          acc[4 * n4 + 3] = fmaf(av, b.w, acc[4 * n4 + 3]);
+        }
+      }
+    }
+    __syncthreads();  // everybody is done reading As
+    float* Cs = As;
+    if (tid < rows) {
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (n < N) Cs[tid * cp + n] = acc[n] + bs[n];
+    }
+    __syncthreads();
+    if (ldc == N) {
+      float* dst = C + m0 * N;
+      for (int e = tid; e < rows * N; e += 256) {
+        const int r = e / N;
+        __stcs(dst + e, Cs[r * cp + (e - r * N)]);
+      }
+    } else {
+      for (int e = tid; e < rows * N; e += 256) {
+        const int r = e / N, n = e - r * N;
+        C[(m0 + r) * ldc + n] = Cs[r * cp + n];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dot: one warp per output row, K long
+template <int NT>
+__global__ void __launch_bounds__(256) k_gemm_dot(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                  int64_t ldb, int transB, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t m = warp; m < M; m += nwarps) {
+    const float* a = A + m * lda;
+    float acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+    for (int64_t k = lane; k < K; k += 32) {
+      const float av = __ldcs(a + k);
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (n < N) acc[n] = fmaf(av, transB ? __ldg(B + int64_t(n) * ldb + k) : __ldg(B + k * ldb + n), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      float v = acc[n];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == n && n < N) C[m * ldc + n] = v + (bias ? bias[n] : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ tn: C = A^T . B with A stored [K, M], split over K
+// Block = 32 columns of A (m) x 8 k-lanes; grid.y tiles M, grid.x splits K.  Reads of A are coalesced along m, the matching row
+// of B (N <= 16 floats) is a broadcast.  Partials [splits][M*N] are folded in split order by the last block of each m-tile.
+template <int NT>
+__global__ void __launch_bounds__(256) k_gemm_tn(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                 int64_t ldb, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int64_t k_per_split,
+                                                 float* __restrict__ part, unsigned int* __restrict__ tickets) {
+  __shared__ float red[8][32][NT + 1];
+  __shared__ unsigned int s_ticket;
+  const int mx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int64_t m = int64_t(blockIdx.y) * 32 + mx;
+  const int64_t k0 = int64_t(blockIdx.x) * k_per_split, k1 = k0 + k_per_split < K ? k0 + k_per_split : K;
+  float acc[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) acc[n] = 0.f;
+  if (m < M) {
+    for (int64_t k = k0 + ky; k < k1; k += 8) {
+      const float av = __ldcs(A + k * lda + m);
+      const float* b = B + k * ldb;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (n < N) acc[n] = fmaf(av, __ldg(b + n), acc[n]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) red[ky][mx][n] = acc[n];
+  __syncthreads();
+  const int splits = gridDim.x;
+  // 32 x N outputs of this block: thread (mx, n = ky, ky+8, ..) folds the 8 k-lanes in order
+  for (int n = ky; n < N; n += 8) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][mx][n];
+    if (m < M) {
+      if (splits == 1) C[m * ldc + n] = s + (bias ? bias[n] : 0.f);
+      else part[(int64_t(blockIdx.x) * M + m) * N + n] = s;
+    }
+  }
+  if (splits == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[blockIdx.y], 1u);
+  __syncthreads();
+  if (s_ticket != unsigned(splits - 1)) return;
+  __threadfence();
+  // fold the split partials: k-lane ky sums the splits z = ky, ky+8, .. (fixed assignment), then the 8 lanes fold in order
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    float s = 0.f;
+    if (n < N && m < M)
+      for (int z = ky; z < splits; z += 8) s += __ldcg(part + (int64_t(z) * M + m) * N + n);
+    red[ky][mx][n] = s;
+  }
+  __syncthreads();
+  for (int n = ky; n < N; n += 8) {
+    if (m >= M) break;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][mx][n];
+    C[m * ldc + n] = s + (bias ? bias[n] : 0.f);
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.y] = 0;
+}
+
+int ensure_tickets(agrs_ctx* ctx, size_t need) {
+  if (need <= ctx->tickets_n) return AGRS_OK;
+  AGRS_NOT_CAPTURING(ctx, "growing the ticket array (run one ordinary step before capturing)");
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->tickets) AGRS_CUDA(ctx, cudaFree(ctx->tickets));
+  ctx->tickets = nullptr;
+  ctx->tickets_n = 0;
+  size_t n = need < 4096 ? 4096 : need;
+  AGRS_CUDA(ctx, cudaMalloc(&ctx->tickets, n * sizeof(unsigned int)));
+  AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, n * sizeof(unsigned int), ctx->stream));
+  ctx->tickets_n = n;
+  return AGRS_OK;
+}
+
+}  // namespace
+
+bool agrs_gemm_skinny_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K) {
+  if (M < 1 || N < 1 || K < 1) return false;
+  if (transA) return !transB && N <= 16;                       // tn
+  if (K <= 64 && N <= 32 && M >= 1024) return true;            // rows
+  return N <= 16 && K > 64;                                    // dot
+}
+
+int agrs_gemm_skinny(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float* C, int64_t ldc, const float* bias) {
+  const int n = int(N);
+  if (transA) {
+    const int64_t my = (M + 31) / 32;
+    AGRS_REQUIRE(ctx, my <= 65535, AGRS_ERR_UNSUPPORTED, "agrs_gemm_skinny(tn): M too large");
+    // split K so the grid fills the machine (~4 blocks per SM), at least 64 rows of K per block
+    int64_t want = (int64_t(ctx->sm_count) * 4 + my - 1) / my, maxs = (K + 63) / 64;
+    int64_t splits = want < maxs ? want : maxs;
+    if (splits < 1) splits = 1;
+    if (splits > 2048) splits = 2048;
+    int64_t kps = (K + splits - 1) / splits;
+    kps = (kps + 7) / 8 * 8;
+    splits = (K + kps - 1) / kps;
+    float* part = nullptr;
+    if (splits > 1) {
+      int rc = agrs_ensure_workspace(ctx, size_t(splits) * size_t(M) * size_t(N) * sizeof(float));
+      if (rc) return rc;
+      rc = ensure_tickets(ctx, size_t(my));
+      if (rc) return rc;
+      part = ctx->workspace;
+    }
+    dim3 grid((unsigned)splits, (unsigned)my);
+    if (n <= 8) k_gemm_tn<8><<<grid, 256, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, C, ldc, bias, kps, part, ctx->tickets);
+    else        k_gemm_tn<16><<<grid, 256, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, C, ldc, bias, kps, part, ctx->tickets);
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
+  if (K <= 64 && N <= 32 && M >= 1024) {
+    const int k = int(K);
+    const int nt = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    const int pitch = k | 1, cp = n | 1;
+    const size_t smem = size_t(256 * (pitch > cp ? pitch : cp) + k * nt + nt) * sizeof(float);
+    const int64_t tiles = (M + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
+    const unsigned grid = unsigned(tiles < cap ? tiles : cap);
+#define AGRS_ROWS(NT_)                                                                                                             \
+  do {                                                                                                                              \
+    AGRS_CUDA(ctx, cudaFuncSetAttribute(k_gemm_rows<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));                \
+    k_gemm_rows<NT_><<<grid, 256, smem, ctx->stream>>>(M, n, k, A, lda, B, ldb, transB, C, ldc, bias);                               \
+  } while (0)
+    if (nt == 8) AGRS_ROWS(8);
+    else if (nt == 16) AGRS_ROWS(16);
+    else AGRS_ROWS(32);
+#undef AGRS_ROWS
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
+  {
+    const int64_t warps_wanted = M, cap = int64_t(ctx->sm_count) * 8 * 8;
+    const int64_t warps = warps_wanted < cap ? warps_wanted : cap;
+    const unsigned grid = unsigned((warps + 7) / 8);
+    if (n <= 8) k_gemm_dot<8><<<grid, 256, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias);
+    else        k_gemm_dot<16><<<grid, 256, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias);
+    AGRS_LAUNCHED(ctx);
+  }
+  return AGRS_OK;
+}

@@ -269,6 +269,7 @@ int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len,
     part = ctx->workspace;
   }
   if (chunks > 1 && size_t(gx * outer) > ctx->tickets_n) {
+    AGRS_NOT_CAPTURING(ctx, "growing the column-sum ticket array (run one ordinary step before capturing)");
     AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->tickets) AGRS_CUDA(ctx, cudaFree(ctx->tickets));
     ctx->tickets = nullptr;
@@ -289,6 +290,7 @@ int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len,
 
 int agrs_equal_f32(agrs_ctx* ctx, const float* a, const float* b, size_t n, int* host_equal) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_equal_f32");
   AGRS_REQUIRE(ctx, host_equal && (n == 0 || (a && b)), AGRS_ERR_INVALID, "agrs_equal_f32: null pointer");
   unsigned* flag = ctx->counter + 8;  // second cache line of the counter block
   AGRS_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(unsigned), ctx->stream));

@@ -208,6 +208,15 @@ class Device:
         self._k("agrs_profile_gemm", int(path), C.byref(n), C.byref(ms), C.byref(fl))
         return int(n.value), float(ms.value), float(fl.value)
 
+    # ---- whole-step CUDA graphs (agrs_capture_*): record one or more training steps, replay them with one driver call each
+    def capture_begin(self):
+        self._k("agrs_capture_begin")
+
+    def capture_end(self):
+        g = C.c_void_p()
+        self._k("agrs_capture_end", C.byref(g))
+        return Graph(self, g)
+
     # pinned host staging for end-to-end runs (agrs_host_alloc): returns a float32 numpy view
     def pinned_empty(self, shape):
         n = int(np.prod(shape))
@@ -218,6 +227,25 @@ class Device:
         buf = (C.c_float * max(n, 1)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=np.float32, count=n).reshape(shape)
         return arr
+
+
+class Graph:
+    """A captured sequence of training steps (agrs_graph): every kernel, memset, allocation and collective of the step,
+    replayed by the driver without the host walking the model again."""
+
+    def __init__(self, dev, handle):
+        self.dev, self._h = dev, handle
+        k, n = C.c_uint64(), C.c_uint64()
+        _capi.lib().agrs_graph_info(handle, C.byref(k), C.byref(n))
+        self.kernel_nodes, self.total_nodes = int(k.value), int(n.value)
+
+    def launch(self, times=1):
+        self.dev._k("agrs_graph_launch", self._h, int(times))
+
+    def close(self):
+        if self._h:
+            _capi.lib().agrs_graph_destroy(self.dev.ctx_handle, self._h)
+            self._h = None
 
 
 class Tensor:

@@ -89,3 +89,27 @@ class Trainer:
         self.optim.step()
         self.model.zero_grad()
         return loss
+
+    def capture(self, x, t, unroll=1, warmup=2):
+        """Record `unroll` consecutive iterations on (x, t) as ONE CUDA graph.  The host walks the model once, here; replay()
+        then costs one driver call per `unroll` steps -- what launch-bound configurations (fit_sine: ~11 tiny kernels per
+        step) need.  The warm-up steps run normally first: workspaces and the memory pool reach their steady state outside
+        the capture.  Returns the loss tensor of the last captured iteration; its buffer keeps its address across replays."""
+        dev = x.dev
+        for _ in range(warmup):
+            self.step(x, t)
+        dev.sync()
+        dev.capture_begin()
+        try:
+            loss = None
+            for _ in range(unroll):
+                loss = self.step(x, t)
+        finally:
+            graph = dev.capture_end()
+        self._graph, self._graph_loss, self._unroll = graph, loss, unroll
+        return loss
+
+    def replay(self, times=1):
+        """run `times` x `unroll` training iterations from the captured graph; returns the (device-resident) loss handle"""
+        self._graph.launch(times)
+        return self._graph_loss

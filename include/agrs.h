@@ -77,11 +77,12 @@ AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);     
  * so the reference's materialised t_clone() copies (storage.rs:84-88) never exist on the device.
  * bias != NULL fuses `+ b` of Linear::forward / Conv2D::forward (operators.rs:144, :379) into the epilogue.
  * Large aligned shapes run the TMA + tcgen05 3xTF32 kernel (f32-faithful: hi*hi + hi*lo + lo*hi);
- * everything else runs the SIMT f32 kernel.  Both are CUDA; the choice never changes semantics. */
+ * skinny outputs (N <= 32: the Conv2D lowering, Linear(3456,10)) run HBM-bound streaming kernels; everything else runs the
+ * tiled SIMT f32 kernel.  All are CUDA; the choice never changes semantics. */
 AGRS_API int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
                   const float* A, int64_t lda, const float* B, int64_t ldb,
                   float* C, int64_t ldc, const float* bias);
-enum agrs_gemm_path { AGRS_GEMM_AUTO = 0, AGRS_GEMM_SIMT = 1, AGRS_GEMM_TCGEN05 = 2 };
+enum agrs_gemm_path { AGRS_GEMM_AUTO = 0, AGRS_GEMM_SIMT = 1, AGRS_GEMM_TCGEN05 = 2, AGRS_GEMM_SKINNY = 3 /* HBM-bound kernels for N <= 32 outputs */ };
 AGRS_API int agrs_set_gemm_path(agrs_ctx* ctx, int path); /* tests/bench: force one path; TCGEN05 on unaligned operands -> AGRS_ERR_UNSUPPORTED */
 AGRS_API int agrs_last_gemm_path(agrs_ctx* ctx);          /* path the most recent agrs_gemm_f32 took */
 /* kernel tuning knobs (tests, benches, profiling); never change results beyond f32 rounding */
@@ -93,6 +94,20 @@ enum agrs_tuning_key {
   AGRS_TUNE_TC_2CTA = 4         /* 1 (default): cta_group::2 pair kernel (256x256 tiles) when M > 128; 0: always the one-CTA kernel */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
+
+/* ---- whole-step CUDA graphs (launch-bound configurations: fit_sine runs ~11 tiny kernels per step) ----
+ * Between agrs_capture_begin and agrs_capture_end every launch, memset, copy, stream-ordered alloc/free and NCCL call made on
+ * this context is RECORDED instead of run.  The graph is then replayed with agrs_graph_launch: one driver call per `times`
+ * training steps instead of one per kernel.  Rules: run at least one ordinary step first (workspaces are grown outside
+ * capture); nothing that blocks (download, sync, timer_end, equal) may be called while capturing; buffers allocated before the
+ * capture and released during it are released when the capture ends; buffers allocated during the capture keep their
+ * addresses across replays, so tensors created in the captured step (the loss) can be read after any replay. */
+typedef struct agrs_graph agrs_graph;
+AGRS_API int agrs_capture_begin(agrs_ctx* ctx);
+AGRS_API int agrs_capture_end(agrs_ctx* ctx, agrs_graph** out);
+AGRS_API int agrs_graph_launch(agrs_ctx* ctx, agrs_graph* graph, int times);
+AGRS_API int agrs_graph_destroy(agrs_ctx* ctx, agrs_graph* graph);
+AGRS_API int agrs_graph_info(agrs_graph* graph, uint64_t* kernel_nodes, uint64_t* total_nodes);
 
 /* device-side stopwatch on the context's stream (CUDA events): begin records, end records + synchronises + returns ms */
 AGRS_API int agrs_timer_begin(agrs_ctx* ctx);

@@ -422,6 +422,42 @@ def test_no_host_sync_inside_a_step(dev):
     assert t_enqueue < 0.5 * t_total, (t_enqueue, t_total)
 
 
+@pytest.mark.parametrize("unroll", [1, 5])
+def test_captured_steps_track_oracle(unroll):
+    """fit_sine with the training step recorded as a CUDA graph (agrs_capture_*): 2 ordinary warm-up steps + replays must land
+    on the same loss and weights as the oracle after the same number of iterations."""
+    d = F.Device(0)
+    try:
+        x, y = O.fit_sine_data(2000, np.float32)
+        model = W.build_mlp(d, [np.zeros((3, 1), np.float32)], [np.zeros((1, 1), np.float32)], None)
+        tr = W.Trainer(model, 1e-3)
+        X, Tt = T(d, x), T(d, y)
+        Tt.requires_grad = False
+        tr.capture(X, Tt, unroll=unroll, warmup=2)
+        assert tr._graph.kernel_nodes >= 8 * unroll
+        replays = 60
+        loss = tr.replay(replays)
+        total = 2 + replays * unroll
+        want, layers = O.mlp_train(x, y, [np.zeros((3, 1))], [np.zeros((1, 1))], None, 1e-3, total, np.float32)
+        assert abs(loss.item() - want[-1]) / want[-1] < TOL
+        scale = float(np.abs(layers[0].w.data).max())
+        got_w = model.parameters()[0].data()
+        assert np.abs(got_w - layers[0].w.data).max() < TOL * scale
+        # the engine is still usable step by step afterwards, continuing from the replayed state
+        l2 = tr.step(X, Tt).item()
+        want2, _ = O.mlp_train(x, y, [np.zeros((3, 1))], [np.zeros((1, 1))], None, 1e-3, total + 1, np.float32)
+        assert abs(l2 - want2[-1]) / want2[-1] < TOL
+        with pytest.raises(F.Panic, match="captured"):
+            d.capture_begin()
+            try:
+                X.data()  # a blocking read inside a capture is refused, not silently wrong
+            finally:
+                d.capture_end().close()
+        tr._graph.close()
+    finally:
+        d.close()
+
+
 def test_prefetch_copy_stream(dev):
     """copy-stream upload (input prefetch of the end-to-end loop): data is what was sent once the compute stream has joined"""
     rng = np.random.default_rng(61)

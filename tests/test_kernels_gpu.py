@@ -298,6 +298,39 @@ def test_gemm_simt(ctx, M, N, Kd, ta, tb):
     assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_SIMT
 
 
+# ------------------------------------------------------------------ skinny (HBM-bound) GEMMs: the LeNet / conv-lowering shapes
+@pytest.mark.parametrize("M,N,Kd,ta,tb", [
+    (20000, 6, 25, 0, 0),     # conv forward: col . K + bias      (rows kernel)
+    (20000, 25, 6, 0, 1),     # conv dxcol: g . K^T               (rows kernel, B transposed)
+    (1024, 32, 64, 0, 0), (1500, 1, 1, 0, 1), (4097, 17, 33, 0, 0), (1024, 9, 64, 0, 1),
+    (1024, 10, 3456, 0, 0),   # Linear(3456,10) forward           (dot kernel)
+    (7, 16, 65, 0, 1), (300, 3, 1000, 0, 0), (1, 1, 100, 0, 0),
+    (25, 6, 200000, 1, 0),    # conv dw: col^T . g                (tn kernel, split K + ticket fold)
+    (3456, 10, 1024, 1, 0),   # Linear dW: x^T . g                (tn kernel)
+    (33, 16, 7, 1, 0), (1, 1, 1, 1, 0), (100, 9, 64, 1, 0),
+])
+def test_gemm_skinny(ctx, M, N, Kd, ta, tb):
+    rng = np.random.default_rng(M + 7 * N + Kd)
+    for bias in (False, True):
+        gemm_case(ctx, rng, M, N, Kd, ta, tb, bias, K.GEMM_SKINNY, 1e-5)
+        assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_SKINNY
+    # AUTO takes the same path for these shapes, twice in a row (the split-K tickets reset themselves)
+    for _ in range(2):
+        gemm_case(ctx, rng, M, N, Kd, ta, tb, True, K.GEMM_AUTO, 1e-5)
+        assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_SKINNY
+
+
+def test_gemm_skinny_refuses_wide_outputs(ctx):
+    d = ctx.empty(256 * 256)
+    ctx.call("agrs_set_gemm_path", K.GEMM_SKINNY)
+    try:
+        with pytest.raises(K.AgrsError) as e:
+            ctx.call("agrs_gemm_f32", 0, 0, 256, 256, 16, d.ptr, 16, d.ptr, 256, d.ptr, 256, None)
+        assert e.value.code == 4
+    finally:
+        ctx.call("agrs_set_gemm_path", K.GEMM_AUTO)
+
+
 def test_gemm_bad_args(ctx):
     d = ctx.empty(64)
     with pytest.raises(K.AgrsError) as e:

@@ -72,6 +72,25 @@ def main():
             cw = time.perf_counter() - t0
             r.update(oracle_final_loss=want[-1], rel_err=abs(final - want[-1]) / want[-1], cpu_oracle_samples_per_s=2000 * steps / cw)
         emit(r)
+        # the same 2000 iterations replayed from a CUDA graph of 10 unrolled steps
+        model = W.build_mlp(dev, [np.zeros((3, 1), np.float32)], [np.zeros((1, 1), np.float32)], None)
+        tr = W.Trainer(model, 1e-3)
+        X, T = F.Tensor.from_numpy(dev, x), F.Tensor.from_numpy(dev, y)
+        T.requires_grad = False
+        n0 = dev.launches()
+        tr.capture(X, T, unroll=10, warmup=10)
+        dev.sync()
+        t0 = time.perf_counter()
+        loss = tr.replay((steps - 10) // 10)
+        final = loss.item()
+        wall = time.perf_counter() - t0
+        rg = {"config": "C1 fit_sine, CUDA graph of 10 steps", "steps": steps, "ms_per_step": wall * 1e3 / (steps - 10), "samples_per_s": 2000 * (steps - 10) / wall,
+              "final_loss": final, "graph_kernel_nodes": tr._graph.kernel_nodes, "graph_total_nodes": tr._graph.total_nodes,
+              "kernels_per_step": (dev.launches() - n0) / steps}
+        if a.cpu:
+            rg.update(oracle_final_loss=want[-1], rel_err=abs(final - want[-1]) / want[-1])
+        emit(rg)
+        tr._graph.close()
     if a.only in ("", "c3"):
         rng = np.random.default_rng(31)
         B = 1024
@@ -103,6 +122,15 @@ def main():
                 O.model_zero_grad(params)
             r["cpu_oracle_samples_per_s"] = B * n / (time.perf_counter() - t0)
         emit(r)
+        tr.capture(X, T, unroll=1, warmup=2)
+        dev.sync()
+        t0 = time.perf_counter()
+        loss = tr.replay(50)
+        final = loss.item()
+        wall = time.perf_counter() - t0
+        emit({"config": "C3 lenet B=1024, CUDA graph", "ms_per_step": wall * 1e3 / 50, "samples_per_s": B * 50 / wall, "final_loss": final,
+              "graph_kernel_nodes": tr._graph.kernel_nodes, "graph_total_nodes": tr._graph.total_nodes})
+        tr._graph.close()
     for name in ("mlp4096", "mlp8192"):
         if a.only not in ("", {"mlp4096": "c2", "mlp8192": "c5"}[name]):
             continue
