@@ -3,7 +3,8 @@
 // kernel wastes 90 % of its tile on them; these kernels stream the big operand once, coalesced, and keep the small one on chip.
 //   rows    C[M,N] = A[M,K] . op(B)      K <= 64, N <= 32, M large       one thread per output row      (conv forward, dxcol)
 //   dot     C[M,N] = A[M,K] . op(B)      N <= 16, K long                 one warp per output row        (Linear 3456 -> 10)
-//   tn      C[M,N] = A[K,M]^T . B[K,N]   N <= 16, any M, K               split-K over blocks, fixed-order fold   (dW: conv, Linear)
+//   tn      C[M,N] = A[K,M]^T . B[K,N]   N <= 16, any M, K               split-K over blocks, fixed-order fold   (dW of Linear)
+//   tn_small  the same with M*N <= 160 and K huge                        staged row streams, one thread per output (conv filter gradient)
 // Plain FFMA in f32; summation order is fixed (deterministic).
 #include "agrs_internal.h"
 
@@ -35,7 +36,10 @@ __global__ void __launch_bounds__(256) k_gemm_rows(int64_t M, int N, int K, cons
     if (lda == K) {   // the tile is one contiguous run of rows*K floats
       const float* src = A + m0 * K;
       const int total = rows * K;
-      if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      if (pitch == K && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {  // odd K: shared layout == global layout, plain 16-byte copy
+        for (int e4 = tid; e4 < total / 4; e4 += 256) reinterpret_cast<float4*>(As)[e4] = __ldcs(reinterpret_cast<const float4*>(src) + e4);
+        for (int e = (total / 4) * 4 + tid; e < total; e += 256) As[e] = src[e];
+      } else if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
         for (int e4 = tid; e4 < total / 4; e4 += 256) {
           const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + e4);
           const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -88,7 +92,12 @@ __global__ void __launch_bounds__(256) k_gemm_rows(int64_t M, int N, int K, cons
         if (n < N) Cs[tid * cp + n] = acc[n] + bs[n];
     }
     __syncthreads();
-    if (ldc == N) {
+    if (ldc == N && cp == N && (reinterpret_cast<uintptr_t>(C + m0 * N) & 15u) == 0) {  // odd N: plain 16-byte copy out
+      float* dst = C + m0 * N;
+      const int total = rows * N;
+      for (int e4 = tid; e4 < total / 4; e4 += 256) __stcs(reinterpret_cast<float4*>(dst) + e4, reinterpret_cast<const float4*>(Cs)[e4]);
+      for (int e = (total / 4) * 4 + tid; e < total; e += 256) dst[e] = Cs[e];
+    } else if (ldc == N) {
       float* dst = C + m0 * N;
       for (int e = tid; e < rows * N; e += 256) {
         const int r = e / N;
@@ -104,30 +113,113 @@ __global__ void __launch_bounds__(256) k_gemm_rows(int64_t M, int N, int K, cons
 }
 
 // ------------------------------------------------------------------ dot: one warp per output row, K long
+// Block = 4 warps = 4 rows.  B is walked in chunks of 512 k staged in shared memory ([512][NT+1], so lane k reading row k is
+// conflict free); every lane strides its row of A by 32 (coalesced) and keeps NT partial sums; a shuffle tree ends the row.
+constexpr int kDotChunk = 512;
 template <int NT>
-__global__ void __launch_bounds__(256) k_gemm_dot(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+__global__ void __launch_bounds__(128) k_gemm_dot(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                                                   int64_t ldb, int transB, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t m = warp; m < M; m += nwarps) {
-    const float* a = A + m * lda;
+  __shared__ float Bs[kDotChunk][NT + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t groups = (M + 3) / 4;
+  for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int64_t m = g * 4 + w;
+    const float* a = A + (m < M ? m : M - 1) * lda;
     float acc[NT];
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[n] = 0.f;
-    for (int64_t k = lane; k < K; k += 32) {
-      const float av = __ldcs(a + k);
+    for (int64_t k0 = 0; k0 < K; k0 += kDotChunk) {
+      const int kc = int(K - k0 < kDotChunk ? K - k0 : kDotChunk);
+      __syncthreads();
+      if (transB) {  // B stored [N, K]: coalesced along k
+        for (int e = threadIdx.x; e < kc * N; e += 128) {
+          const int n = e / kc, k = e - n * kc;
+          Bs[k][n] = __ldg(B + int64_t(n) * ldb + k0 + k);
+        }
+      } else {       // B stored [K, N]: rows of N floats
+        for (int e = threadIdx.x; e < kc * N; e += 128) {
+          const int k = e / N, n = e - k * N;
+          Bs[k][n] = __ldg(B + (k0 + k) * ldb + n);
+        }
+      }
+      __syncthreads();
+      for (int k = lane; k < kc; k += 32) {
+        const float av = __ldcs(a + k0 + k);
 #pragma unroll
-      for (int n = 0; n < NT; ++n)
-        if (n < N) acc[n] = fmaf(av, transB ? __ldg(B + int64_t(n) * ldb + k) : __ldg(B + k * ldb + n), acc[n]);
+        for (int n = 0; n < NT; ++n)
+          if (n < N) acc[n] = fmaf(av, Bs[k][n], acc[n]);
+      }
     }
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       float v = acc[n];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == n && n < N) C[m * ldc + n] = v + (bias ? bias[n] : 0.f);
+      if (lane == n && n < N && m < M) C[m * ldc + n] = v + (bias ? bias[n] : 0.f);
     }
   }
+}
+
+// ------------------------------------------------------------------ tn_small: C[M,N] = A[K,M]^T . B[K,N] with M*N <= 160, K huge
+// (the conv filter gradient: 25 x 6 outputs over K = B*P rows).  A and B are contiguous streams of short rows; a block stages
+// 256 rows of each with coalesced loads, and output (m, n) is owned by ONE thread (two row-parity groups of 160 threads) that
+// walks the staged rows in order.  Block partials go to a workspace; the last block folds them in block order.
+constexpr int kTnRows = 256;
+__global__ void __launch_bounds__(320) k_gemm_tn_small(int M, int N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                       int64_t ldb, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
+                                                       int64_t rows_per_block, float* __restrict__ part, unsigned int* __restrict__ ticket) {
+  extern __shared__ float sm[];
+  float* As = sm;                       // [kTnRows][M]
+  float* Bs = sm + kTnRows * M;         // [kTnRows][N]
+  __shared__ float half[160];
+  __shared__ unsigned int s_ticket;
+  const int tid = threadIdx.x, grp = tid / 160, t = tid - grp * 160, MN = M * N;
+  const int m = t / N, n = t - m * N;
+  const int64_t k0 = int64_t(blockIdx.x) * rows_per_block, k1 = k0 + rows_per_block < K ? k0 + rows_per_block : K;
+  float acc = 0.f;
+  for (int64_t kb = k0; kb < k1; kb += kTnRows) {
+    const int rows = int(k1 - kb < kTnRows ? k1 - kb : kTnRows);
+    __syncthreads();
+    if (lda == M) {
+      const float* src = A + kb * M;
+      for (int e = tid; e < rows * M; e += 320) As[e] = __ldcs(src + e);
+    } else {
+      for (int e = tid; e < rows * M; e += 320) As[e] = A[(kb + e / M) * lda + e % M];
+    }
+    if (ldb == N) {
+      const float* src = B + kb * N;
+      for (int e = tid; e < rows * N; e += 320) Bs[e] = __ldcs(src + e);
+    } else {
+      for (int e = tid; e < rows * N; e += 320) Bs[e] = B[(kb + e / N) * ldb + e % N];
+    }
+    __syncthreads();
+    if (t < MN)
+      for (int r = grp; r < rows; r += 2) acc = fmaf(As[r * M + m], Bs[r * N + n], acc);
+  }
+  __syncthreads();
+  if (grp == 1 && t < MN) half[t] = acc;
+  __syncthreads();
+  const int splits = gridDim.x;
+  if (grp == 0 && t < MN) {
+    acc += half[t];
+    if (splits == 1) C[int64_t(m) * ldc + n] = acc + (bias ? bias[n] : 0.f);
+    else part[int64_t(blockIdx.x) * MN + t] = acc;
+  }
+  if (splits == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != unsigned(splits - 1)) return;
+  __threadfence();
+  // fold: thread (grp, t) sums the blocks z = grp, grp+2, ..; then the two halves in order
+  float s = 0.f;
+  if (t < MN)
+    for (int z = grp; z < splits; z += 2) s += __ldcg(part + int64_t(z) * MN + t);
+  if (grp == 1 && t < MN) half[t] = s;
+  __syncthreads();
+  if (grp == 0 && t < MN) C[int64_t(m) * ldc + n] = s + half[t] + (bias ? bias[n] : 0.f);
+  if (tid == 0) *ticket = 0;
 }
 
 // ------------------------------------------------------------------ tn: C = A^T . B with A stored [K, M], split over K
@@ -220,6 +312,24 @@ bool agrs_gemm_skinny_eligible(int transA, int transB, int64_t M, int64_t N, int
 int agrs_gemm_skinny(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                      int64_t ldb, float* C, int64_t ldc, const float* bias) {
   const int n = int(N);
+  if (transA && M * N <= 160 && K >= 4096) {  // tn_small
+    const int64_t blocks_wanted = int64_t(ctx->sm_count) * 4, max_blocks = (K + kTnRows - 1) / kTnRows;
+    int64_t blocks = blocks_wanted < max_blocks ? blocks_wanted : max_blocks;
+    int64_t rpb = ((K + blocks - 1) / blocks + kTnRows - 1) / kTnRows * kTnRows;
+    blocks = (K + rpb - 1) / rpb;
+    float* part = nullptr;
+    if (blocks > 1) {
+      int rc = agrs_ensure_workspace(ctx, size_t(blocks) * size_t(M * N) * sizeof(float));
+      if (rc) return rc;
+      rc = ensure_tickets(ctx, 1);
+      if (rc) return rc;
+      part = ctx->workspace;
+    }
+    const size_t smem = size_t(kTnRows) * size_t(M + N) * sizeof(float);
+    k_gemm_tn_small<<<unsigned(blocks), 320, smem, ctx->stream>>>(int(M), n, K, A, lda, B, ldb, C, ldc, bias, rpb, part, ctx->tickets);
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
   if (transA) {
     const int64_t my = (M + 31) / 32;
     AGRS_REQUIRE(ctx, my <= 65535, AGRS_ERR_UNSUPPORTED, "agrs_gemm_skinny(tn): M too large");
@@ -265,11 +375,10 @@ int agrs_gemm_skinny(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N
     return AGRS_OK;
   }
   {
-    const int64_t warps_wanted = M, cap = int64_t(ctx->sm_count) * 8 * 8;
-    const int64_t warps = warps_wanted < cap ? warps_wanted : cap;
-    const unsigned grid = unsigned((warps + 7) / 8);
-    if (n <= 8) k_gemm_dot<8><<<grid, 256, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias);
-    else        k_gemm_dot<16><<<grid, 256, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias);
+    const int64_t groups = (M + 3) / 4, cap = int64_t(ctx->sm_count) * 8;
+    const unsigned grid = unsigned(groups < cap ? groups : cap);
+    if (n <= 8) k_gemm_dot<8><<<grid, 128, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias);
+    else        k_gemm_dot<16><<<grid, 128, 0, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias);
     AGRS_LAUNCHED(ctx);
   }
   return AGRS_OK;

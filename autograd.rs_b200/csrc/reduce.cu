@@ -176,6 +176,56 @@ __global__ void __launch_bounds__(256) k_sum_axis_mid(const float* __restrict__ 
   if (threadIdx.x == 0) tickets[o * gridDim.x + blockIdx.x] = 0;
 }
 
+// ---- outer == 1 and a SHORT inner axis (db of a narrow layer: [B*P, 6] -> [6], [1024, 10] -> [10]) ----
+// The array is read as one flat, fully coalesced stream: T = 256 - 256 % inner threads are active and thread t owns the flat
+// indices t, t+T, t+2T, ..; T is a multiple of inner, so every one of them lies in column t % inner.  Columns are then folded
+// across threads, and across blocks by the last block to finish, always in index order (deterministic).
+__global__ void __launch_bounds__(256) k_colsum_narrow(const float* __restrict__ x, int64_t n, int inner, int64_t elems_per_block,
+                                                       float* __restrict__ part, unsigned int* __restrict__ ticket, float* __restrict__ out) {
+  __shared__ float s[256];
+  __shared__ unsigned int s_ticket;
+  const int tid = threadIdx.x, T = 256 - 256 % inner;
+  const int64_t b0 = int64_t(blockIdx.x) * elems_per_block, b1 = b0 + elems_per_block < n ? b0 + elems_per_block : n;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (tid < T) {
+    int64_t i = b0 + tid;
+    for (; i + 3 * int64_t(T) < b1; i += 4 * int64_t(T)) {
+      a0 += __ldcs(x + i);
+      a1 += __ldcs(x + i + T);
+      a2 += __ldcs(x + i + 2 * int64_t(T));
+      a3 += __ldcs(x + i + 3 * int64_t(T));
+    }
+    for (; i < b1; i += T) a0 += __ldcs(x + i);
+  }
+  s[tid] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  const int blocks = gridDim.x;
+  if (tid < inner) {
+    float c = 0.f;
+    for (int t = tid; t < T; t += inner) c += s[t];
+    if (blocks == 1) out[tid] = c;
+    else part[int64_t(blockIdx.x) * inner + tid] = c;
+  }
+  if (blocks == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != unsigned(blocks - 1)) return;
+  __threadfence();
+  float c = 0.f;
+  if (tid < T)
+    for (int z = tid / inner; z < blocks; z += T / inner) c += __ldcg(part + int64_t(z) * inner + tid % inner);
+  s[tid] = c;
+  __syncthreads();
+  if (tid < inner) {
+    float r = 0.f;
+    for (int t = tid; t < T; t += inner) r += s[t];
+    out[tid] = r;
+  }
+  if (tid == 0) *ticket = 0;
+}
+
 // ---- inner == 1 (sum over the last axis): one warp per output row for long rows, one thread for short ----
 __global__ void k_sum_last_warp(const float* __restrict__ x, int64_t rows, int64_t len, float* __restrict__ out) {
   int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -248,6 +298,29 @@ int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len,
     } else {
       k_sum_last_thread<<<unsigned((outer + 255) / 256), 256, 0, ctx->stream>>>(x, outer, len, out);
     }
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
+  if (outer == 1 && inner < 32 && len >= 512) {
+    const int64_t n = len * inner;
+    const int T = 256 - 256 % int(inner);
+    int64_t blocks = int64_t(ctx->sm_count) * 4, maxb = (n + 8 * T - 1) / (8 * T);
+    if (blocks > maxb) blocks = maxb;
+    int64_t epb = ((n + blocks - 1) / blocks + T - 1) / T * T;  // a multiple of T (hence of inner): block starts are column-aligned
+    blocks = (n + epb - 1) / epb;
+    float* part = nullptr;
+    if (blocks > 1) {
+      int rc = agrs_ensure_workspace(ctx, size_t(blocks) * size_t(inner) * sizeof(float));
+      if (rc) return rc;
+      if (ctx->tickets_n < 1) {
+        AGRS_NOT_CAPTURING(ctx, "growing the ticket array (run one ordinary step before capturing)");
+        AGRS_CUDA(ctx, cudaMalloc(&ctx->tickets, 4096 * sizeof(unsigned int)));
+        AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, 4096 * sizeof(unsigned int), ctx->stream));
+        ctx->tickets_n = 4096;
+      }
+      part = ctx->workspace;
+    }
+    k_colsum_narrow<<<unsigned(blocks), 256, 0, ctx->stream>>>(x, n, int(inner), epb, part, ctx->tickets, out);
     AGRS_LAUNCHED(ctx);
     return AGRS_OK;
   }

@@ -220,7 +220,8 @@ def test_sum_mean(ctx, n):
 
 
 @pytest.mark.parametrize("outer,length,inner", [(1, 1, 1), (1, 8192, 4096), (1, 2000, 1), (1, 1000, 10), (1, 777, 6),
-                                                (3, 50, 129), (5000, 3, 1), (37, 200, 1), (9 * 25, 3, 1), (1, 100000, 8)])
+                                                (3, 50, 129), (5000, 3, 1), (37, 200, 1), (9 * 25, 3, 1), (1, 100000, 8), (1, 589824, 6), (1, 5000, 31),
+                                                (1, 600, 3), (1, 512, 25)])
 def test_sum_axis(ctx, outer, length, inner):
     rng = np.random.default_rng(outer + length + inner)
     x = rnd(rng, outer, length, inner)
