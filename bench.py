@@ -34,6 +34,24 @@ METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library prints there (NCCL prints its version to stdout when
+    NCCL_DEBUG is VERSION or WARN) is re-routed to stderr; emit() writes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -186,7 +204,7 @@ def run_reference_arm(args, cfg):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cfg, world):
@@ -356,7 +374,7 @@ def run_b200_arm(args, cfg):
     if dp is not None:
         dp.close()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     del tr, model, X, T, loss
     if dist is not None:
         dist.barrier()
@@ -374,6 +392,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce gradients after backward instead of during it")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     from autograd_rs_b200 import workloads as W
     cfg = dict(W.CONFIGS[args.config])
