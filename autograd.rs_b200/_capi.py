@@ -64,6 +64,14 @@ def lib():
             "agrs_set_gemm_path": [vp, i32],
             "agrs_last_gemm_path": [vp],
             "agrs_set_tuning": [vp, i32, i64],
+            "agrs_peer_alloc": [vp, sz, C.POINTER(vp)],
+            "agrs_peer_free": [vp, vp],
+            "agrs_peer_export": [vp, vp, vp],
+            "agrs_peer_open": [vp, vp, C.POINTER(vp)],
+            "agrs_peer_close": [vp, vp],
+            "agrs_fused_create": [vp, i32, i32, C.POINTER(vp), sz, sz, sz, C.POINTER(vp)],
+            "agrs_fused_destroy": [vp],
+            "agrs_fused_sgd_step": [vp, f32],
             "agrs_capture_begin": [vp],
             "agrs_capture_end": [vp, C.POINTER(vp)],
             "agrs_graph_launch": [vp, vp, i32],
@@ -110,6 +118,8 @@ def lib():
         L.agrs_launch_count.restype = C.c_uint64
         L.agrs_graph_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.agrs_graph_info.restype = i32
+        L.agrs_fused_flag_floats.argtypes = []
+        L.agrs_fused_flag_floats.restype = C.c_size_t
         L.agrs_version.argtypes = []
         L.agrs_version.restype = C.c_char_p
         _lib = L

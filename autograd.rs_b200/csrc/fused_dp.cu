@@ -1,0 +1,240 @@
+// Fused data-parallel optimiser step over NVLink peer memory: ONE kernel per training step replaces
+//     all-reduce(grad)  ->  w -= lr * grad  (optim.rs:25-34)  ->  zero_grad (model.rs:14-21)
+// Every rank keeps its parameters and parameter gradients in an "arena" (one cudaMalloc block, IPC-exported, mapped by
+// every peer at the same offsets).  Rank r owns the r-th slice of the arena:
+//     barrier 1   every rank's gradients are complete
+//     reduce      g = (sum over ranks p = 0..world-1 of G_p[i]) / world      P2P loads over NVLink (fixed order: replicas
+//                                                                           stay bit-identical)
+//     update      w = W_r[i] - lr * g                                       two roundings, as agrs_sgd_step_f32
+//     broadcast   W_p[i] = w for every rank p                               P2P stores over NVLink
+//     barrier 2   every rank's slice has landed everywhere; nobody still reads my gradients
+// i.e. reduce-scatter + SGD + all-gather with the weights never making a separate pass through HBM.
+// The barriers are flag arrays in the arenas, written with system-scope releases by the peers and polled with system-scope
+// acquires; every wait is bounded (a lost rank traps the kernel instead of hanging the GPU).  One process per GPU: each
+// rank's kernel runs on its own device, so the ranks always run concurrently.
+#include <string.h>
+
+#include "agrs_internal.h"
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+constexpr int kFlagFloats = 256;  // first 1 KB of every arena: barrier flags (unsigned), then the data regions
+
+struct FusedArgs {
+  float* base[kMaxWorld];  // arena of every rank, as mapped in THIS process (base[rank] is the local one)
+  int world, rank;
+  size_t w_off, g_off;     // float offsets of the weight and gradient regions inside an arena
+  size_t total;            // floats in each region; a multiple of 4 * world
+  float lr;
+  unsigned epoch;          // strictly increasing per call: barrier generation
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// data accesses to peer arenas: system-scope, so neither a stale L1 line nor a cached remote line can be read
+__device__ __forceinline__ float4 ld_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_sys_v4(float* p, float4 v) {
+  asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Cross-rank + grid barrier `which` (0 or 1).  Flags of an arena (unsigned words):
+//   [which*32 + p]  "rank p reached barrier `which` of generation epoch"      written by rank p into EVERY arena
+//   [64 + which]    "all ranks reached it": local go flag for the other CTAs  written by this rank's CTA 0
+//   [66 + which]    CTA arrival counter of this rank (device scope)
+__device__ void rank_barrier(const FusedArgs& a, int which) {
+  unsigned* mine = reinterpret_cast<unsigned*>(a.base[a.rank]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // this CTA's loads/stores of the phase before the barrier are performed
+    atomicAdd(mine + 66 + which, 1u);
+  }
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0) {  // wait for every CTA of this rank, then tell the peers
+      const unsigned want = gridDim.x * a.epoch;  // the counter is never reset: generation g ends at g * gridDim.x
+      for (unsigned spins = 0; ld_acquire_gpu(mine + 66 + which) < want; ++spins)
+        if (spins > (1u << 28)) { printf("agrs fused step: local barrier timeout (rank %d)\n", a.rank); __trap(); }
+      __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+      const int p = threadIdx.x;
+      st_release_sys(reinterpret_cast<unsigned*>(a.base[p]) + which * 32 + a.rank, a.epoch);
+      for (unsigned spins = 0; ld_acquire_sys(mine + which * 32 + p) < a.epoch; ++spins)
+        if (spins > (1u << 28)) { printf("agrs fused step: rank %d never saw rank %d at barrier %d\n", a.rank, p, which); __trap(); }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(mine + 64 + which, a.epoch);
+    }
+  } else if (threadIdx.x == 0) {
+    for (unsigned spins = 0; ld_acquire_gpu(mine + 64 + which) < a.epoch; ++spins)
+      if (spins > (1u << 28)) { printf("agrs fused step: go-flag timeout (rank %d)\n", a.rank); __trap(); }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+template <int WORLD>  // 0 = run-time world size
+__global__ void __launch_bounds__(256) k_fused_dp_sgd(const FusedArgs a) {
+  const int world = WORLD ? WORLD : a.world;
+  rank_barrier(a, 0);
+  const size_t shard4 = a.total / 4 / world;  // float4 per rank
+  const size_t first4 = shard4 * a.rank;
+  const float inv = 1.0f / float(world);
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < shard4; i += stride) {
+    const size_t e = (first4 + i) * 4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < (WORLD ? WORLD : kMaxWorld); ++p) {
+      if (p >= world) break;
+      const float4 v = ld_sys_v4(a.base[p] + a.g_off + e);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
+    float4 w = ld_sys_v4(a.base[a.rank] + a.w_off + e);
+    w.x = __fsub_rn(w.x, __fmul_rn(g.x, a.lr));
+    w.y = __fsub_rn(w.y, __fmul_rn(g.y, a.lr));
+    w.z = __fsub_rn(w.z, __fmul_rn(g.z, a.lr));
+    w.w = __fsub_rn(w.w, __fmul_rn(g.w, a.lr));
+#pragma unroll
+    for (int p = 0; p < (WORLD ? WORLD : kMaxWorld); ++p) {
+      if (p >= world) break;
+      st_sys_v4(a.base[p] + a.w_off + e, w);
+    }
+  }
+  rank_barrier(a, 1);
+}
+
+}  // namespace
+
+struct agrs_fused {
+  agrs_ctx* ctx = nullptr;
+  FusedArgs args{};
+  size_t grid = 0;  // CTAs per launch: fixed at the first call (the barrier counters assume it)
+};
+
+extern "C" {
+
+int agrs_peer_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_peer_alloc");
+  AGRS_REQUIRE(ctx, out && nbytes > 0, AGRS_ERR_INVALID, "agrs_peer_alloc: bad arguments");
+  AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  AGRS_CUDA(ctx, cudaMalloc(out, nbytes));  // plain allocation: stream-ordered pool memory cannot be exported with cudaIpcGetMemHandle
+  AGRS_CUDA(ctx, cudaMemsetAsync(*out, 0, nbytes, ctx->stream));
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_peer_free(agrs_ctx* ctx, void* ptr) {
+  AGRS_CHECK_CTX(ctx);
+  if (!ptr) return AGRS_OK;
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  AGRS_CUDA(ctx, cudaFree(ptr));
+  return AGRS_OK;
+}
+
+int agrs_peer_export(agrs_ctx* ctx, void* ptr, void* handle64) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, ptr && handle64, AGRS_ERR_INVALID, "agrs_peer_export: null pointer");
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == AGRS_PEER_HANDLE_BYTES, "IPC handle size");
+  AGRS_CUDA(ctx, cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, sizeof(h));
+  return AGRS_OK;
+}
+
+int agrs_peer_open(agrs_ctx* ctx, const void* handle64, void** out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, handle64 && out, AGRS_ERR_INVALID, "agrs_peer_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  AGRS_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return AGRS_OK;
+}
+
+int agrs_peer_close(agrs_ctx* ctx, void* ptr) {
+  AGRS_CHECK_CTX(ctx);
+  if (ptr) AGRS_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
+  return AGRS_OK;
+}
+
+size_t agrs_fused_flag_floats(void) { return kFlagFloats; }
+
+int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, size_t w_off, size_t g_off, size_t total, agrs_fused** out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out && arenas && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, AGRS_ERR_INVALID,
+               "agrs_fused_create: bad arguments (world <= %d)", kMaxWorld);
+  AGRS_REQUIRE(ctx, total % (4 * size_t(world)) == 0 && w_off % 4 == 0 && g_off % 4 == 0 && w_off >= kFlagFloats && g_off >= kFlagFloats,
+               AGRS_ERR_INVALID, "agrs_fused_create: regions must start after the %d flag words and be multiples of 4*world floats", kFlagFloats);
+  agrs_fused* f = new agrs_fused();
+  f->ctx = ctx;
+  for (int p = 0; p < world; ++p) {
+    AGRS_REQUIRE(ctx, arenas[p] && agrs_aligned16(arenas[p]), AGRS_ERR_INVALID, "agrs_fused_create: arena %d is null or unaligned", p);
+    f->args.base[p] = static_cast<float*>(arenas[p]);
+  }
+  f->args.world = world;
+  f->args.rank = rank;
+  f->args.w_off = w_off;
+  f->args.g_off = g_off;
+  f->args.total = total;
+  f->args.epoch = 0;
+  *out = f;
+  return AGRS_OK;
+}
+
+int agrs_fused_destroy(agrs_fused* f) {
+  if (!f) return AGRS_OK;
+  delete f;
+  return AGRS_OK;
+}
+
+int agrs_fused_sgd_step(agrs_fused* f, float lr) {
+  if (!f) return AGRS_ERR_INVALID;
+  agrs_ctx* ctx = f->ctx;
+  AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_fused_sgd_step (its barrier generation is a launch argument)");
+  f->args.lr = lr;
+  f->args.epoch += 1;
+  // Every CTA must be resident at once (they wait on each other): one wave, sized by the occupancy the runtime reports.
+  int per_sm = 0;
+  AGRS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_dp_sgd<0>, 256, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  const size_t shard4 = f->args.total / 4 / size_t(f->args.world);
+  size_t blocks = (shard4 + 255) / 256;
+  const size_t cap = size_t(ctx->sm_count) * size_t(per_sm);
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  // the barrier counter arithmetic assumes the same grid on every call
+  static_assert(kFlagFloats >= 68, "flag words");
+  if (f->grid == 0) f->grid = blocks;
+  AGRS_REQUIRE(ctx, f->grid == blocks, AGRS_ERR_INVALID, "agrs_fused_sgd_step: grid changed between calls");
+  switch (f->args.world) {
+    case 2: k_fused_dp_sgd<2><<<unsigned(blocks), 256, 0, ctx->stream>>>(f->args); break;
+    case 4: k_fused_dp_sgd<4><<<unsigned(blocks), 256, 0, ctx->stream>>>(f->args); break;
+    case 8: k_fused_dp_sgd<8><<<unsigned(blocks), 256, 0, ctx->stream>>>(f->args); break;
+    default: k_fused_dp_sgd<0><<<unsigned(blocks), 256, 0, ctx->stream>>>(f->args); break;
+  }
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+}  // extern "C"

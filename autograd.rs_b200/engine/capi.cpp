@@ -520,6 +520,26 @@ int agrs_eng_dp_sync_grads(agrs_dp* dp) {
     dp->dp.sync_grads();
   });
 }
+int agrs_eng_dp_fused_prepare(agrs_dp* dp, void* handle64) {
+  return guarded([&] {
+    need(dp, "dp");
+    need(handle64, "handle buffer");
+    dp->dp.fused_prepare(handle64);
+  });
+}
+int agrs_eng_dp_fused_connect(agrs_dp* dp, const void* handles) {
+  return guarded([&] {
+    need(dp, "dp");
+    need(handles, "handles");
+    dp->dp.fused_connect(handles);
+  });
+}
+int agrs_eng_dp_fused_sgd_step(agrs_dp* dp, float lr) {
+  return guarded([&] {
+    need(dp, "dp");
+    dp->dp.fused_sgd_step(lr);
+  });
+}
 int agrs_eng_dp_mean_scalar(agrs_dp* dp, agrs_tensor* t) {
   return guarded([&] {
     need(dp, "dp");

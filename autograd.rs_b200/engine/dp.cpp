@@ -9,7 +9,70 @@ DataParallel::DataParallel(Device* dev, int world, int rank, const void* unique_
 DataParallel::~DataParallel() {
   for (auto& c : cells_)
     if (c->hook == this) c->hook = nullptr;
+  if (fused_) agrs_fused_destroy(fused_);
+  for (size_t p = 0; p < peer_maps_.size(); ++p)
+    if (int(p) != rank_ && peer_maps_[p]) agrs_peer_close(dev_->ctx(), peer_maps_[p]);
+  if (arena_) {
+    // parameters move back to ordinary storage before the arena goes away
+    for (auto& t : params_) {
+      if (t.data->buf->owned) continue;
+      auto nb = std::make_shared<Buffer>(dev_, t.data->buf->n);
+      agrs_copy(dev_->ctx(), nb->ptr, t.data->buf->ptr, size_t(nb->n) * sizeof(float));
+      t.data->buf = nb;
+    }
+    agrs_peer_free(dev_->ctx(), arena_);
+  }
   if (comm_) agrs_comm_destroy(comm_);
+}
+
+void DataParallel::fused_prepare(void* handle64) {
+  if (arena_) throw Panic("DataParallel::fused_prepare called twice");
+  if (params_.empty()) throw Panic("DataParallel::fused_prepare: register the parameters first");
+  int64_t off = 0;
+  for (auto& t : params_) {
+    if (t.data->transposed) throw Panic("DataParallel(fused): transposed parameter view", AGRS_ERR_UNSUPPORTED);
+    slots_[t.grad.get()] = Slot{off, t.len()};
+    off += (t.len() + 63) / 64 * 64;  // 256-byte aligned slots: TMA-mappable, float4-friendly
+  }
+  const int64_t q = 4 * int64_t(world_) * 64;
+  region_ = size_t((off + q - 1) / q * q);
+  w_off_ = agrs_fused_flag_floats();
+  g_off_ = w_off_ + region_;
+  void* a = nullptr;
+  dev_->check(agrs_peer_alloc(dev_->ctx(), (g_off_ + region_) * sizeof(float), &a));
+  arena_ = static_cast<float*>(a);
+  for (auto& t : params_) {
+    const Slot& sl = slots_[t.grad.get()];
+    float* dst = arena_ + w_off_ + sl.off;
+    dev_->check(agrs_copy(dev_->ctx(), dst, t.data->rptr(), size_t(sl.n) * sizeof(float)));
+    t.data->buf = std::make_shared<Buffer>(dev_, dst, sl.n);  // the shared storage cell now points into the arena
+  }
+  dev_->sync();
+  dev_->check(agrs_peer_export(dev_->ctx(), arena_, handle64));
+}
+
+void DataParallel::fused_connect(const void* handles) {
+  if (!arena_) throw Panic("DataParallel::fused_connect before fused_prepare");
+  if (fused_) throw Panic("DataParallel::fused_connect called twice");
+  peer_maps_.assign(size_t(world_), nullptr);
+  for (int p = 0; p < world_; ++p) {
+    if (p == rank_) {
+      peer_maps_[size_t(p)] = arena_;
+      continue;
+    }
+    dev_->check(agrs_peer_open(dev_->ctx(), static_cast<const char*>(handles) + size_t(p) * AGRS_PEER_HANDLE_BYTES, &peer_maps_[size_t(p)]));
+  }
+  dev_->check(agrs_fused_create(dev_->ctx(), world_, rank_, peer_maps_.data(), w_off_, g_off_, region_, &fused_));
+}
+
+void DataParallel::fused_sgd_step(float lr) {
+  if (!fused_) throw Panic("DataParallel::fused_sgd_step before fused_connect");
+  for (auto& c : cells_) {
+    bool& dirty = dirty_[c.get()];
+    if (!dirty) throw Panic("called `Option::unwrap()` on a `None` value (DataParallel fused step: a parameter received no gradient)");
+    dirty = false;
+  }
+  dev_->check(agrs_fused_sgd_step(fused_, lr));
 }
 
 void DataParallel::shard_rows(int64_t rows, int world, int rank, int64_t* begin, int64_t* end) {
@@ -24,6 +87,7 @@ void DataParallel::register_parameters(const std::vector<Tensor>& params, bool o
     if (!p.grad) throw Panic("DataParallel: parameter without a grad cell");
     if (dirty_.count(p.grad.get())) continue;
     cells_.push_back(p.grad);
+    params_.push_back(p);
     dirty_[p.grad.get()] = false;
     p.grad->hook = this;
   }
@@ -43,6 +107,13 @@ void DataParallel::on_accumulated(GradCell& cell) {
   // Averaging is linear and an averaged gradient is identical on every rank, so mean_r(avg + local_r) = avg + mean_r(local_r):
   // reducing after every accumulation (overlap) or once before the optimiser step gives the same result.
   it->second = true;
+  if (fused_) {  // the gradient joins the arena; the exchange itself is the fused step's job
+    const Slot& sl = slots_[&cell];
+    const Storage& g = *cell.get();
+    if (g.transposed || g.len() != sl.n) throw Panic("DataParallel(fused): gradient does not match its parameter", AGRS_ERR_SHAPE);
+    dev_->check(agrs_copy(dev_->ctx(), arena_ + g_off_ + sl.off, g.rptr(), size_t(sl.n) * sizeof(float)));
+    return;
+  }
   if (!overlap_ || world_ == 1) return;
   reduce(cell);
   it->second = false;

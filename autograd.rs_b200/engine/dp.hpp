@@ -28,6 +28,18 @@ class DataParallel : public GradHook {
 
   void on_accumulated(GradCell& cell) override;
 
+  // ---- fused optimiser step over NVLink peer memory (csrc/fused_dp.cu): replaces sync_grads() + SGD::step ----
+  // fused_prepare  lays the registered parameters out in an arena (agrs_peer_alloc), moves their values there and re-points
+  //                the parameter storages at it (every clone of the parameter sees the move), exports the arena (64 bytes);
+  // fused_connect  maps the arenas of all ranks (handles gathered by the launcher, world x 64 bytes, rank order);
+  // fused_sgd_step one kernel: barrier, reduce-scatter of the gradients (P2P loads), w -= lr * mean(g) on the owned slice,
+  //                all-gather of the new weights (P2P stores), barrier.  Gradients reach the arena as backward produces them
+  //                (on_accumulated copies them in).  p.grad() keeps this rank's LOCAL gradient: the mean is never materialised.
+  void fused_prepare(void* handle64);
+  void fused_connect(const void* handles);
+  void fused_sgd_step(float lr);
+  bool fused() const { return fused_ != nullptr; }
+
   // rows [begin, end) of a global batch owned by `rank` (equal shards; the remainder goes to the first ranks)
   static void shard_rows(int64_t rows, int world, int rank, int64_t* begin, int64_t* end);
 
@@ -38,6 +50,14 @@ class DataParallel : public GradHook {
   int world_, rank_;
   bool overlap_ = false;
   std::vector<std::shared_ptr<GradCell>> cells_;
+  // fused mode
+  struct Slot { int64_t off = 0, n = 0; };
+  std::vector<Tensor> params_;                    // registration order (one per cell)
+  std::unordered_map<GradCell*, Slot> slots_;     // float offset of the parameter inside the weight / gradient regions
+  float* arena_ = nullptr;
+  std::vector<void*> peer_maps_;                  // arenas of all ranks as mapped here ([rank] = arena_)
+  size_t w_off_ = 0, g_off_ = 0, region_ = 0;
+  agrs_fused* fused_ = nullptr;
   std::unordered_map<GradCell*, bool> dirty_;  // holds local contributions that have not been averaged yet
 };
 

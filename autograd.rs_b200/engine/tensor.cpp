@@ -52,8 +52,9 @@ Buffer::Buffer(Device* d, int64_t n_elems) : dev(d), keep(d->weak_from_this().lo
   dev->check(agrs_alloc(dev->ctx(), size_t(n_elems) * sizeof(float), &p));
   ptr = static_cast<float*>(p);
 }
+Buffer::Buffer(Device* d, float* external, int64_t n_elems) : dev(d), keep(d->weak_from_this().lock()), ptr(external), n(n_elems), owned(false) {}
 Buffer::~Buffer() {
-  if (ptr) agrs_free(dev->ctx(), ptr);
+  if (ptr && owned) agrs_free(dev->ctx(), ptr);
 }
 
 Storage::Storage(Device* d, const Shape& s) : buf(std::make_shared<Buffer>(d, numel(s))), shape(s) {

@@ -55,7 +55,9 @@ struct Buffer {
   std::shared_ptr<Device> keep;  // null when the Device is not shared-owned (plain C++ use: the Device must outlive its tensors)
   float* ptr = nullptr;
   int64_t n = 0;
+  bool owned = true;             // false: a window into memory owned elsewhere (a parameter living in the data-parallel arena)
   Buffer(Device* d, int64_t n_elems);
+  Buffer(Device* d, float* external, int64_t n_elems);  // non-owning
   ~Buffer();
   Buffer(const Buffer&) = delete;
 };

@@ -108,6 +108,9 @@ def lib():
         "agrs_eng_dp_register": [vp, pvp, i32, i32],
         "agrs_eng_dp_sync_grads": [vp],
         "agrs_eng_dp_mean_scalar": [vp, vp],
+        "agrs_eng_dp_fused_prepare": [vp, vp],
+        "agrs_eng_dp_fused_connect": [vp, vp],
+        "agrs_eng_dp_fused_sgd_step": [vp, f32],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -733,6 +736,23 @@ class DataParallel:
 
     def mean_scalar(self, t):
         _check(lib().agrs_eng_dp_mean_scalar(self._h, t._h))
+
+    # ---- fused optimiser step over NVLink peer memory (csrc/fused_dp.cu) ----
+    fused = False
+
+    def enable_fused(self, all_gather):
+        """Move the parameters into an IPC-exported arena and map every peer's arena.  `all_gather(bytes) -> list[bytes]` is the
+        launcher's exchange (rank order), e.g. torch.distributed.all_gather_object; for world == 1 pass `lambda h: [h]`."""
+        buf = C.create_string_buffer(64)
+        _check(lib().agrs_eng_dp_fused_prepare(self._h, buf))
+        handles = all_gather(buf.raw)
+        assert len(handles) == self.world and all(len(h) == 64 for h in handles)
+        _check(lib().agrs_eng_dp_fused_connect(self._h, b"".join(handles)))
+        self.fused = True
+
+    def fused_sgd_step(self, lr):
+        """reduce-scatter(grad) + w -= lr * mean(grad) + all-gather(w) in one kernel; replaces sync_grads() and SGD.step()"""
+        _check(lib().agrs_eng_dp_fused_sgd_step(self._h, float(lr)))
 
     def close(self):
         if self._h:

@@ -84,9 +84,14 @@ class Trainer:
         pred = self.model.forward([x.clone()])
         loss = self.loss_layer.forward([pred, t.clone()])
         loss.backward()
-        if self.dp is not None:
-            self.dp.sync_grads()
-        self.optim.step()
+        if self.dp is not None and self.dp.fused:
+            # one kernel over NVLink peer memory: reduce-scatter of the gradients + SGD on the owned slice + all-gather of the
+            # weights.  Only the registered parameters exist in this model, so it replaces sync_grads() and optim.step().
+            self.dp.fused_sgd_step(self.optim.lr)
+        else:
+            if self.dp is not None:
+                self.dp.sync_grads()
+            self.optim.step()
         self.model.zero_grad()
         return loss
 

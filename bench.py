@@ -212,6 +212,8 @@ def workload_config(args, cfg, world):
                         f"{cfg['rows']} rows per GPU ({ {'mlp4096': 'BASELINE.json configs[1]', 'mlp8192': 'BASELINE.json configs[4], per-GPU shard'}.get(args.config, 'test-size') })",
             "rows_per_gpu": cfg["rows"], "global_batch": cfg["rows"] * world, "width": cfg["width"], "layers": cfg["layers"],
             "activation": cfg["act"], "lr": cfg["lr"], "parallelism": f"dp{world}",
+            "gradient_exchange": ("none" if world == 1 else ("fused peer-memory kernel (reduce-scatter + SGD + all-gather)" if getattr(args, "fused", False)
+                                                              else "NCCL all-reduce(avg) per parameter" + ("" if getattr(args, "no_overlap", False) else ", overlapped with backward"))),
             "l2": "working set (activations + weights, > 2 GB) is larger than the 126 MB L2; no flush needed"}
 
 
@@ -244,6 +246,12 @@ def run_b200_arm(args, cfg):
         ids = [F.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         dp = F.DataParallel(dev, world, rank, ids[0], model.parameters(), overlap=not args.no_overlap)
+        if args.fused:
+            def all_gather_bytes(h):
+                out = [None] * world
+                dist.all_gather_object(out, h)
+                return out
+            dp.enable_fused(all_gather_bytes)
     tr = W.Trainer(model, cfg["lr"], dp=dp)
 
     x, t = W.mlp_batch(cfg["rows"], cfg["width"], cfg["width"], seed=1, rank=rank)  # this rank's shard of the global batch
@@ -391,6 +399,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce gradients after backward instead of during it")
+    ap.add_argument("--fused", action="store_true", help="N > 1: one fused reduce-scatter + SGD + all-gather kernel over NVLink peer memory "
+                                                         "instead of NCCL all-reduce + SGD")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -181,6 +181,27 @@ AGRS_API int agrs_comm_info(agrs_comm* comm, int* world, int* rank);
 AGRS_API int agrs_comm_allreduce_f32(agrs_comm* comm, float* buf, size_t n, int average);
 AGRS_API int agrs_comm_join(agrs_comm* comm);
 
+/* ---- fused data-parallel optimiser step over NVLink peer memory (csrc/fused_dp.cu) ----
+ * Each rank keeps parameters and parameter gradients in an ARENA: one agrs_peer_alloc block laid out identically on every
+ * rank ([flag words | ... weight region at w_off ... | ... gradient region at g_off ...], offsets in floats).  The arenas are
+ * exported (agrs_peer_export -> 64-byte handle, exchanged by the launcher) and mapped by every peer (agrs_peer_open).
+ * agrs_fused_sgd_step then runs ONE kernel per training step: cross-rank barrier, reduce-scatter of the gradients with P2P
+ * loads, w -= lr * mean(g) on the owned slice, all-gather of the updated weights with P2P stores, cross-rank barrier.
+ * It replaces all-reduce + agrs_sgd_step_f32 (optim.rs:25-34).  Every rank must call it the same number of times. */
+#define AGRS_PEER_HANDLE_BYTES 64
+typedef struct agrs_fused agrs_fused;
+AGRS_API int agrs_peer_alloc(agrs_ctx* ctx, size_t nbytes, void** out);          /* zeroed; plain cudaMalloc (IPC-exportable) */
+AGRS_API int agrs_peer_free(agrs_ctx* ctx, void* ptr);
+AGRS_API int agrs_peer_export(agrs_ctx* ctx, void* ptr, void* handle64);
+AGRS_API int agrs_peer_open(agrs_ctx* ctx, const void* handle64, void** out);    /* maps a PEER's arena into this process */
+AGRS_API int agrs_peer_close(agrs_ctx* ctx, void* ptr);
+AGRS_API size_t agrs_fused_flag_floats(void);                                    /* floats reserved at the start of an arena */
+/* arenas[p]: rank p's arena as mapped here (arenas[rank] = the local block); total: floats per region, multiple of 4*world */
+AGRS_API int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, size_t w_off, size_t g_off, size_t total,
+                               agrs_fused** out);
+AGRS_API int agrs_fused_destroy(agrs_fused* f);
+AGRS_API int agrs_fused_sgd_step(agrs_fused* f, float lr);
+
 AGRS_API const char* agrs_version(void);
 
 #ifdef __cplusplus

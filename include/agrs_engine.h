@@ -131,6 +131,18 @@ AGRS_API int agrs_eng_dp_register(agrs_dp* dp, agrs_tensor* const* params, int n
 /* all-reduce whatever has not been reduced yet, make the compute stream wait for the communication stream, and turn
  * the sums into means.  Call between backward() and sgd_step(). */
 AGRS_API int agrs_eng_dp_sync_grads(agrs_dp* dp);
+/* Fused optimiser step over NVLink peer memory (agrs_fused_*, agrs.h): ONE kernel does reduce-scatter of the gradients,
+ * w -= lr * mean(g) and all-gather of the new weights; it replaces agrs_eng_dp_sync_grads + agrs_eng_sgd_step for the
+ * registered parameters.  Set-up, once, after agrs_eng_dp_register:
+ *   agrs_eng_dp_fused_prepare(dp, handle)   moves the parameters into an exportable arena (their storages are re-pointed: every
+ *                                           clone follows) and returns its 64-byte IPC handle;
+ *   the launcher gathers the handles of all ranks (world x 64 bytes, rank order);
+ *   agrs_eng_dp_fused_connect(dp, handles)  maps the peers' arenas.
+ * Then, every iteration: backward(); agrs_eng_dp_fused_sgd_step(dp, lr); zero_grad().  The tensors' grad() keep the LOCAL
+ * gradient of this rank (the mean only exists inside the kernel). */
+AGRS_API int agrs_eng_dp_fused_prepare(agrs_dp* dp, void* handle64_out);
+AGRS_API int agrs_eng_dp_fused_connect(agrs_dp* dp, const void* handles);
+AGRS_API int agrs_eng_dp_fused_sgd_step(agrs_dp* dp, float lr);
 /* mean over ranks of a 1-element tensor (the loss value), in place */
 AGRS_API int agrs_eng_dp_mean_scalar(agrs_dp* dp, agrs_tensor* t);
 

@@ -487,6 +487,38 @@ def test_data_parallel_two_gpus_tracks_oracle():
     assert r.returncode == 0 and "DP PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_fused_optimizer_world1_matches_plain_sgd(dev):
+    """The fused peer-memory step with a single rank: parameters move into the arena (address changes, values and every
+    clone follow), one kernel per step does reduce + SGD + broadcast on the whole arena, and the losses are those of the plain
+    path bit for bit (mean over one rank is the identity; the update keeps the two roundings of optim.rs:31-33)."""
+    ws, bs = W.mlp_init(3, 192, seed=71)
+    x, t = W.mlp_batch(320, 192, 192, seed=72)
+    want, params_plain, _ = run_device_mlp(dev, x, t, ws, bs, "sigmoid", 1e-4, 4)
+    model = W.build_mlp(dev, ws, bs, "sigmoid")
+    params = model.parameters()
+    before = [p.data_ptr() for p in params]
+    dp = F.DataParallel(dev, 1, 0, F.comm_unique_id(), params, overlap=True)
+    dp.enable_fused(lambda h: [h])
+    after = [p.data_ptr() for p in params]
+    assert all(a != b for a, b in zip(after, before)) and all(a % 256 == 0 for a in after)
+    assert after == sorted(after)  # one arena, registration order
+    for p, w0 in zip(params, [a for pair in zip(ws, bs) for a in pair]):
+        assert np.array_equal(p.data(), w0)
+    tr = W.Trainer(model, 1e-4, dp=dp)
+    X, Tt = T(dev, x), T(dev, t)
+    Tt.requires_grad = False
+    n0 = dev.launches()
+    got = [tr.step(X, Tt).item() for _ in range(4)]
+    assert got == want
+    for p, q in zip(model.parameters(), params_plain):
+        assert np.array_equal(p.data(), q)
+    assert [p.data_ptr() for p in model.parameters()] == after  # the parameters stay in the arena
+    dp.close()
+    # after close the parameters live in ordinary storage again, values intact
+    for p, q in zip(model.parameters(), params_plain):
+        assert np.array_equal(p.data(), q)
+
+
 def test_data_parallel_world1_is_identity(dev):
     """DataParallel with one rank: registration + sync are no-ops on the numbers (the N>1 path runs under torchrun)."""
     ws, bs = W.mlp_init(2, 128, seed=51)

@@ -1,5 +1,5 @@
 """Data-parallel parity on real GPUs (run under torchrun): N ranks train a small MLP on disjoint shards of one global batch with the
-engine's DataParallel (NCCL all-reduce, overlap on and off); rank 0 also runs the ORACLE on the whole global batch.  Checks: every
+engine's DataParallel (NCCL all-reduce with overlap on and off, then the fused peer-memory optimiser step); rank 0 also runs the ORACLE on the whole global batch.  Checks: every
 loss (mean of shard means) and every final weight within 1e-4 of the single-device oracle; weights bit-identical across ranks."""
 import os
 import sys
@@ -22,11 +22,18 @@ def main():
     ws, bs = W.mlp_init(layers, width, seed=3)
     x, t = W.mlp_batch(rows, width, width, seed=4)          # the global batch, identical on every rank
     b, e = F.shard_rows(rows, world, rank)
-    for overlap in (True, False):
+    def all_gather_bytes(h):
+        out = [None] * world
+        dist.all_gather_object(out, h)
+        return out
+
+    for overlap, fused in ((True, False), (False, False), (True, True)):
         ids = [F.comm_unique_id() if rank == 0 else None]   # an NCCL id is good for ONE communicator
         dist.broadcast_object_list(ids, src=0)
         model = W.build_mlp(dev, ws, bs, "sigmoid")
         dp = F.DataParallel(dev, world, rank, ids[0], model.parameters(), overlap=overlap)
+        if fused:
+            dp.enable_fused(all_gather_bytes)   # parameters move into the peer-mapped arena; one fused kernel per step
         tr = W.Trainer(model, lr, dp=dp)
         X, T = F.Tensor.from_numpy(dev, x[b:e]), F.Tensor.from_numpy(dev, t[b:e])
         T.requires_grad = False
@@ -47,7 +54,7 @@ def main():
             want, olayers = O.mlp_train(x, t, ws, bs, "sigmoid", lr, steps, np.float32)
             el = max(abs(a - c) / abs(c) for a, c in zip(losses, want))
             ew = max(O.rel_err(p, q.data) for p, q in zip(params, [q for l in olayers for q in l.parameters()]))
-            print(f"world={world} overlap={overlap}: losses {losses} oracle {want}; max rel err loss {el:.2e} weights {ew:.2e}")
+            print(f"world={world} overlap={overlap} fused={fused}: losses {losses} oracle {want}; max rel err loss {el:.2e} weights {ew:.2e}")
             assert el < 1e-4 and ew < 1e-4
         dp.close()
         dist.barrier()
