@@ -3,8 +3,7 @@
 // Every rank keeps its parameters and parameter gradients in an "arena" (one cudaMalloc block, IPC-exported, mapped by
 // every peer at the same offsets).  Rank r owns the r-th slice of the arena:
 //     barrier 1   every rank's gradients are complete
-//     reduce      g = (sum over ranks p = 0..world-1 of G_p[i]) / world      P2P loads over NVLink (fixed order: replicas
-//                                                                           stay bit-identical)
+//     reduce      g = (sum over ranks p of G_p[i]) / world                  P2P loads over NVLink, peers visited from rank+1 on
 //     update      w = W_r[i] - lr * g                                       two roundings, as agrs_sgd_step_f32
 //     broadcast   W_p[i] = w for every rank p                               P2P stores over NVLink
 //     barrier 2   every rank's slice has landed everywhere; nobody still reads my gradients
@@ -99,12 +98,27 @@ __global__ void __launch_bounds__(256) k_fused_dp_sgd(const FusedArgs a) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < shard4; i += stride) {
     const size_t e = (first4 + i) * 4;
+    // Peers are visited starting at the next rank (rank+1, rank+2, .., rank): at any moment the ranks pull from different
+    // peers, so no GPU's NVLink egress is everybody's target.  The slice's owner fixes the summation order, every element has
+    // exactly one owner and its result is broadcast: deterministic, and the replicas stay bit-identical.
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (WORLD) {
+      float4 v[WORLD ? WORLD : 1];
 #pragma unroll
-    for (int p = 0; p < (WORLD ? WORLD : kMaxWorld); ++p) {
-      if (p >= world) break;
-      const float4 v = ld_sys_v4(a.base[p] + a.g_off + e);
-      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      for (int j = 0; j < (WORLD ? WORLD : 1); ++j) {  // all loads in flight before the first add
+        int p = a.rank + 1 + j;
+        p -= p >= world ? world : 0;
+        v[j] = ld_sys_v4(a.base[p] + a.g_off + e);
+      }
+#pragma unroll
+      for (int j = 0; j < (WORLD ? WORLD : 1); ++j) { g.x += v[j].x; g.y += v[j].y; g.z += v[j].z; g.w += v[j].w; }
+    } else {
+      for (int j = 0; j < world; ++j) {
+        int p = a.rank + 1 + j;
+        p -= p >= world ? world : 0;
+        const float4 v = ld_sys_v4(a.base[p] + a.g_off + e);
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
     }
     g.x *= inv; g.y *= inv; g.z *= inv; g.w *= inv;
     float4 w = ld_sys_v4(a.base[a.rank] + a.w_off + e);
@@ -113,8 +127,10 @@ __global__ void __launch_bounds__(256) k_fused_dp_sgd(const FusedArgs a) {
     w.z = __fsub_rn(w.z, __fmul_rn(g.z, a.lr));
     w.w = __fsub_rn(w.w, __fmul_rn(g.w, a.lr));
 #pragma unroll
-    for (int p = 0; p < (WORLD ? WORLD : kMaxWorld); ++p) {
-      if (p >= world) break;
+    for (int j = 0; j < (WORLD ? WORLD : kMaxWorld); ++j) {
+      if (j >= world) break;
+      int p = a.rank + 1 + j;
+      p -= p >= world ? world : 0;
       st_sys_v4(a.base[p] + a.w_off + e, w);
     }
   }

@@ -9,7 +9,8 @@ StoragePtr contig(const StoragePtr& s) { return s->transposed ? s->contiguous_co
 
 // C = op(a) * op(b) (+ bias row).  `ta`/`tb` ask for the LOGICAL transpose of the operand; a storage that is
 // itself a transposed view flips the flag back.  Nothing is ever copied: majors go to the GEMM as flags.
-Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bias = nullptr) {
+Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bias = nullptr,
+            const std::shared_ptr<Buffer>& out_buf = nullptr) {
   if (a.ndim() != 2 || b.ndim() != 2) throw Panic("Ndarray only supports 1d/2d matmul!");
   if (a.dev() != b.dev()) throw Panic("Tensors must be on same device");
   const Shape& as = a.shape();
@@ -22,10 +23,17 @@ Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bia
                 AGRS_ERR_SHAPE);
   const bool fa = ta != a.data->transposed, fb = tb != b.data->transposed;  // memory-level flags
   // memory row pitch: A stored [M,K] (fa=0) -> K, stored [K,M] (fa=1) -> M; B stored [K,N] (fb=0) -> N, [N,K] (fb=1) -> K
-  auto out = std::make_shared<Storage>(a.dev(), Shape{M, N});
+  auto out = (out_buf && out_buf->n == M * N) ? std::make_shared<Storage>(out_buf, Shape{M, N}) : std::make_shared<Storage>(a.dev(), Shape{M, N});
   a.dev()->check(agrs_gemm_f32(a.dev()->ctx(), fa, fb, M, N, K, a.data->rptr(), fa ? M : K, b.data->rptr(), fb ? K : N, out->buf->ptr,
                                N, bias));
   return Tensor(out);
+}
+
+// where a freshly computed parameter gradient should be written: the parameter's arena window when the coming accumulation
+// is a plain hand-over (first touch or lazily zeroed cell), otherwise an ordinary allocation
+std::shared_ptr<Buffer> grad_sink(const Tensor& param) {
+  if (param.grad && param.grad->sink && param.grad->next_accumulate_is_handover()) return param.grad->sink;
+  return nullptr;
 }
 
 Tensor fresh_like(const Tensor& x) { return Tensor(std::make_shared<Storage>(x.dev(), x.shape())); }
@@ -138,7 +146,7 @@ std::vector<Tensor> bwd(const Sigmoid&, const std::vector<Tensor>& xs, const Ten
 std::vector<Tensor> bwd(const Linear&, const std::vector<Tensor>& xs, const Tensor& grad) {
   const Tensor &x = xs.at(0), &w = xs.at(1);
   Tensor dx = gemm(grad, false, w, true);   // g.dot(&w.t_clone())   operators.rs:159
-  Tensor dw = gemm(x, true, grad, false);   // x.t_clone().dot(g)    operators.rs:160
+  Tensor dw = gemm(x, true, grad, false, nullptr, grad_sink(w));   // x.t_clone().dot(g)    operators.rs:160
   Tensor db = grad.sum_axis(0);             // 1-D [O]               operators.rs:161
   return {dx, dw, db};
 }

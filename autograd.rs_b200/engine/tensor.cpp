@@ -336,7 +336,7 @@ void Tensor::zero_grad() const {
   // only runs if somebody reads the gradient before the next accumulation (GradCell::get); the usual next event is
   // backward's `zeros += dW`, which then degenerates to taking dW's buffer (0 + x == x) -- no memset, no add pass.
   auto& g = grad->g;
-  if (g && g->len() == data->len() && g->buf.use_count() == 1) {
+  if (g && g->len() == data->len() && (g->buf.use_count() == 1 || g->buf == grad->sink)) {
     g->shape = data->shape;
     g->transposed = false;
   } else {

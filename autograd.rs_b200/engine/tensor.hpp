@@ -97,6 +97,10 @@ struct GradCell {  // Rc<RefCell<Option<StorageType<f32>>>>, tensor.rs:32
   StoragePtr g;
   bool zero_pending = false;   // g is logically all zeros but its buffer has not been cleared yet (lazy zero_grad)
   GradHook* hook = nullptr;    // not owned
+  // Preferred home of the NEXT gradient (a window of the data-parallel arena): an operator that produces this gradient as a
+  // fresh tensor may write it there directly, so the fused optimiser step finds it in place and no copy is needed.
+  std::shared_ptr<Buffer> sink;
+  bool next_accumulate_is_handover() const { return !g || zero_pending; }
   const StoragePtr& get();     // the gradient storage with any pending zero fill applied: what every reader must use
 };
 

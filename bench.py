@@ -400,9 +400,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce gradients after backward instead of during it")
     ap.add_argument("--fused", action="store_true", help="N > 1: one fused reduce-scatter + SGD + all-gather kernel over NVLink peer memory "
-                                                         "instead of NCCL all-reduce + SGD")
+                                                         "instead of NCCL all-reduce + SGD (the default)")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all-reduce per parameter + SGD kernel (the baseline the fused kernel replaces)")
     args = ap.parse_args()
     claim_stdout()
+    args.fused = not args.nccl
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     from autograd_rs_b200 import workloads as W
     cfg = dict(W.CONFIGS[args.config])
