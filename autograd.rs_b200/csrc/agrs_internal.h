@@ -25,6 +25,7 @@ struct agrs_ctx {
   int tc_bn = 256;         // tcgen05 tile width: 256 (2 smem stages) or 128 (3 stages)
   int tc_kchunk = 1024;    // K elements accumulated inside the tensor core before an RN fold into C (0: whole K)
   int tc_2cta = 1;         // use the cta_group::2 pair kernel when the problem has more than one 128-row block
+  int tc_splitk = 0;       // pair kernel: 0 = choose the K split that fills the last wave, n > 0 = force n splits
   int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
   int64_t tc_min_flops = 1LL << 24;  // AUTO path: below this many MACs the SIMT kernel wins on launch+fill latency
   // small scratch for reductions (block partials + completion counter), allocated once

@@ -28,6 +28,10 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
       AGRS_REQUIRE(ctx, value >= 0 && value < (1LL << 30), AGRS_ERR_INVALID, "AGRS_TUNE_TC_KCHUNK out of range");
       ctx->tc_kchunk = int(value);
       return AGRS_OK;
+    case AGRS_TUNE_TC_SPLITK:
+      AGRS_REQUIRE(ctx, value >= 0 && value <= 64, AGRS_ERR_INVALID, "AGRS_TUNE_TC_SPLITK out of range");
+      ctx->tc_splitk = int(value);
+      return AGRS_OK;
     case AGRS_TUNE_TC_2CTA:
       ctx->tc_2cta = value ? 1 : 0;
       return AGRS_OK;

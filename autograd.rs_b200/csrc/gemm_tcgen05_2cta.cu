@@ -81,7 +81,7 @@ __device__ __forceinline__ float lo_of(float x) {
 template <bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C, int64_t ldc,
-                   const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk) {
+                   const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
@@ -98,9 +98,25 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
   const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
-  const int64_t num_tiles = m_tiles * n_tiles;
   const int num_kb = int((K + BK - 1) / BK);
-  const int num_chunks = (num_kb + kb_per_chunk - 1) / kb_per_chunk;
+  // Work items = output tiles x K splits.  Splitting K fills the last wave when the tile count is just above a multiple of the
+  // 74 CTA pairs (dW of the 4096-wide layers: 256 tiles = 3.46 waves): split s > 0 writes its partial to the workspace Cw
+  // ([splits-1][M][N]) and a small kernel adds the partials to C in split order afterwards (deterministic).
+  const int64_t tiles_mn = m_tiles * n_tiles;
+  const int64_t num_tiles = tiles_mn * splits;
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  struct Work {
+    int64_t mb, nb;
+    int kb0, kb1, split;
+  };
+  auto work_item = [&](int64_t t) {
+    Work w;
+    w.split = int(t / tiles_mn);
+    tile_coords(t - w.split * tiles_mn, m_tiles, n_tiles, w.mb, w.nb);
+    w.kb0 = w.split * kb_per_split;
+    w.kb1 = w.kb0 + kb_per_split < num_kb ? w.kb0 + kb_per_split : num_kb;
+    return w;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -138,10 +154,9 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int r = 0;
       uint32_t rph = 0;
       for (int64_t t = pair; t < num_tiles; t += num_pairs) {
-        int64_t mb, nb;
-        tile_coords(t, m_tiles, n_tiles, mb, nb);
-        const int32_t m0 = int32_t(mb * 2 * BM + rank * BM), n0 = int32_t(nb * BN + rank * BNH);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const Work w = work_item(t);
+        const int32_t m0 = int32_t(w.mb * 2 * BM + rank * BM), n0 = int32_t(w.nb * BN + rank * BNH);
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(raw_free(r), rph ^ 1u);
           const uint32_t a_dst = smem_base + r * RAW_BYTES, b_dst = a_dst + A_BYTES;
           mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
@@ -169,18 +184,19 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int r = 0, l = 0, acc = 0;
       uint32_t lph = 0, acc_ph = 0;
       for (int64_t t = pair; t < num_tiles; t += num_pairs) {
-        for (int ch = 0; ch < num_chunks; ++ch) {
+        const Work w = work_item(t);
+        for (int c0 = w.kb0; c0 < w.kb1; c0 += kb_per_chunk) {
           mbar_wait_cluster(tempty_bar(acc), acc_ph ^ 1u);  // both epilogues have drained this accumulator stage
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-          const int kb_end = (ch + 1) * kb_per_chunk < num_kb ? (ch + 1) * kb_per_chunk : num_kb;
-          for (int kb = ch * kb_per_chunk; kb < kb_end; ++kb) {
+          const int kb_end = c0 + kb_per_chunk < w.kb1 ? c0 + kb_per_chunk : w.kb1;
+          for (int kb = c0; kb < kb_end; ++kb) {
             mbar_wait_cluster(split_done(l), lph);  // both CTAs: raw tile landed and lo tile written
             tc_fence_after();
             if (lane == 0) {
               const uint32_t a_hi = smem_base + r * RAW_BYTES, b_hi = a_hi + A_BYTES;
               const uint32_t a_lo = lo_base + l * RAW_BYTES, b_lo = a_lo + A_BYTES;
-              const bool first_kb = (kb == ch * kb_per_chunk);
+              const bool first_kb = (kb == c0);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 const uint64_t da_hi = make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>());
@@ -211,7 +227,8 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint32_t rph = 0, lph = 0;
     constexpr int kPerThread = RAW_BYTES / (kSplitWarps * 32 * 16);  // 8 float4 per thread per stage
     for (int64_t t = pair; t < num_tiles; t += num_pairs) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const Work w = work_item(t);
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(raw_full(r), rph);
         mbar_wait(lo_free(l), lph ^ 1u);
         const uint32_t src = smem_base + r * RAW_BYTES + tid * 16, dst = lo_base + l * RAW_BYTES + tid * 16;
@@ -237,14 +254,20 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ===================== epilogue (both CTAs): my 128 rows of the pair tile =====================
     const int q = warp - kEpiWarp0;  // == warp % 4: TMEM lanes [32q, 32q+32)
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+    const bool vec_w = ((N & 3) == 0) && (((M * N) & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cw) & 15u) == 0);
     const uint32_t tempty_remote = mapa_rank(tempty_bar(0), 0);
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int64_t t = pair; t < num_tiles; t += num_pairs) {
-      int64_t mb, nb;
-      tile_coords(t, m_tiles, n_tiles, mb, nb);
-      const int64_t row = mb * 2 * BM + rank * BM + q * 32 + lane;
-      for (int ch = 0; ch < num_chunks; ++ch) {
+      const Work w = work_item(t);
+      const int64_t nb = w.nb;
+      const int64_t row = w.mb * 2 * BM + rank * BM + q * 32 + lane;
+      // split 0 produces C (with the bias); split s > 0 its own partial [M][N] in the workspace
+      float* const Cs = w.split == 0 ? C : Cw + int64_t(w.split - 1) * M * N;
+      const int64_t lds = w.split == 0 ? ldc : N;
+      const float* const bias_s = w.split == 0 ? bias : nullptr;
+      const bool vec_s = w.split == 0 ? vec_ok : vec_w;
+      for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
@@ -255,13 +278,13 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tmem_wait_ld();
           const int64_t col0 = nb * BN + c * 32;
           if (row < M && col0 < N) {
-            float* dst = C + row * ldc + col0;
-            if (vec_ok && col0 + 32 <= N) {
+            float* dst = Cs + row * lds + col0;
+            if (vec_s && col0 + 32 <= N) {
               float4 base[8];
               if (ch == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  base[j] = bias ? __ldg(reinterpret_cast<const float4*>(bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  base[j] = bias_s ? __ldg(reinterpret_cast<const float4*>(bias_s + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) base[j] = *reinterpret_cast<const float4*>(dst + 4 * j);  // previous chunks (L2)
@@ -279,7 +302,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < N) {
-                  float b = ch == 0 ? (bias ? __ldg(bias + col0 + j) : 0.f) : dst[j];
+                  float b = ch == 0 ? (bias_s ? __ldg(bias_s + col0 + j) : 0.f) : dst[j];
                   dst[j] = b + __uint_as_float(v[j]);
                 }
             }
@@ -302,6 +325,47 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
+// C[m, n] += P_1[m, n] + P_2[m, n] + ..  (split order; P_s contiguous [M][N])
+__global__ void __launch_bounds__(256) k_add_partials(float* __restrict__ C, int64_t ldc, const float* __restrict__ P, int nparts, int64_t M,
+                                                      int64_t N) {
+  const int64_t total = M * N, stride = int64_t(gridDim.x) * blockDim.x;
+  if ((N & 3) == 0 && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(P)) & 15u) == 0) {
+    for (int64_t i4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i4 < total / 4; i4 += stride) {
+      const int64_t i = i4 * 4, m = i / N, n = i - m * N;
+      float4 c = *reinterpret_cast<const float4*>(C + m * ldc + n);
+      for (int s = 0; s < nparts; ++s) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(P + int64_t(s) * total + i));
+        c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+      }
+      *reinterpret_cast<float4*>(C + m * ldc + n) = c;
+    }
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const int64_t m = i / N, n = i - m * N;
+      float c = C[m * ldc + n];
+      for (int s = 0; s < nparts; ++s) c += P[int64_t(s) * total + i];
+      C[m * ldc + n] = c;
+    }
+  }
+}
+
+// K splits that fill the last wave of CTA pairs: efficiency = work items / (waves * pairs)
+static int choose_splits(int64_t tiles, int64_t pairs, int64_t num_kb, int forced) {
+  if (forced > 0) return int(forced < num_kb ? forced : num_kb);
+  auto eff = [&](int64_t items) { return double(items) / double(((items + pairs - 1) / pairs) * pairs); };
+  int best = 1;
+  double best_eff = eff(tiles);
+  for (int s = 2; s <= 4; ++s) {
+    if (num_kb / s < 8) break;  // at least 256 of K per split
+    const double e = eff(tiles * s);
+    if (e > best_eff * 1.05) {  // worth a second pass over C only for a real gain
+      best = s;
+      best_eff = e;
+    }
+  }
+  return best;
+}
+
 template <bool A_MN, bool B_MN>
 static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
                   int64_t N, int64_t K, int kb_per_chunk) {
@@ -309,9 +373,27 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int64_t pairs = ctx->sm_count / 2;
-  const int grid = int(2 * (tiles < pairs ? tiles : pairs));
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk);
+  const int64_t num_kb = (K + BK - 1) / BK;
+  int splits = choose_splits(tiles, pairs, num_kb, ctx->tc_splitk);
+  {  // the kernel gives every split ceil(num_kb / splits) k-blocks: drop splits that would be left with none
+    const int64_t kps = (num_kb + splits - 1) / splits;
+    splits = int((num_kb + kps - 1) / kps);
+  }
+  float* Cw = nullptr;
+  if (splits > 1) {
+    int rc = agrs_ensure_workspace(ctx, size_t(splits - 1) * size_t(M) * size_t(N) * sizeof(float));
+    if (rc) return rc;
+    Cw = ctx->workspace;
+  }
+  const int64_t items = tiles * splits;
+  const int grid = int(2 * (items < pairs ? items : pairs));
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw);
   AGRS_LAUNCHED(ctx);
+  if (splits > 1) {
+    const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
+    k_add_partials<<<unsigned(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap), 256, 0, ctx->stream>>>(C, ldc, Cw, splits - 1, M, N);
+    AGRS_LAUNCHED(ctx);
+  }
   return AGRS_OK;
 }
 

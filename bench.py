@@ -362,8 +362,18 @@ def run_b200_arm(args, cfg):
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak_alg, "unit": "TFLOP/s", "frac": ach / peak_alg, "traffic": traffic,
                     "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2 kind::tf32 x3)", "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_tflops": 3 * ach,
-                    "gemm_share_of_step": g_ms / (ms if world == 1 else ms),
+                    "gemm_share_of_step": g_ms / ms,
                     "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / 3 (3xTF32)"}
+        # context: what cuBLAS itself reaches on this pool's B200s for PLAIN tf32 (one MMA per product) -- tools/tf32_cublas_peak.py
+        cub = os.path.join(ROOT, "profiles", "r1_cublas_peaks.json")
+        if os.path.exists(cub):
+            try:
+                c = json.load(open(cub))
+                roofline["cublas_tf32_tflops"] = {"burst": c["tf32"]["burst_tflops"], "sustained": c["tf32"]["sustained_tflops"]}
+                roofline["executed_frac_of_cublas_tf32_sustained"] = 3 * ach / c["tf32"]["sustained_tflops"]
+                roofline["cublas_f32_simt_tflops"] = c["f32_simt"]["sustained_tflops"]
+            except Exception:
+                pass
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

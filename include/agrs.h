@@ -91,7 +91,8 @@ enum agrs_tuning_key {
   AGRS_TUNE_TC_EXPLICIT_HI = 1, /* 1: write the tf32-truncated hi tile explicitly instead of relying on the MMA ignoring the low 13 bits */
   AGRS_TUNE_TC_MIN_MACS = 2,    /* AUTO path: minimum M*N*K for the tcgen05 kernel */
   AGRS_TUNE_TC_KCHUNK = 3,      /* K elements accumulated in TMEM between round-to-nearest folds into C (0 = all of K; default 1024) */
-  AGRS_TUNE_TC_2CTA = 4         /* 1 (default): cta_group::2 pair kernel (256x256 tiles) when M > 128; 0: always the one-CTA kernel */
+  AGRS_TUNE_TC_2CTA = 4,        /* 1 (default): cta_group::2 pair kernel (256x256 tiles) when M > 128; 0: always the one-CTA kernel */
+  AGRS_TUNE_TC_SPLITK = 5       /* pair kernel: 0 (default) = pick the K split that fills the last wave of CTA pairs; n = force n splits */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
 

@@ -299,6 +299,39 @@ def test_gemm_simt(ctx, M, N, Kd, ta, tb):
     assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_SIMT
 
 
+# ------------------------------------------------------------------ tcgen05 3xTF32 GEMMs (one-CTA and pair kernels, K splits)
+@pytest.mark.parametrize("M,N,Kd,ta,tb", [(256, 256, 32, 0, 1), (384, 1000, 520, 0, 1), (1000, 520, 3000, 1, 0), (200, 300, 100, 1, 1),
+                                         (2048, 1024, 1024, 0, 0), (132, 260, 4100, 1, 1), (129, 8, 8, 0, 0), (4100, 132, 260, 1, 0)])
+@pytest.mark.parametrize("pair,splitk", [(0, 0), (1, 0), (1, 1), (1, 2), (1, 3)])
+def test_gemm_tcgen05(ctx, M, N, Kd, ta, tb, pair, splitk):
+    """f32-faithful: max error <= 2e-5 of max|C| against the f64 product (measured ~8e-6; plain TF32 would be ~5e-4)"""
+    rng = np.random.default_rng(M + 3 * N + 5 * Kd + pair)
+    ctx.call("agrs_set_tuning", K.TUNE_TC_2CTA, pair)
+    ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, splitk)
+    try:
+        for bias in (False, True):
+            gemm_case(ctx, rng, M, N, Kd, ta, tb, bias, K.GEMM_TCGEN05, 2e-5)
+            assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_TCGEN05
+    finally:
+        ctx.call("agrs_set_tuning", K.TUNE_TC_2CTA, 1)
+        ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, 0)
+
+
+def test_gemm_tcgen05_special_values(ctx):
+    """inf / NaN / zeros propagate as in f32 arithmetic (the lo term of a non-finite value is forced to 0)"""
+    A = np.ones((256, 64), np.float32)
+    B = np.ones((64, 256), np.float32)
+    A[3, 5] = np.inf
+    A[7, 1] = np.nan
+    A[9, :] = 0.0
+    for pair in (0, 1):
+        ctx.call("agrs_set_tuning", K.TUNE_TC_2CTA, pair)
+        got = ctx.gemm(A, B, path=K.GEMM_TCGEN05)
+        assert np.all(np.isposinf(got[3])) and np.all(np.isnan(got[7])) and np.all(got[9] == 0.0)
+        assert np.all(got[0] == 64.0)
+    ctx.call("agrs_set_tuning", K.TUNE_TC_2CTA, 1)
+
+
 # ------------------------------------------------------------------ skinny (HBM-bound) GEMMs: the LeNet / conv-lowering shapes
 @pytest.mark.parametrize("M,N,Kd,ta,tb", [
     (20000, 6, 25, 0, 0),     # conv forward: col . K + bias      (rows kernel)

@@ -14,12 +14,13 @@ import autograd_rs_b200  # noqa: F401,E402
 from autograd_rs_b200 import _capi  # noqa: E402
 
 
-def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias=False):
+def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias=False, splitk=0):
     A = rng.uniform(-1, 1, (K, M) if ta else (M, K)).astype(np.float32)
     B = rng.uniform(-1, 1, (N, K) if tb else (K, N)).astype(np.float32)
     bv = rng.uniform(-1, 1, N).astype(np.float32) if bias else None
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_2CTA, pair)
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_KCHUNK, kchunk)
+    ctx.call("agrs_set_tuning", _capi.TUNE_TC_SPLITK, splitk)
     ctx.call("agrs_set_gemm_path", _capi.GEMM_TCGEN05)
     dA, dB, dC = ctx.to_device(A), ctx.to_device(B), ctx.empty(M * N)
     dbias = ctx.to_device(bv) if bias else None
@@ -34,7 +35,7 @@ def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias
     err = float(np.abs(got[rows] - truth).max() / scale)
     f32 = ((A.T if ta else A)[rows] @ (B.T if tb else B)).astype(np.float64) + (bv if bias else 0.0)
     err32 = float(np.abs(f32 - truth).max() / scale)
-    res = {"M": M, "N": N, "K": K, "ta": int(ta), "tb": int(tb), "pair": pair, "kchunk": kchunk, "bias": bias, "rel_err_vs_f64": err,
+    res = {"M": M, "N": N, "K": K, "ta": int(ta), "tb": int(tb), "pair": pair, "kchunk": kchunk, "splitk": splitk, "bias": bias, "rel_err_vs_f64": err,
            "numpy_f32_rel_err_vs_f64": err32, "finite": bool(np.isfinite(got).all())}
     if iters:
         for _ in range(3):
@@ -59,6 +60,7 @@ def main():
     ap.add_argument("--odd", action="store_true", help="ragged shapes (partial tiles in M, N and K)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kchunk", type=int, default=1024)
+    ap.add_argument("--splitk", default="0", help="comma list of forced K splits for the pair kernel (0 = automatic)")
     ap.add_argument("--majors", default="00,01,10", help="ta tb pairs for the square sizes: 00 = X.W, 01 = G.W^T, 10 = X^T.G, 11")
     a = ap.parse_args()
     pairs = [0, 1] if a.pair == "both" else [int(a.pair)]
@@ -77,9 +79,10 @@ def main():
     out = []
     for (M, N, K, ta, tb, bias) in cases:
         for p in pairs:
-            r = run_case(ctx, M, N, K, ta, tb, p, a.iters, a.kchunk, rng, bias=bias)
-            print(json.dumps(r), flush=True)
-            out.append(r)
+            for sk in ([int(x) for x in a.splitk.split(",")] if p else [0]):
+                r = run_case(ctx, M, N, K, ta, tb, p, a.iters, a.kchunk, rng, bias=bias, splitk=sk)
+                print(json.dumps(r), flush=True)
+                out.append(r)
     bad = [r for r in out if not r["finite"] or r["rel_err_vs_f64"] > 2e-5]
     print(json.dumps({"cases": len(out), "bad": len(bad), "max_rel_err": max(r["rel_err_vs_f64"] for r in out)}))
     ctx.close()
