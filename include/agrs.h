@@ -76,7 +76,8 @@ AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);     
  * transB=0: B is [K,N] (ldb>=N); transB=1: B is stored [N,K] (ldb>=K)   -- dX = G W^T (operators.rs:159)
  * so the reference's materialised t_clone() copies (storage.rs:84-88) never exist on the device.
  * bias != NULL fuses `+ b` of Linear::forward / Conv2D::forward (operators.rs:144, :379) into the epilogue.
- * Large aligned shapes run the TMA + tcgen05 3xTF32 kernel (f32-faithful: hi*hi + hi*lo + lo*hi);
+ * Large aligned shapes run the TMA + tcgen05 3xTF32 kernel (f32-faithful: hi*hi + hi*lo + lo*hi; finite inputs: <= 1e-5 of
+ * max|C|; NaN and zero propagate as in f32; an inf INPUT yields a non-finite result that may be NaN where f32 gives inf);
  * skinny outputs (N <= 32: the Conv2D lowering, Linear(3456,10)) run HBM-bound streaming kernels; everything else runs the
  * tiled SIMT f32 kernel.  All are CUDA; the choice never changes semantics. */
 AGRS_API int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
