@@ -44,6 +44,21 @@ def test_engine_fails_loudly_without_device():
     assert e.value.code == 5 and "no CPU fallback" in str(e.value)
 
 
+def test_rust_sys_crate_matches_headers():
+    """rust/agrs-sys/src/lib.rs (generated, uncompiled here) declares exactly the functions the two headers declare"""
+    import importlib.util
+    import re
+    root = os.path.dirname(_capi.HERE)
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(root, "tools", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    on_disk = open(os.path.join(root, "rust", "agrs-sys", "src", "lib.rs")).read()
+    assert on_disk == gen.render(), "run python tools/gen_rust_sys.py"
+    from autograd_rs_b200 import frontend
+    declared = set(_capi.declared_symbols()) | set(frontend.declared_symbols())
+    assert set(re.findall(r"pub fn (agrs_\w+)\(", on_disk)) == declared
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
