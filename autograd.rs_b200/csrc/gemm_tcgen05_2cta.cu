@@ -23,6 +23,10 @@ constexpr int kThreads = 512;
 constexpr int kEpiWarp0 = 4;
 constexpr int kSplitWarp0 = 8;
 constexpr int kSplitWarps = 8;
+#ifndef AGRS_SPLIT_GROUPS
+#define AGRS_SPLIT_GROUPS 2
+#endif
+constexpr int kSplitGroups = AGRS_SPLIT_GROUPS;  // groups of splitter warps that alternate k-blocks
 constexpr int BN = 256;   // pair-tile width
 constexpr int BNH = 128;  // columns of B staged per CTA
 constexpr int R = 4;      // raw (TMA) stages
@@ -129,7 +133,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     for (int s = 0; s < L; ++s) {
       mbar_init(lo_free(s), 1);
-      mbar_init(split_done(s), 2 * kSplitWarps);  // both CTAs' splitter warps arrive on the leader's barrier
+      mbar_init(split_done(s), 2 * kSplitWarps / kSplitGroups);  // the splitter warps of one group, in both CTAs, arrive on the leader's barrier
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -221,14 +225,21 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp >= kSplitWarp0) {
     // ===================== splitters (both CTAs): lo = x - trunc_tf32(x), same swizzled offsets as the raw tile =====================
-    const int tid = threadIdx.x - kSplitWarp0 * 32;  // 0..255
+    // The 8 warps form kSplitGroups groups that take k-blocks in turn (group g: k-blocks g, g + kSplitGroups, ..): every warp
+    // then has kSplitGroups k-block times for its wait -> load -> split -> store -> fence -> arrive chain, whose fixed latencies
+    // (barrier polls, LDS round trip, proxy fence) would otherwise cap the pipeline with all 8 warps serialised on each k-block.
+    constexpr int kGroupWarps = kSplitWarps / kSplitGroups;
+    const int grp = (warp - kSplitWarp0) / kGroupWarps;
+    const int tid = threadIdx.x - (kSplitWarp0 + grp * kGroupWarps) * 32;  // 0 .. 32*kGroupWarps-1 inside the group
     const uint32_t done_remote = mapa_rank(split_done(0), 0);
-    int r = 0, l = 0;
-    uint32_t rph = 0, lph = 0;
-    constexpr int kPerThread = RAW_BYTES / (kSplitWarps * 32 * 16);  // 8 float4 per thread per stage
+    constexpr int kPerThread = RAW_BYTES / (kGroupWarps * 32 * 16);  // float4 per thread per stage
+    constexpr uint32_t kStride = kGroupWarps * 32 * 16;
+    uint32_t it = 0;  // k-blocks since kernel start: ring positions are it % R and it % L
     for (int64_t t = pair; t < num_tiles; t += num_pairs) {
       const Work w = work_item(t);
-      for (int kb = w.kb0; kb < w.kb1; ++kb) {
+      for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
+        if (int(it % kSplitGroups) != grp) continue;
+        const uint32_t r = it % R, rph = (it / R) & 1u, l = it % L, lph = (it / L) & 1u;
         mbar_wait(raw_full(r), rph);
         mbar_wait(lo_free(l), lph ^ 1u);
         const uint32_t src = smem_base + r * RAW_BYTES + tid * 16, dst = lo_base + l * RAW_BYTES + tid * 16;
@@ -237,17 +248,15 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int i = 0; i < kPerThread; ++i)
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                        : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
-                       : "r"(src + i * (kSplitWarps * 32 * 16)));
+                       : "r"(src + i * kStride));
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i)
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + i * (kSplitWarps * 32 * 16)), "f"(lo_of(v[i].x)),
-                       "f"(lo_of(v[i].y)), "f"(lo_of(v[i].z)), "f"(lo_of(v[i].w))
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + i * kStride), "f"(lo_of(v[i].x)), "f"(lo_of(v[i].y)),
+                       "f"(lo_of(v[i].z)), "f"(lo_of(v[i].w))
                        : "memory");
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(done_remote + 8u * l);
-        if (++r == R) { r = 0; rph ^= 1u; }
-        if (++l == L) { l = 0; lph ^= 1u; }
       }
     }
   } else if (warp >= kEpiWarp0) {
