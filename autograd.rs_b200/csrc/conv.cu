@@ -2,6 +2,8 @@
 // Index maps follow src/operators/functional_ndarray.rs:40-138 of the reference exactly;
 // both are pure data movement (HBM-bound).  Samples that fit in shared memory take the staged kernels (k_*_tile);
 // the one-thread-per-output-element kernels remain for samples that do not.
+#include <stdlib.h>
+
 #include "agrs_internal.h"
 
 namespace {
@@ -133,30 +135,91 @@ __global__ void __launch_bounds__(kTileThreads) k_im2col_tile(const float* __res
 }
 
 // same summation order as k_col2im (increasing patch index), reading the sample's col block from shared memory.
-// The block is staged with cp.async (16-byte LDGSTS, no register round trip, every thread's copies in flight at once).
-__global__ void __launch_bounds__(kTileThreads) k_col2im_tile(const float* __restrict__ col, int B, int C, int Hi, int Wi, int k, int s, int Ho,
-                                                              int Wo, float* __restrict__ im, int vec_in) {
-  extern __shared__ float sm[];
+// The block is staged with cp.async (16-byte LDGSTS, no register round trip).  NBUF = 2: while the CTA gathers sample i from
+// one buffer, the cp.async copies of sample i+1 are already in flight into the other (one CTA of 1024 threads per SM);
+// NBUF = 1 for col blocks too large to double-buffer.
+template <int NBUF, int KS>  // KS: kernel size known at compile time (0 = run time): the stride-1 gather is then fully unrolled
+__global__ void __launch_bounds__(NBUF >= 2 ? 1024 : kTileThreads) k_col2im_tile(const float* __restrict__ col, int B, int C, int Hi, int Wi, int k,
+                                                                               int s, int Ho, int Wo, float* __restrict__ im, int vec_in) {
+  extern __shared__ float sm_all[];
   const int kk = k * k, K = C * kk, P = Ho * Wo, per = P * K, n_im = C * Hi * Wi;
-  const uint32_t sm_addr = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
-    __syncthreads();
+  const int per_pad = (per + 3) & ~3;
+  const uint32_t sm_addr = static_cast<uint32_t>(__cvta_generic_to_shared(sm_all));
+  auto stage = [&](int b, int buf) {  // start copying sample b's col block into buffer buf
     const float* src = col + int64_t(b) * per;
     if (vec_in) {
       for (int t = threadIdx.x; t < per / 4; t += blockDim.x)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sm_addr + 16u * t), "l"(src + 4 * t) : "memory");
-      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sm_addr + 4u * (buf * per_pad) + 16u * t), "l"(src + 4 * t) : "memory");
     } else {
-      for (int t = threadIdx.x; t < per; t += blockDim.x) sm[t] = __ldg(src + t);
+      float* dstb = sm_all + buf * per_pad;
+      for (int t = threadIdx.x; t < per; t += blockDim.x) dstb[t] = __ldg(src + t);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto decode_taps = [&](int idx, int& base, uint32_t& mask) {
+    const int w = idx % Wi, t = idx / Wi, h = t % Hi, c = t / Hi;
+    base = (h * Wo + w) * K + c * kk;
+    mask = 0;
+    for (int i = 0; i < KS; ++i)
+      for (int j = 0; j < KS; ++j)
+        if (h - i >= 0 && h - i < Ho && w - j >= 0 && w - j < Wo) mask |= 1u << (i * KS + j);
+  };
+  int tap_base0 = 0;
+  uint32_t tap_mask0 = 0;
+  if (KS > 0 && s == 1 && int(threadIdx.x) < n_im) decode_taps(threadIdx.x, tap_base0, tap_mask0);
+  int buf = 0;
+  if (NBUF >= 2) {  // prologue: NBUF-1 samples in flight (empty groups keep the group count uniform)
+#pragma unroll
+    for (int j = 0; j < NBUF - 1; ++j) {
+      const int64_t pb = int64_t(blockIdx.x) + int64_t(j) * gridDim.x;
+      if (pb < B) stage(int(pb), j);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    if (NBUF >= 2) {
+      const int64_t nb = int64_t(b) + int64_t(NBUF - 1) * gridDim.x;
+      int nbuf = buf + NBUF - 1;
+      nbuf -= nbuf >= NBUF ? NBUF : 0;
+      if (nb < B) stage(int(nb), nbuf);  // NBUF-1 samples ahead: in flight during this gather
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(NBUF >= 2 ? NBUF - 1 : 0) : "memory");  // this sample has landed
+    } else {
+      __syncthreads();  // previous sample fully consumed
+      stage(b, 0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const float* sm = sm_all + buf * per_pad;
     float* dst = im + int64_t(b) * n_im;
+    if (KS > 0 && s == 1) {
+      // Unit stride, kernel size known: which taps of an output pixel exist and where its first patch sits depend on (c, h, w)
+      // only, so they were decoded once per thread (tap_mask0 / tap_base0) for the pixel the thread owns in the first round.
+      // Every tap is then an independent predicated shared-memory load, all in flight at once, added in the reference's order.
+      for (int idx = threadIdx.x, round = 0; idx < n_im; idx += blockDim.x, ++round) {
+        int base = tap_base0;
+        uint32_t mask = tap_mask0;
+        if (round > 0) decode_taps(idx, base, mask);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = KS - 1; i >= 0; --i) {
+#pragma unroll
+          for (int j = KS - 1; j >= 0; --j) {
+            const bool ok = (mask >> (i * KS + j)) & 1u;
+            const float v = ok ? sm[base + i * KS + j - (i * Wo + j) * K] : 0.f;  // patch (h-i, w-j), tap (i, j)
+            acc = ok ? acc + v : acc;
+          }
+        }
+        __stcs(dst + idx, acc);
+      }
+    } else
     for (int idx = threadIdx.x; idx < n_im; idx += blockDim.x) {
       const int w = idx % Wi;
       int t = idx / Wi;
       const int h = t % Hi, c = t / Hi;
       float acc = 0.f;
-      if (s == 1) {  // unit stride: taps i in [h-Ho+1, h] and j in [w-Wo+1, w], clipped to the kernel
+      if (KS > 0 && s == 1) {  // handled by the hoisted path above
+      } else if (s == 1) {  // unit stride: taps i in [h-Ho+1, h] and j in [w-Wo+1, w], clipped to the kernel
         const int i_hi = h < k - 1 ? h : k - 1, i_lo = h - (Ho - 1) > 0 ? h - (Ho - 1) : 0;
         const int j_hi = w < k - 1 ? w : k - 1, j_lo = w - (Wo - 1) > 0 ? w - (Wo - 1) : 0;
         for (int i = i_hi; i >= i_lo; --i) {
@@ -178,7 +241,11 @@ __global__ void __launch_bounds__(kTileThreads) k_col2im_tile(const float* __res
           }
         }
       }
-      dst[idx] = acc;
+      __stcs(dst + idx, acc);
+    }
+    if (NBUF >= 2) {
+      __syncthreads();  // everybody is done with this buffer before a later iteration's copies overwrite it
+      buf = buf + 1 == NBUF ? 0 : buf + 1;
     }
   }
 }
@@ -243,11 +310,32 @@ int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t C, int64
   const int64_t per = Ho * Wo * C * k * k;
   const size_t smem = size_t(per) * sizeof(float);
   if (smem <= kTileSmemMax && C * Hi * Wi < (1LL << 30) && B < (1LL << 31)) {
-    AGRS_CUDA(ctx, cudaFuncSetAttribute(k_col2im_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));
     const int vec_in = (per % 4 == 0) && agrs_aligned16(col);
-    const int64_t cap = int64_t(ctx->sm_count) * 4;
-    k_col2im_tile<<<unsigned(B < cap ? B : cap), kTileThreads, smem, ctx->stream>>>(col, int(B), int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho),
-                                                                          int(Wo), im_out, vec_in);
+    const size_t per_pad = size_t((per + 3) & ~int64_t(3)) * sizeof(float);
+    static const int nbuf_env = getenv("AGRS_COL2IM_NBUF") ? atoi(getenv("AGRS_COL2IM_NBUF")) : 3;
+    int nbuf = 1;  // samples resident per CTA: as many as fit (up to 3) when there are enough samples to pipeline
+    if (B >= 2 * int64_t(ctx->sm_count) && nbuf_env >= 2) nbuf = (nbuf_env >= 3 && 3 * per_pad <= kTileSmemMax) ? 3 : (2 * per_pad <= kTileSmemMax ? 2 : 1);
+    const int64_t per_sm = nbuf == 1 ? 4 : (int64_t(kTileSmemMax) / int64_t(nbuf * per_pad) >= 2 ? 2 : 1);
+    const int64_t cap = int64_t(ctx->sm_count) * per_sm;
+    const unsigned grid = unsigned(B < cap ? B : cap);
+#define AGRS_COL2IM(NB_, KS_)                                                                                                        \
+  do {                                                                                                                                \
+    AGRS_CUDA(ctx, cudaFuncSetAttribute(k_col2im_tile<NB_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileSmemMax)));    \
+    k_col2im_tile<NB_, KS_><<<grid, NB_ >= 2 ? 1024 : kTileThreads, NB_ * per_pad, ctx->stream>>>(col, int(B), int(C), int(Hi), int(Wi), int(k),    \
+                                                                                                 int(stride), int(Ho), int(Wo), im_out, vec_in); \
+  } while (0)
+#define AGRS_COL2IM_K(NB_)                          \
+  do {                                              \
+    if (k == 5) AGRS_COL2IM(NB_, 5);                \
+    else if (k == 3) AGRS_COL2IM(NB_, 3);           \
+    else if (k == 2) AGRS_COL2IM(NB_, 2);           \
+    else AGRS_COL2IM(NB_, 0);                       \
+  } while (0)
+    if (nbuf == 3) AGRS_COL2IM_K(3);
+    else if (nbuf == 2) AGRS_COL2IM_K(2);
+    else AGRS_COL2IM_K(1);
+#undef AGRS_COL2IM_K
+#undef AGRS_COL2IM
   } else {
     k_col2im<<<grid1d(ctx, total), 256, 0, ctx->stream>>>(col, total, int(C), int(Hi), int(Wi), int(k), int(stride), int(Ho), int(Wo), im_out);
   }
