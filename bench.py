@@ -85,6 +85,20 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_ready(self, timeout=6.0):
+        """Block until nvidia-smi has printed its first sample: its start-up (NVML initialisation, device enumeration) takes
+        a few hundred ms and contends for the driver with CUDA launches -- it must be over before anything is timed."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.05)
+
     def window(self, t0, t1):
         self.windows.append((t0, t1))
 
@@ -281,6 +295,8 @@ def run_b200_arm(args, cfg):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    barrier()
     for _ in range(args.warmup):
         loss = tr.step(X, T)
     barrier()
