@@ -52,6 +52,8 @@ def lib():
             "agrs_device_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(sz), C.POINTER(sz)],
             "agrs_alloc": [vp, sz, C.POINTER(vp)],
             "agrs_free": [vp, vp],
+            "agrs_pool_reserve": [vp, sz],
+            "agrs_pool_stats": [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)],
             "agrs_host_alloc": [vp, sz, C.POINTER(vp)],
             "agrs_host_free": [vp, vp],
             "agrs_upload": [vp, vp, vp, sz],

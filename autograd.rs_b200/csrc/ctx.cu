@@ -232,6 +232,28 @@ int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
   return AGRS_OK;
 }
 
+int agrs_pool_reserve(agrs_ctx* ctx, size_t nbytes) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_NOT_CAPTURING(ctx, "agrs_pool_reserve");
+  if (nbytes == 0) return AGRS_OK;
+  void* p = nullptr;
+  AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  AGRS_CUDA(ctx, cudaMallocFromPoolAsync(&p, nbytes, ctx->pool, ctx->stream));
+  AGRS_CUDA(ctx, cudaFreeAsync(p, ctx->stream));
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AGRS_OK;
+}
+
+int agrs_pool_stats(agrs_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes, size_t* reserved_high, size_t* used_high) {
+  AGRS_CHECK_CTX(ctx);
+  uint64_t v = 0;
+  if (reserved_bytes) { AGRS_CUDA(ctx, cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &v)); *reserved_bytes = size_t(v); }
+  if (used_bytes) { AGRS_CUDA(ctx, cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &v)); *used_bytes = size_t(v); }
+  if (reserved_high) { AGRS_CUDA(ctx, cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemHigh, &v)); *reserved_high = size_t(v); }
+  if (used_high) { AGRS_CUDA(ctx, cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemHigh, &v)); *used_high = size_t(v); }
+  return AGRS_OK;
+}
+
 int agrs_free(agrs_ctx* ctx, void* ptr) {
   AGRS_CHECK_CTX(ctx);
   if (!ptr) return AGRS_OK;

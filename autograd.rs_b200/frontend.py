@@ -211,6 +211,16 @@ class Device:
         self._k("agrs_profile_gemm", int(path), C.byref(n), C.byref(ms), C.byref(fl))
         return int(n.value), float(ms.value), float(fl.value)
 
+    # ---- memory pool: back it with device memory up front so that no training step pays for pool growth (a driver call)
+    def pool_reserve(self, nbytes):
+        self._k("agrs_pool_reserve", int(nbytes))
+
+    def pool_stats(self):
+        """(reserved now, used now, reserved high-water mark, used high-water mark) in bytes"""
+        a = [C.c_size_t() for _ in range(4)]
+        self._k("agrs_pool_stats", *[C.byref(x) for x in a])
+        return tuple(int(x.value) for x in a)
+
     # ---- whole-step CUDA graphs (agrs_capture_*): record one or more training steps, replay them with one driver call each
     def capture_begin(self):
         self._k("agrs_capture_begin")

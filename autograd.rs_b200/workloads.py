@@ -95,6 +95,19 @@ class Trainer:
         self.model.zero_grad()
         return loss
 
+    def reserve_pool(self, x, t, factor=2.5):
+        """Run one iteration, then back the device memory pool with `factor` x its high-water mark in one block.  Two steps'
+        worth of activations are alive at a time (the previous step's graph is dropped after the next one is enqueued), and
+        without this the stream-ordered pool keeps growing in small increments for several steps -- each growth a driver call
+        of 1-100 ms on the host inside what may be a timed region."""
+        dev = x.dev
+        loss = self.step(x, t)
+        dev.sync()
+        del loss
+        used_high = dev.pool_stats()[3]
+        dev.pool_reserve(int(factor * used_high) + (64 << 20))
+        return used_high
+
     def capture(self, x, t, unroll=1, warmup=2):
         """Record `unroll` consecutive iterations on (x, t) as ONE CUDA graph.  The host walks the model once, here; replay()
         then costs one driver call per `unroll` steps -- what launch-bound configurations (fit_sine: ~11 tiny kernels per

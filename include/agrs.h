@@ -57,6 +57,10 @@ AGRS_API int agrs_device_info(agrs_ctx* ctx, int* sm_count, int* cc_major, int* 
 AGRS_API uint64_t agrs_launch_count(agrs_ctx* ctx);
 
 AGRS_API int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out); /* stream-ordered pool; 256-B aligned */
+/* Back the pool with `nbytes` of device memory now (allocate + free once; the pool never returns memory to the driver), so that
+ * the first training steps do not pay for pool growth -- a driver call that takes milliseconds per GB -- inside a timed region. */
+AGRS_API int agrs_pool_reserve(agrs_ctx* ctx, size_t nbytes);
+AGRS_API int agrs_pool_stats(agrs_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes, size_t* reserved_high, size_t* used_high);
 AGRS_API int agrs_free(agrs_ctx* ctx, void* ptr);                  /* stream-ordered: safe with work in flight */
 AGRS_API int agrs_host_alloc(agrs_ctx* ctx, size_t nbytes, void** out); /* pinned host staging */
 AGRS_API int agrs_host_free(agrs_ctx* ctx, void* ptr);
