@@ -753,12 +753,32 @@ class DataParallel:
     def enable_fused(self, all_gather):
         """Move the parameters into an IPC-exported arena and map every peer's arena.  `all_gather(bytes) -> list[bytes]` is the
         launcher's exchange (rank order), e.g. torch.distributed.all_gather_object; for world == 1 pass `lambda h: [h]`."""
+        # Both phases end in a collective vote, so a rank whose set-up fails (no IPC / no peer access on this machine) can never
+        # leave the others waiting: either every rank switches to the fused step or none does (the NCCL exchange stays in use;
+        # parameters that already moved into the arena simply keep living there).  Returns True when the fused step is active.
         buf = C.create_string_buffer(64)
-        _check(lib().agrs_eng_dp_fused_prepare(self._h, buf))
-        handles = all_gather(buf.raw)
-        assert len(handles) == self.world and all(len(h) == 64 for h in handles)
-        _check(lib().agrs_eng_dp_fused_connect(self._h, b"".join(handles)))
+        err = None
+        try:
+            _check(lib().agrs_eng_dp_fused_prepare(self._h, buf))
+            mine = buf.raw
+        except Panic as e:
+            err, mine = e, b""
+        handles = all_gather(mine)
+        assert len(handles) == self.world
+        if any(len(h) != 64 for h in handles):
+            self.fused_error = err or "a peer could not export its arena"
+            return False
+        try:
+            _check(lib().agrs_eng_dp_fused_connect(self._h, b"".join(handles)))
+            ok = b"\x01"
+        except Panic as e:
+            err, ok = e, b"\x00"
+        votes = all_gather(ok)
+        if any(v != b"\x01" for v in votes):
+            self.fused_error = err or "a peer could not map the arenas"
+            return False
         self.fused = True
+        return True
 
     def fused_sgd_step(self, lr):
         """reduce-scatter(grad) + w -= lr * mean(grad) + all-gather(w) in one kernel; replaces sync_grads() and SGD.step()"""

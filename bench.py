@@ -265,7 +265,10 @@ def run_b200_arm(args, cfg):
                 out = [None] * world
                 dist.all_gather_object(out, h)
                 return out
-            dp.enable_fused(all_gather_bytes)
+            if not dp.enable_fused(all_gather_bytes):   # collective decision: all ranks or none
+                args.fused = False
+                if rank == 0:
+                    print(f"fused peer-memory optimiser unavailable ({dp.fused_error}); using the NCCL exchange", file=sys.stderr)
     tr = W.Trainer(model, cfg["lr"], dp=dp)
 
     x, t = W.mlp_batch(cfg["rows"], cfg["width"], cfg["width"], seed=1, rank=rank)  # this rank's shard of the global batch

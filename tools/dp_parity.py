@@ -33,7 +33,7 @@ def main():
         model = W.build_mlp(dev, ws, bs, "sigmoid")
         dp = F.DataParallel(dev, world, rank, ids[0], model.parameters(), overlap=overlap)
         if fused:
-            dp.enable_fused(all_gather_bytes)   # parameters move into the peer-mapped arena; one fused kernel per step
+            assert dp.enable_fused(all_gather_bytes), dp.fused_error   # parameters move into the peer-mapped arena; one fused kernel per step
         tr = W.Trainer(model, lr, dp=dp)
         X, T = F.Tensor.from_numpy(dev, x[b:e]), F.Tensor.from_numpy(dev, t[b:e])
         T.requires_grad = False
