@@ -78,7 +78,8 @@ def main():
         X, T = F.Tensor.from_numpy(dev, x), F.Tensor.from_numpy(dev, y)
         T.requires_grad = False
         n0 = dev.launches()
-        tr.capture(X, T, unroll=10, warmup=10)
+        tr.capture(X, T, unroll=10, warmup=0)
+        tr.replay(1)   # first launch: graph upload, allocations backed, clocks back up after the CPU leg
         dev.sync()
         t0 = time.perf_counter()
         loss = tr.replay((steps - 10) // 10)
