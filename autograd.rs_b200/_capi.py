@@ -74,6 +74,8 @@ def lib():
             "agrs_fused_create": [vp, i32, i32, C.POINTER(vp), sz, sz, sz, C.POINTER(vp)],
             "agrs_fused_destroy": [vp],
             "agrs_fused_sgd_step": [vp, f32],
+            "agrs_fused_scatter_f32": [vp, vp, sz, sz],
+            "agrs_gemm_f32_scatter": [vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, vp, vp, sz],
             "agrs_capture_begin": [vp],
             "agrs_capture_end": [vp, C.POINTER(vp)],
             "agrs_graph_launch": [vp, vp, i32],

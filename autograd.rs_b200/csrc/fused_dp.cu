@@ -1,13 +1,16 @@
-// Fused data-parallel optimiser step over NVLink peer memory: ONE kernel per training step replaces
-//     all-reduce(grad)  ->  w -= lr * grad  (optim.rs:25-34)  ->  zero_grad (model.rs:14-21)
-// Every rank keeps its parameters and parameter gradients in an "arena" (one cudaMalloc block, IPC-exported, mapped by
-// every peer at the same offsets).  Rank r owns the r-th slice of the arena:
-//     barrier 1   every rank's gradients are complete
-//     reduce      g = (sum over ranks p of G_p[i]) / world                  P2P loads over NVLink, peers visited from rank+1 on
+// Fused data-parallel optimiser step over NVLink peer memory: reduce-scatter + SGD + all-gather without NCCL, replacing
+//     all-reduce(grad)  ->  w -= lr * grad  (optim.rs:25-34)
+// Every rank keeps its parameters and a gradient exchange region in an "arena" (one cudaMalloc block, IPC-exported, mapped by
+// every peer at the same offsets).  The flat parameter space is cut into `world` slices; rank r OWNS slice r and its gradient
+// region holds one SLOT per source rank: [world][slice].
+//     scatter     during backward every rank pushes its gradient values into slot [its rank] of the owner's region with P2P
+//                 stores over NVLink -- straight from the dW GEMM's epilogue, tile by tile (gemm_tcgen05_2cta.cu), or with
+//                 k_scatter_grad for gradients produced elsewhere (bias sums, conv filters)
+//     barrier 1   every rank's pushes have landed
+//     reduce      g = (slot 0 + slot 1 + ..) / world on the owned slice      LOCAL loads, rank order: deterministic
 //     update      w = W_r[i] - lr * g                                       two roundings, as agrs_sgd_step_f32
-//     broadcast   W_p[i] = w for every rank p                               P2P stores over NVLink
-//     barrier 2   every rank's slice has landed everywhere; nobody still reads my gradients
-// i.e. reduce-scatter + SGD + all-gather with the weights never making a separate pass through HBM.
+//     broadcast   W_p[i] = w for every rank p                               P2P stores over NVLink, peers visited from rank+1 on
+//     barrier 2   every rank's slice has landed everywhere; the slots may be overwritten by the next backward
 // The barriers are flag arrays in the arenas, written with system-scope releases by the peers and polled with system-scope
 // acquires; every wait is bounded (a lost rank traps the kernel instead of hanging the GPU).  One process per GPU: each
 // rank's kernel runs on its own device, so the ranks always run concurrently.
@@ -98,25 +101,20 @@ __global__ void __launch_bounds__(256) k_fused_dp_sgd(const FusedArgs a) {
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < shard4; i += stride) {
     const size_t e = (first4 + i) * 4;
-    // Peers are visited starting at the next rank (rank+1, rank+2, .., rank): at any moment the ranks pull from different
-    // peers, so no GPU's NVLink egress is everybody's target.  The slice's owner fixes the summation order, every element has
-    // exactly one owner and its result is broadcast: deterministic, and the replicas stay bit-identical.
+    // The reduce-scatter already happened: every rank pushed its piece of MY slice into slot [its rank] of my gradient
+    // region (from the dW GEMM's epilogue or k_scatter_grad).  What is left is a LOCAL sum over the slots, in rank order:
+    // deterministic, every element has exactly one owner and its result is broadcast, so the replicas stay bit-identical.
+    const float* slots = a.base[a.rank] + a.g_off + i * 4;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (WORLD) {
       float4 v[WORLD ? WORLD : 1];
 #pragma unroll
-      for (int j = 0; j < (WORLD ? WORLD : 1); ++j) {  // all loads in flight before the first add
-        int p = a.rank + 1 + j;
-        p -= p >= world ? world : 0;
-        v[j] = ld_sys_v4(a.base[p] + a.g_off + e);
-      }
+      for (int p = 0; p < (WORLD ? WORLD : 1); ++p) v[p] = ld_sys_v4(slots + size_t(p) * shard4 * 4);  // all loads in flight before the first add
 #pragma unroll
-      for (int j = 0; j < (WORLD ? WORLD : 1); ++j) { g.x += v[j].x; g.y += v[j].y; g.z += v[j].z; g.w += v[j].w; }
+      for (int p = 0; p < (WORLD ? WORLD : 1); ++p) { g.x += v[p].x; g.y += v[p].y; g.z += v[p].z; g.w += v[p].w; }
     } else {
-      for (int j = 0; j < world; ++j) {
-        int p = a.rank + 1 + j;
-        p -= p >= world ? world : 0;
-        const float4 v = ld_sys_v4(a.base[p] + a.g_off + e);
+      for (int p = 0; p < world; ++p) {
+        const float4 v = ld_sys_v4(slots + size_t(p) * shard4 * 4);
         g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
       }
     }
@@ -137,6 +135,24 @@ __global__ void __launch_bounds__(256) k_fused_dp_sgd(const FusedArgs a) {
   rank_barrier(a, 1);
 }
 
+// The scatter half of the reduce-scatter for a gradient that was NOT produced by the scattering GEMM (bias sums, conv filters,
+// second accumulations): element e of the gradient region belongs to rank e / shard, which keeps one slot per source rank;
+// this rank's values go to slot [rank] of the owner with P2P stores.  `off` and `n` are multiples of 4.
+__global__ void __launch_bounds__(256) k_scatter_grad(const FusedArgs a, const float* __restrict__ src, size_t off, size_t n) {
+  const size_t shard = a.total / size_t(a.world);  // a multiple of 4: a float4 never straddles two owners
+  const size_t stride = size_t(gridDim.x) * blockDim.x, n4 = (n + 3) / 4;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const size_t e = off + 4 * i;
+    const size_t owner = e / shard, idx = e - owner * shard;
+    float* dst = a.base[owner] + a.g_off + size_t(a.rank) * shard + idx;
+    if (4 * i + 3 < n) {
+      st_sys_v4(dst, __ldcs(reinterpret_cast<const float4*>(src) + i));
+    } else {
+      for (size_t j = 4 * i; j < n; ++j) asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst + (j - 4 * i)), "f"(src[j]) : "memory");
+    }
+  }
+}
+
 }  // namespace
 
 struct agrs_fused {
@@ -144,6 +160,15 @@ struct agrs_fused {
   FusedArgs args{};
   size_t grid = 0;  // CTAs per launch: fixed at the first call (the barrier counters assume it)
 };
+
+// what a scattering GEMM epilogue needs to know (gemm_tcgen05_2cta.cu)
+void agrs_fused_scatter_target(const agrs_fused* f, float* const** bases, int* world, int* rank, size_t* g_off, size_t* shard) {
+  *bases = f->args.base;
+  *world = f->args.world;
+  *rank = f->args.rank;
+  *g_off = f->args.g_off;
+  *shard = f->args.total / size_t(f->args.world);
+}
 
 extern "C" {
 
@@ -219,6 +244,19 @@ int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, s
 int agrs_fused_destroy(agrs_fused* f) {
   if (!f) return AGRS_OK;
   delete f;
+  return AGRS_OK;
+}
+
+int agrs_fused_scatter_f32(agrs_fused* f, const float* src, size_t off, size_t n) {
+  if (!f) return AGRS_ERR_INVALID;
+  agrs_ctx* ctx = f->ctx;
+  AGRS_CHECK_CTX(ctx);
+  if (n == 0) return AGRS_OK;
+  AGRS_REQUIRE(ctx, src && agrs_aligned16(src) && off % 4 == 0 && off + n <= f->args.total, AGRS_ERR_INVALID,
+               "agrs_fused_scatter_f32: source must be 16-byte aligned and [off, off+n) a 4-aligned range of the gradient region");
+  size_t blocks = ((n + 3) / 4 + 255) / 256, cap = size_t(ctx->sm_count) * 8;
+  k_scatter_grad<<<unsigned(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(f->args, src, off, n);
+  AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }
 

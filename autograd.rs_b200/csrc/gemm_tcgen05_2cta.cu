@@ -82,10 +82,23 @@ __device__ __forceinline__ float lo_of(float x) {
   return (lo == lo) ? lo : 0.f;                       // inf - inf: keep inf/NaN in the hi term only
 }
 
-template <bool A_MN, bool B_MN>
+// GEMM -> reduce-scatter (data-parallel weight gradients, csrc/fused_dp.cu): with SCATTER the epilogue also pushes every finished
+// 32-column piece of C to the rank that owns it -- element e = off + row*N + col of the flat parameter space belongs to rank
+// e / shard, which keeps one slot per source rank -- with P2P stores over NVLink, tile by tile, while the tensor cores are already
+// on the next tile.
+struct ScatterArgs {
+  float* base[16];  // arena of every rank as mapped here
+  int world, rank;
+  size_t g_off;     // float offset of the gradient region in an arena
+  size_t shard;     // floats per owner (a multiple of 32)
+  size_t off;       // float offset of C inside the flat parameter space (a multiple of 32)
+};
+
+template <bool A_MN, bool B_MN, bool SCATTER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C, int64_t ldc,
-                   const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw) {
+                   const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
+                   const __grid_constant__ ScatterArgs sc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
@@ -288,6 +301,12 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int64_t col0 = nb * BN + c * 32;
           if (row < M && col0 < N) {
             float* dst = Cs + row * lds + col0;
+            float* push = nullptr;  // where the finished piece also goes: this rank's slot at the piece's owner
+            if (SCATTER && c0 + kb_per_chunk >= w.kb1) {
+              const size_t e = sc.off + size_t(row) * size_t(N) + size_t(col0);
+              const size_t owner = e / sc.shard;
+              push = sc.base[owner] + sc.g_off + size_t(sc.rank) * sc.shard + (e - owner * sc.shard);
+            }
             if (vec_s && col0 + 32 <= N) {
               float4 base[8];
               if (ch == 0) {
@@ -306,6 +325,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 o.z = base[j].z + __uint_as_float(v[4 * j + 2]);
                 o.w = base[j].w + __uint_as_float(v[4 * j + 3]);
                 *reinterpret_cast<float4*>(dst + 4 * j) = o;
+                if (SCATTER && push) *reinterpret_cast<float4*>(push + 4 * j) = o;  // P2P store (a local one when I am the owner)
               }
             } else {
 #pragma unroll
@@ -375,15 +395,15 @@ static int choose_splits(int64_t tiles, int64_t pairs, int64_t num_kb, int force
   return best;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool SCATTER>
 static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
-                  int64_t N, int64_t K, int kb_per_chunk) {
-  auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN>;
+                  int64_t N, int64_t K, int kb_per_chunk, const ScatterArgs& sc) {
+  auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN, SCATTER>;
   AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int64_t pairs = ctx->sm_count / 2;
   const int64_t num_kb = (K + BK - 1) / BK;
-  int splits = choose_splits(tiles, pairs, num_kb, ctx->tc_splitk);
+  int splits = SCATTER ? 1 : choose_splits(tiles, pairs, num_kb, ctx->tc_splitk);  // the scattering epilogue writes final values only
   {  // the kernel gives every split ceil(num_kb / splits) k-blocks: drop splits that would be left with none
     const int64_t kps = (num_kb + splits - 1) / splits;
     splits = int((num_kb + kps - 1) / kps);
@@ -396,7 +416,7 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   }
   const int64_t items = tiles * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw);
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc);
   AGRS_LAUNCHED(ctx);
   if (splits > 1) {
     const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
@@ -408,8 +428,8 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
 
 }  // namespace tc2
 
-int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
-                      const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias) {
+static int gemm_tc_2cta_impl(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                             const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, const tc2::ScatterArgs* sc) {
   int rc = tc::resolve_encode(ctx);
   if (rc) return rc;
   const bool A_MN = transA != 0;  // A stored [K, M]: M contiguous
@@ -423,8 +443,43 @@ int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t 
   if (rc) return rc;
   const int64_t num_kb = (K + tc::BK - 1) / tc::BK;
   const int kpc = ctx->tc_kchunk > 0 ? int((ctx->tc_kchunk + tc::BK - 1) / tc::BK) : int(num_kb);
-  if (A_MN && B_MN) return tc2::launch<true, true>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
-  if (A_MN) return tc2::launch<true, false>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
-  if (B_MN) return tc2::launch<false, true>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
-  return tc2::launch<false, false>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc);
+  static const tc2::ScatterArgs none{};
+#define AGRS_PAIR(AM, BMJ)                                                                                          \
+  (sc ? tc2::launch<AM, BMJ, true>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc)                                     \
+      : tc2::launch<AM, BMJ, false>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none))
+  if (A_MN && B_MN) return AGRS_PAIR(true, true);
+  if (A_MN) return AGRS_PAIR(true, false);
+  if (B_MN) return AGRS_PAIR(false, true);
+  return AGRS_PAIR(false, false);
+#undef AGRS_PAIR
+}
+
+int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                      const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias) {
+  return gemm_tc_2cta_impl(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, nullptr);
+}
+
+// fused_dp.cu
+void agrs_fused_scatter_target(const agrs_fused* f, float* const** bases, int* world, int* rank, size_t* g_off, size_t* shard);
+
+extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                                     const float* B, int64_t ldb, float* C, const float* bias, agrs_fused* f, size_t off) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, f, AGRS_ERR_INVALID, "agrs_gemm_f32_scatter: null exchange");
+  tc2::ScatterArgs sc{};
+  float* const* bases = nullptr;
+  agrs_fused_scatter_target(f, &bases, &sc.world, &sc.rank, &sc.g_off, &sc.shard);
+  for (int p = 0; p < sc.world; ++p) sc.base[p] = bases[p];
+  sc.off = off;
+  // the pair kernel's vector epilogue must own whole 32-float pieces that never straddle two owners
+  const bool fused_ok = ctx->gemm_path != AGRS_GEMM_SIMT && ctx->tc_2cta && M > 128 && K > 0 && N % 32 == 0 && off % 32 == 0 && sc.shard % 32 == 0 &&
+                        agrs_aligned16(C) && agrs_gemm_tc_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, N, bias) &&
+                        (M * N) * K >= ctx->tc_min_flops;
+  if (fused_ok) {
+    ctx->last_gemm_path = AGRS_GEMM_TCGEN05;
+    return gemm_tc_2cta_impl(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias, &sc);
+  }
+  int rc = agrs_gemm_f32(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias);
+  if (rc) return rc;
+  return agrs_fused_scatter_f32(f, C, off, size_t(M) * size_t(N));
 }

@@ -9,8 +9,7 @@ StoragePtr contig(const StoragePtr& s) { return s->transposed ? s->contiguous_co
 
 // C = op(a) * op(b) (+ bias row).  `ta`/`tb` ask for the LOGICAL transpose of the operand; a storage that is
 // itself a transposed view flips the flag back.  Nothing is ever copied: majors go to the GEMM as flags.
-Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bias = nullptr,
-            const std::shared_ptr<Buffer>& out_buf = nullptr) {
+Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bias = nullptr, GradCell* scatter_to = nullptr) {
   if (a.ndim() != 2 || b.ndim() != 2) throw Panic("Ndarray only supports 1d/2d matmul!");
   if (a.dev() != b.dev()) throw Panic("Tensors must be on same device");
   const Shape& as = a.shape();
@@ -23,16 +22,24 @@ Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bia
                 AGRS_ERR_SHAPE);
   const bool fa = ta != a.data->transposed, fb = tb != b.data->transposed;  // memory-level flags
   // memory row pitch: A stored [M,K] (fa=0) -> K, stored [K,M] (fa=1) -> M; B stored [K,N] (fb=0) -> N, [N,K] (fb=1) -> K
-  auto out = (out_buf && out_buf->n == M * N) ? std::make_shared<Storage>(out_buf, Shape{M, N}) : std::make_shared<Storage>(a.dev(), Shape{M, N});
-  a.dev()->check(agrs_gemm_f32(a.dev()->ctx(), fa, fb, M, N, K, a.data->rptr(), fa ? M : K, b.data->rptr(), fb ? K : N, out->buf->ptr,
-                               N, bias));
+  auto out = std::make_shared<Storage>(a.dev(), Shape{M, N});
+  if (scatter_to) {
+    // data-parallel weight gradient: GEMM -> reduce-scatter in one kernel, the epilogue pushes each tile to its owner over NVLink
+    a.dev()->check(agrs_gemm_f32_scatter(a.dev()->ctx(), fa, fb, M, N, K, a.data->rptr(), fa ? M : K, b.data->rptr(), fb ? K : N,
+                                         out->buf->ptr, bias, scatter_to->scatter, scatter_to->scatter_off));
+    scatter_to->scattered = true;
+  } else {
+    a.dev()->check(agrs_gemm_f32(a.dev()->ctx(), fa, fb, M, N, K, a.data->rptr(), fa ? M : K, b.data->rptr(), fb ? K : N, out->buf->ptr,
+                                 N, bias));
+  }
   return Tensor(out);
 }
 
-// where a freshly computed parameter gradient should be written: the parameter's arena window when the coming accumulation
-// is a plain hand-over (first touch or lazily zeroed cell), otherwise an ordinary allocation
-std::shared_ptr<Buffer> grad_sink(const Tensor& param) {
-  if (param.grad && param.grad->sink && param.grad->next_accumulate_is_handover()) return param.grad->sink;
+// A freshly computed parameter gradient can be pushed to its owners by the GEMM itself when the coming accumulation is a plain
+// hand-over (first touch or lazily zeroed cell) and the parameter takes part in a fused data-parallel exchange.
+GradCell* scatter_target(const Tensor& param, int64_t n) {
+  GradCell* c = param.grad.get();
+  if (c && c->scatter && c->next_accumulate_is_handover() && param.len() == n && !param.data->transposed) return c;
   return nullptr;
 }
 
@@ -146,7 +153,7 @@ std::vector<Tensor> bwd(const Sigmoid&, const std::vector<Tensor>& xs, const Ten
 std::vector<Tensor> bwd(const Linear&, const std::vector<Tensor>& xs, const Tensor& grad) {
   const Tensor &x = xs.at(0), &w = xs.at(1);
   Tensor dx = gemm(grad, false, w, true);   // g.dot(&w.t_clone())   operators.rs:159
-  Tensor dw = gemm(x, true, grad, false, nullptr, grad_sink(w));   // x.t_clone().dot(g)    operators.rs:160
+  Tensor dw = gemm(x, true, grad, false, nullptr, scatter_target(w, x.shapei(1) * grad.shapei(1)));   // x.t_clone().dot(g)    operators.rs:160
   Tensor db = grad.sum_axis(0);             // 1-D [O]               operators.rs:161
   return {dx, dw, db};
 }

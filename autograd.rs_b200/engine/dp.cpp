@@ -9,14 +9,8 @@ DataParallel::DataParallel(Device* dev, int world, int rank, const void* unique_
 DataParallel::~DataParallel() {
   for (auto& c : cells_) {
     if (c->hook == this) c->hook = nullptr;
-    if (c->sink) {  // gradients that still live in the arena move out with it
-      if (c->g && c->g->buf.get() == c->sink.get()) {
-        auto nb = std::make_shared<Buffer>(dev_, c->g->buf->n);
-        agrs_copy(dev_->ctx(), nb->ptr, c->g->buf->ptr, size_t(nb->n) * sizeof(float));
-        c->g->buf = nb;
-      }
-      c->sink = nullptr;
-    }
+    c->scatter = nullptr;
+    c->scattered = false;
   }
   if (fused_) agrs_fused_destroy(fused_);
   for (size_t p = 0; p < peer_maps_.size(); ++p)
@@ -55,7 +49,7 @@ void DataParallel::fused_prepare(void* handle64) {
     float* dst = arena_ + w_off_ + sl.off;
     dev_->check(agrs_copy(dev_->ctx(), dst, t.data->rptr(), size_t(sl.n) * sizeof(float)));
     t.data->buf = std::make_shared<Buffer>(dev_, dst, sl.n);  // the shared storage cell now points into the arena
-    t.grad->sink = std::make_shared<Buffer>(dev_, arena_ + g_off_ + sl.off, sl.n);  // where operators may write the gradient directly
+    t.grad->scatter_off = size_t(sl.off);
   }
   dev_->sync();
   dev_->check(agrs_peer_export(dev_->ctx(), arena_, handle64));
@@ -73,6 +67,7 @@ void DataParallel::fused_connect(const void* handles) {
     dev_->check(agrs_peer_open(dev_->ctx(), static_cast<const char*>(handles) + size_t(p) * AGRS_PEER_HANDLE_BYTES, &peer_maps_[size_t(p)]));
   }
   dev_->check(agrs_fused_create(dev_->ctx(), world_, rank_, peer_maps_.data(), w_off_, g_off_, region_, &fused_));
+  for (auto& c : cells_) c->scatter = fused_;  // from now on the dW GEMMs push their tiles to the owners themselves
 }
 
 void DataParallel::fused_sgd_step(float lr) {
@@ -121,8 +116,10 @@ void DataParallel::on_accumulated(GradCell& cell) {
     const Slot& sl = slots_[&cell];
     const Storage& g = *cell.get();
     if (g.transposed || g.len() != sl.n) throw Panic("DataParallel(fused): gradient does not match its parameter", AGRS_ERR_SHAPE);
-    if (g.rptr() != arena_ + g_off_ + sl.off)  // not produced in place (bias sums, second accumulations): copy it in
-      dev_->check(agrs_copy(dev_->ctx(), arena_ + g_off_ + sl.off, g.rptr(), size_t(sl.n) * sizeof(float)));
+    if (cell.scattered)  // the GEMM that produced it already pushed it, tile by tile
+      cell.scattered = false;
+    else                 // bias sums, conv filters, second accumulations: push it now
+      dev_->check(agrs_fused_scatter_f32(fused_, g.rptr(), size_t(sl.off), size_t(sl.n)));
     return;
   }
   if (!overlap_ || world_ == 1) return;

@@ -336,7 +336,7 @@ void Tensor::zero_grad() const {
   // only runs if somebody reads the gradient before the next accumulation (GradCell::get); the usual next event is
   // backward's `zeros += dW`, which then degenerates to taking dW's buffer (0 + x == x) -- no memset, no add pass.
   auto& g = grad->g;
-  if (g && g->len() == data->len() && (g->buf.use_count() == 1 || g->buf == grad->sink)) {
+  if (g && g->len() == data->len() && g->buf.use_count() == 1) {
     g->shape = data->shape;
     g->transposed = false;
   } else {
@@ -360,6 +360,7 @@ void Tensor::accumulate_grad_from_grad_tensor(const Tensor& gt) const {
     // Some(a) => a += b with ndarray broadcasting of b onto a (todo!() at HEAD: defect D2)
     grad->get();
     storage_binary_into(AGRS_ADD, *g, *g, *src);
+    grad->scattered = false;  // what a scattering GEMM pushed to the owners was only the new term: the sum must be pushed again
   }
 }
 

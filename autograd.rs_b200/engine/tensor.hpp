@@ -97,9 +97,12 @@ struct GradCell {  // Rc<RefCell<Option<StorageType<f32>>>>, tensor.rs:32
   StoragePtr g;
   bool zero_pending = false;   // g is logically all zeros but its buffer has not been cleared yet (lazy zero_grad)
   GradHook* hook = nullptr;    // not owned
-  // Preferred home of the NEXT gradient (a window of the data-parallel arena): an operator that produces this gradient as a
-  // fresh tensor may write it there directly, so the fused optimiser step finds it in place and no copy is needed.
-  std::shared_ptr<Buffer> sink;
+  // Data-parallel exchange in fused mode (engine/dp.cpp, csrc/fused_dp.cu): where this parameter's gradient belongs in the flat
+  // parameter space.  An operator that produces the gradient as a fresh tensor may use a GEMM whose epilogue pushes the result
+  // to the owning ranks as it is produced (agrs_gemm_f32_scatter) and then sets `scattered`; otherwise the hook pushes it.
+  agrs_fused* scatter = nullptr;
+  size_t scatter_off = 0;
+  bool scattered = false;  // the gradient taken over by the last accumulation is already at its owners
   bool next_accumulate_is_handover() const { return !g || zero_pending; }
   const StoragePtr& get();     // the gradient storage with any pending zero fill applied: what every reader must use
 };

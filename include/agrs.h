@@ -191,8 +191,10 @@ AGRS_API int agrs_comm_join(agrs_comm* comm);
  * Each rank keeps parameters and parameter gradients in an ARENA: one agrs_peer_alloc block laid out identically on every
  * rank ([flag words | ... weight region at w_off ... | ... gradient region at g_off ...], offsets in floats).  The arenas are
  * exported (agrs_peer_export -> 64-byte handle, exchanged by the launcher) and mapped by every peer (agrs_peer_open).
- * agrs_fused_sgd_step then runs ONE kernel per training step: cross-rank barrier, reduce-scatter of the gradients with P2P
- * loads, w -= lr * mean(g) on the owned slice, all-gather of the updated weights with P2P stores, cross-rank barrier.
+ * The gradient region of an arena holds one slot per source rank for the slice of the parameter space this rank owns.  During
+ * backward every rank pushes its gradients into its slot at the owners (agrs_gemm_f32_scatter from the dW GEMM's epilogue,
+ * agrs_fused_scatter_f32 otherwise); agrs_fused_sgd_step then runs ONE kernel per training step: cross-rank barrier, local
+ * sum of the slots, w -= lr * mean(g) on the owned slice, all-gather of the updated weights with P2P stores, cross-rank barrier.
  * It replaces all-reduce + agrs_sgd_step_f32 (optim.rs:25-34).  Every rank must call it the same number of times. */
 #define AGRS_PEER_HANDLE_BYTES 64
 typedef struct agrs_fused agrs_fused;
@@ -206,6 +208,14 @@ AGRS_API size_t agrs_fused_flag_floats(void);                                   
 AGRS_API int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, size_t w_off, size_t g_off, size_t total,
                                agrs_fused** out);
 AGRS_API int agrs_fused_destroy(agrs_fused* f);
+/* the scatter half of the reduce-scatter: push `n` gradient values that belong at float offset `off` of the (flat) parameter
+ * space into this rank's slot at their owners.  src is device memory, 16-byte aligned; off a multiple of 4. */
+AGRS_API int agrs_fused_scatter_f32(agrs_fused* f, const float* src, size_t off, size_t n);
+/* agrs_gemm_f32 whose result C ([M,N] contiguous, ldc == N) is ALSO pushed to the owners' slots as the tiles are produced: the
+ * GEMM -> reduce-scatter of the weight gradient in one kernel (P2P stores from the epilogue of the tcgen05 pair kernel).  Shapes
+ * that kernel does not take run agrs_gemm_f32 followed by agrs_fused_scatter_f32: same result. */
+AGRS_API int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                                   const float* B, int64_t ldb, float* C, const float* bias, agrs_fused* f, size_t off);
 AGRS_API int agrs_fused_sgd_step(agrs_fused* f, float lr);
 
 AGRS_API const char* agrs_version(void);

@@ -491,12 +491,14 @@ def test_data_parallel_two_gpus_tracks_oracle():
     assert r.returncode == 0 and "DP PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_fused_optimizer_world1_matches_plain_sgd(dev):
+@pytest.mark.parametrize("width,rows", [(192, 320), (256, 512)])
+def test_fused_optimizer_world1_matches_plain_sgd(dev, width, rows):
     """The fused peer-memory step with a single rank: parameters move into the arena (address changes, values and every
-    clone follow), one kernel per step does reduce + SGD + broadcast on the whole arena, and the losses are those of the plain
-    path bit for bit (mean over one rank is the identity; the update keeps the two roundings of optim.rs:31-33)."""
-    ws, bs = W.mlp_init(3, 192, seed=71)
-    x, t = W.mlp_batch(320, 192, 192, seed=72)
+    clone follow), gradients reach the exchange slots (192 wide: scatter kernel after the GEMM; 256 wide: pushed by the
+    epilogue of the tcgen05 pair GEMM itself), one kernel per step does the slot sum + SGD + broadcast, and the losses are those
+    of the plain path bit for bit (mean over one rank is the identity; the update keeps the two roundings of optim.rs:31-33)."""
+    ws, bs = W.mlp_init(3, width, seed=71)
+    x, t = W.mlp_batch(rows, width, width, seed=72)
     want, params_plain, _ = run_device_mlp(dev, x, t, ws, bs, "sigmoid", 1e-4, 4)
     model = W.build_mlp(dev, ws, bs, "sigmoid")
     params = model.parameters()
@@ -513,13 +515,17 @@ def test_fused_optimizer_world1_matches_plain_sgd(dev):
     Tt.requires_grad = False
     n0 = dev.launches()
     got = [tr.step(X, Tt).item() for _ in range(4)]
-    assert got == want
+    # 192 wide: the same kernels in the same order as the plain path -> the same bits.  256 wide: the scattering GEMM never
+    # splits K while the plain dW GEMM may (a different, equally valid summation order) -> equal to f32 rounding.
+    same = (lambda a, b: np.array_equal(a, b)) if width == 192 else (lambda a, b: np.allclose(a, b, rtol=2e-5, atol=1e-7))
+    assert same(np.array(got), np.array(want))
     for p, q in zip(model.parameters(), params_plain):
-        assert np.array_equal(p.data(), q)
+        assert same(p.data(), q)
     assert [p.data_ptr() for p in model.parameters()] == after  # the parameters stay in the arena
+    final = [p.data() for p in model.parameters()]
     dp.close()
     # after close the parameters live in ordinary storage again, values intact
-    for p, q in zip(model.parameters(), params_plain):
+    for p, q in zip(model.parameters(), final):
         assert np.array_equal(p.data(), q)
 
 
