@@ -475,7 +475,11 @@ extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int6
   const bool fused_ok = ctx->gemm_path != AGRS_GEMM_SIMT && ctx->tc_2cta && M > 128 && K > 0 && N % 32 == 0 && off % 32 == 0 && sc.shard % 32 == 0 &&
                         agrs_aligned16(C) && agrs_gemm_tc_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, N, bias) &&
                         (M * N) * K >= ctx->tc_min_flops;
-  if (fused_ok) {
+  // When splitting K fills the last wave of CTA pairs (dW of the 4096-wide layers: +7 %), the final values only exist after the
+  // partials are added: that shape keeps the split-K GEMM and pushes the result with the scatter kernel instead.
+  const int64_t tiles = ((M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((N + tc2::BN - 1) / tc2::BN);
+  const bool wants_split = tc2::choose_splits(tiles, ctx->sm_count / 2, (K + tc::BK - 1) / tc::BK, ctx->tc_splitk) > 1;
+  if (fused_ok && !wants_split) {
     ctx->last_gemm_path = AGRS_GEMM_TCGEN05;
     return gemm_tc_2cta_impl(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias, &sc);
   }
