@@ -1,8 +1,9 @@
 // Fused data-parallel optimiser step over NVLink peer memory: reduce-scatter + SGD + all-gather without NCCL, replacing
 //     all-reduce(grad)  ->  w -= lr * grad  (optim.rs:25-34)
 // Every rank keeps its parameters and a gradient exchange region in an "arena" (one cudaMalloc block, IPC-exported, mapped by
-// every peer at the same offsets).  The flat parameter space is cut into `world` slices; rank r OWNS slice r and its gradient
-// region holds one SLOT per source rank: [world][slice].
+// every peer at the same offsets).  The flat parameter space is dealt out in granules of 32 floats: granule g belongs to rank
+// g % world (interleaved, so whatever part of it a kernel is working on, its traffic spreads over all ranks' NVLink ports);
+// rank r OWNS the slice made of its granules and its gradient region holds one SLOT per source rank: [world][slice].
 //     scatter     during backward every rank pushes its gradient values into slot [its rank] of the owner's region with P2P
 //                 stores over NVLink -- straight from the dW GEMM's epilogue, tile by tile (gemm_tcgen05_2cta.cu), or with
 //                 k_scatter_grad for gradients produced elsewhere (bias sums, conv filters)
@@ -96,11 +97,12 @@ __global__ void __launch_bounds__(256) k_fused_dp_sgd(const FusedArgs a) {
   const int world = WORLD ? WORLD : a.world;
   rank_barrier(a, 0);
   const size_t shard4 = a.total / 4 / world;  // float4 per rank
-  const size_t first4 = shard4 * a.rank;
   const float inv = 1.0f / float(world);
   const size_t stride = size_t(gridDim.x) * blockDim.x;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < shard4; i += stride) {
-    const size_t e = (first4 + i) * 4;
+    // my slice is every world-th granule of 32 floats: local float index 4i lies in my granule (4i >> 5), which is granule
+    // (4i >> 5) * world + rank of the flat parameter space
+    const size_t e = ((((4 * i) >> 5) * size_t(world) + size_t(a.rank)) << 5) + ((4 * i) & 31);
     // The reduce-scatter already happened: every rank pushed its piece of MY slice into slot [its rank] of my gradient
     // region (from the dW GEMM's epilogue or k_scatter_grad).  What is left is a LOCAL sum over the slots, in rank order:
     // deterministic, every element has exactly one owner and its result is broadcast, so the replicas stay bit-identical.
@@ -139,11 +141,11 @@ __global__ void __launch_bounds__(256) k_fused_dp_sgd(const FusedArgs a) {
 // second accumulations): element e of the gradient region belongs to rank e / shard, which keeps one slot per source rank;
 // this rank's values go to slot [rank] of the owner with P2P stores.  `off` and `n` are multiples of 4.
 __global__ void __launch_bounds__(256) k_scatter_grad(const FusedArgs a, const float* __restrict__ src, size_t off, size_t n) {
-  const size_t shard = a.total / size_t(a.world);  // a multiple of 4: a float4 never straddles two owners
+  const size_t shard = a.total / size_t(a.world);
   const size_t stride = size_t(gridDim.x) * blockDim.x, n4 = (n + 3) / 4;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const size_t e = off + 4 * i;
-    const size_t owner = e / shard, idx = e - owner * shard;
+    const size_t e = off + 4 * i;  // a multiple of 4: a float4 never straddles two granules of 32
+    const size_t g = e >> 5, owner = g % size_t(a.world), idx = ((g / size_t(a.world)) << 5) + (e & 31);
     float* dst = a.base[owner] + a.g_off + size_t(a.rank) * shard + idx;
     if (4 * i + 3 < n) {
       st_sys_v4(dst, __ldcs(reinterpret_cast<const float4*>(src) + i));
@@ -223,8 +225,8 @@ int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, s
   AGRS_CHECK_CTX(ctx);
   AGRS_REQUIRE(ctx, out && arenas && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, AGRS_ERR_INVALID,
                "agrs_fused_create: bad arguments (world <= %d)", kMaxWorld);
-  AGRS_REQUIRE(ctx, total % (4 * size_t(world)) == 0 && w_off % 4 == 0 && g_off % 4 == 0 && w_off >= kFlagFloats && g_off >= kFlagFloats,
-               AGRS_ERR_INVALID, "agrs_fused_create: regions must start after the %d flag words and be multiples of 4*world floats", kFlagFloats);
+  AGRS_REQUIRE(ctx, total % (32 * size_t(world)) == 0 && w_off % 32 == 0 && g_off % 32 == 0 && w_off >= kFlagFloats && g_off >= kFlagFloats,
+               AGRS_ERR_INVALID, "agrs_fused_create: regions must start after the %d flag words, on 32-float boundaries, and hold a multiple of 32*world floats", kFlagFloats);
   agrs_fused* f = new agrs_fused();
   f->ctx = ctx;
   for (int p = 0; p < world; ++p) {

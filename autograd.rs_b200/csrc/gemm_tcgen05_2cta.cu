@@ -303,9 +303,12 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             float* dst = Cs + row * lds + col0;
             float* push = nullptr;  // where the finished piece also goes: this rank's slot at the piece's owner
             if (SCATTER && c0 + kb_per_chunk >= w.kb1) {
-              const size_t e = sc.off + size_t(row) * size_t(N) + size_t(col0);
-              const size_t owner = e / sc.shard;
-              push = sc.base[owner] + sc.g_off + size_t(sc.rank) * sc.shard + (e - owner * sc.shard);
+              // ownership is interleaved in granules of 32 floats: granule g of the flat parameter space belongs to rank g % world
+              // and is the (g / world)-th granule of that rank's slice -- the eight pieces a thread pushes per tile row go to
+              // eight different ranks, so no rank's NVLink ingress is everybody's target
+              const size_t g = (sc.off + size_t(row) * size_t(N) + size_t(col0)) >> 5;
+              const size_t owner = g % size_t(sc.world);
+              push = sc.base[owner] + sc.g_off + size_t(sc.rank) * sc.shard + ((g / size_t(sc.world)) << 5);
             }
             if (vec_s && col0 + 32 <= N) {
               float4 base[8];
