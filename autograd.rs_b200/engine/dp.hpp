@@ -28,13 +28,14 @@ class DataParallel : public GradHook {
 
   void on_accumulated(GradCell& cell) override;
 
-  // ---- fused optimiser step over NVLink peer memory (csrc/fused_dp.cu): replaces sync_grads() + SGD::step ----
+  // ---- fused exchange + optimiser step over NVLink peer memory (csrc/fused_dp.cu): replaces sync_grads() + SGD::step ----
   // fused_prepare  lays the registered parameters out in an arena (agrs_peer_alloc), moves their values there and re-points
   //                the parameter storages at it (every clone of the parameter sees the move), exports the arena (64 bytes);
   // fused_connect  maps the arenas of all ranks (handles gathered by the launcher, world x 64 bytes, rank order);
-  // fused_sgd_step one kernel: barrier, reduce-scatter of the gradients (P2P loads), w -= lr * mean(g) on the owned slice,
-  //                all-gather of the new weights (P2P stores), barrier.  Gradients reach the arena as backward produces them
-  //                (on_accumulated copies them in).  p.grad() keeps this rank's LOCAL gradient: the mean is never materialised.
+  // during backward every parameter gradient is pushed into this rank's slot at the ranks that own it: by the epilogue of the
+  //                dW GEMM itself (Linear::backward asks for agrs_gemm_f32_scatter) or by on_accumulated (scatter kernel);
+  // fused_sgd_step one kernel: barrier, local sum of the slots, w -= lr * mean(g) on the owned slice, all-gather of the new
+  //                weights (P2P stores), barrier.  p.grad() keeps this rank's LOCAL gradient: the mean is never materialised.
   void fused_prepare(void* handle64);
   void fused_connect(const void* handles);
   void fused_sgd_step(float lr);
