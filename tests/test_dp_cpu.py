@@ -86,3 +86,69 @@ def test_two_rank_data_parallel_tracks_single_device(tmp_path):
     for i, p in enumerate([q for l in layers for q in l.parameters()]):
         assert np.array_equal(r0[f"p{i}"], r1[f"p{i}"])            # replicas stay bit-identical
         assert O.rel_err(r0[f"p{i}"], p.data) < 1e-5               # and track the single-device run
+
+
+# ---- the fused exchange's ownership map (csrc/fused_dp.cu, gemm_tcgen05_2cta.cu), restated in NumPy -----------------------
+GRANULE = 32  # floats
+
+
+def _owner_and_index(e, world):
+    """flat parameter offset e -> (owning rank, float index inside the owner's slice): k_scatter_grad / the GEMM epilogue"""
+    g = e // GRANULE
+    return g % world, (g // world) * GRANULE + e % GRANULE
+
+
+def _flat_offset(i, world, rank):
+    """float index i of rank's slice -> flat parameter offset: k_fused_dp_sgd"""
+    return ((i // GRANULE) * world + rank) * GRANULE + i % GRANULE
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_fused_exchange_ownership_is_a_bijection(world):
+    total = GRANULE * world * 7
+    shard = total // world
+    e = np.arange(total)
+    owner, idx = _owner_and_index(e, world)
+    assert idx.max() == shard - 1 and np.bincount(owner).tolist() == [shard] * world
+    for r in range(world):
+        back = _flat_offset(np.arange(shard), world, r)
+        assert np.array_equal(np.sort(e[owner == r]), np.sort(back))             # the optimiser visits exactly what it owns
+        assert np.array_equal(_owner_and_index(back, world)[1], np.arange(shard))  # and finds slot index i for local index i
+    # a 32-float piece pushed by one epilogue thread never straddles two owners; consecutive pieces go to consecutive ranks
+    first = np.arange(0, total, GRANULE)
+    assert np.array_equal(owner[first], owner[first + GRANULE - 1]) and np.array_equal(owner[first], (first // GRANULE) % world)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_fused_exchange_emulated_equals_mean_gradient_sgd(world):
+    """scatter into per-source slots -> slot sum in rank order / world -> SGD on the owned slice -> broadcast, in NumPy with
+    the kernels' index maps: every rank ends with w - lr * mean_r(g_r), bit-identical across ranks."""
+    rng = np.random.default_rng(world)
+    total, lr = GRANULE * world * 5, np.float32(0.01)
+    shard = total // world
+    w0 = rng.standard_normal(total).astype(np.float32)
+    grads = [rng.standard_normal(total).astype(np.float32) for _ in range(world)]
+    W = [w0.copy() for _ in range(world)]
+    slots = [np.zeros((world, shard), np.float32) for _ in range(world)]   # slots[owner][source]
+    e = np.arange(total)
+    owner, idx = _owner_and_index(e, world)
+    for src in range(world):                                               # k_scatter_grad / scattering epilogue on rank src
+        for o in range(world):
+            m = owner == o
+            slots[o][src, idx[m]] = grads[src][m]
+    for r in range(world):                                                 # k_fused_dp_sgd on rank r
+        i = np.arange(shard)
+        g = np.zeros(shard, np.float32)
+        for p in range(world):
+            g = g + slots[r][p]
+        g = g * np.float32(1.0 / world)
+        flat = _flat_offset(i, world, r)
+        new = W[r][flat] - g * lr
+        for p in range(world):
+            W[p][flat] = new
+    acc = np.zeros(total, np.float32)
+    for p in range(world):
+        acc = acc + grads[p]
+    want = w0 - (acc * np.float32(1.0 / world)) * lr
+    for r in range(world):
+        assert np.array_equal(W[r], W[0]) and np.array_equal(W[r], want)
