@@ -226,7 +226,7 @@ def workload_config(args, cfg, world):
                         f"{cfg['rows']} rows per GPU ({ {'mlp4096': 'BASELINE.json configs[1]', 'mlp8192': 'BASELINE.json configs[4], per-GPU shard'}.get(args.config, 'test-size') })",
             "rows_per_gpu": cfg["rows"], "global_batch": cfg["rows"] * world, "width": cfg["width"], "layers": cfg["layers"],
             "activation": cfg["act"], "lr": cfg["lr"], "parallelism": f"dp{world}",
-            "gradient_exchange": ("none" if world == 1 else ("fused peer-memory kernel (reduce-scatter + SGD + all-gather)" if getattr(args, "fused", False)
+            "gradient_exchange": ("none" if world == 1 else ("fused over NVLink peer memory: reduce-scatter pushed from the dW GEMM epilogue / scatter kernel, then one slot-sum + SGD + all-gather kernel" if getattr(args, "fused", False)
                                                               else "NCCL all-reduce(avg) per parameter" + ("" if getattr(args, "no_overlap", False) else ", overlapped with backward"))),
             "l2": "working set (activations + weights, > 2 GB) is larger than the 126 MB L2; no flush needed"}
 

@@ -378,3 +378,40 @@ def test_gemm_bad_args(ctx):
         assert e.value.code == 4
     finally:
         ctx.call("agrs_set_gemm_path", K.GEMM_AUTO)
+
+
+# ------------------------------------------------------------------ fused exchange primitives on one rank (world = 1)
+def test_fused_scatter_and_step_single_rank(ctx):
+    """agrs_peer_alloc / agrs_fused_create / agrs_fused_scatter_f32 / agrs_fused_sgd_step with world = 1: a ragged gradient
+    (n % 4 != 0) pushed at a non-zero offset lands in slot 0 at the same offsets (one rank owns every granule), untouched
+    elsewhere, and the step applies w -= lr * g exactly (two roundings) on the whole region."""
+    import ctypes as C
+    L = ctx.L
+    flag = int(L.agrs_fused_flag_floats())
+    total = 32 * 9
+    w_off, g_off = flag, flag + total
+    arena = C.c_void_p()
+    ctx.call("agrs_peer_alloc", (g_off + total) * 4, C.byref(arena))
+    arenas = (C.c_void_p * 1)(arena.value)
+    f = C.c_void_p()
+    ctx.call("agrs_fused_create", 1, 0, arenas, w_off, g_off, total, C.byref(f))
+    rng = np.random.default_rng(5)
+    w = rng.standard_normal(total).astype(np.float32)
+    g = rng.standard_normal(37).astype(np.float32)
+    ctx.call("agrs_upload", arena.value + 4 * w_off, w.ctypes.data, w.nbytes)
+    dg = ctx.to_device(g)
+    assert L.agrs_fused_scatter_f32(f, dg.ptr, 64, 37) == 0
+    slot = np.empty(total, np.float32)
+    ctx.call("agrs_download", slot.ctypes.data, arena.value + 4 * g_off, slot.nbytes)
+    want_slot = np.zeros(total, np.float32)
+    want_slot[64:64 + 37] = g
+    assert np.array_equal(slot, want_slot)
+    assert L.agrs_fused_sgd_step(f, C.c_float(0.25)) == 0
+    assert L.agrs_fused_sgd_step(f, C.c_float(0.0)) == 0   # a second generation of the barriers; lr = 0 leaves w alone
+    got = np.empty(total, np.float32)
+    ctx.call("agrs_download", got.ctypes.data, arena.value + 4 * w_off, got.nbytes)
+    assert np.array_equal(got, w - want_slot * np.float32(0.25))
+    with pytest.raises(K.AgrsError):
+        ctx.check(L.agrs_fused_scatter_f32(f, dg.ptr, 2, 37))  # offsets must be multiples of 4
+    L.agrs_fused_destroy(f)
+    ctx.call("agrs_peer_free", arena)
