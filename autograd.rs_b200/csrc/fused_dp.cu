@@ -23,6 +23,9 @@ namespace {
 
 constexpr int kMaxWorld = 16;
 constexpr int kFlagFloats = 256;  // first 1 KB of every arena: barrier flags (unsigned), then the data regions
+// Bound of every barrier spin: each poll is a system- or device-scope load (~0.5-1 us), so a rank that never shows up traps
+// the kernel after roughly half a minute instead of hanging the GPU; honest skew between ranks is milliseconds.
+constexpr unsigned kMaxSpins = 1u << 25;
 
 struct FusedArgs {
   float* base[kMaxWorld];  // arena of every rank, as mapped in THIS process (base[rank] is the local one)
@@ -69,7 +72,7 @@ __device__ void rank_barrier(const FusedArgs& a, int which) {
     if (threadIdx.x == 0) {  // wait for every CTA of this rank, then tell the peers
       const unsigned want = gridDim.x * a.epoch;  // the counter is never reset: generation g ends at g * gridDim.x
       for (unsigned spins = 0; ld_acquire_gpu(mine + 66 + which) < want; ++spins)
-        if (spins > (1u << 28)) { printf("agrs fused step: local barrier timeout (rank %d)\n", a.rank); __trap(); }
+        if (spins > kMaxSpins) { printf("agrs fused step: local barrier timeout (rank %d)\n", a.rank); __trap(); }
       __threadfence_system();
     }
     __syncthreads();
@@ -77,7 +80,7 @@ __device__ void rank_barrier(const FusedArgs& a, int which) {
       const int p = threadIdx.x;
       st_release_sys(reinterpret_cast<unsigned*>(a.base[p]) + which * 32 + a.rank, a.epoch);
       for (unsigned spins = 0; ld_acquire_sys(mine + which * 32 + p) < a.epoch; ++spins)
-        if (spins > (1u << 28)) { printf("agrs fused step: rank %d never saw rank %d at barrier %d\n", a.rank, p, which); __trap(); }
+        if (spins > kMaxSpins) { printf("agrs fused step: rank %d never saw rank %d at barrier %d\n", a.rank, p, which); __trap(); }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -86,7 +89,7 @@ __device__ void rank_barrier(const FusedArgs& a, int which) {
     }
   } else if (threadIdx.x == 0) {
     for (unsigned spins = 0; ld_acquire_gpu(mine + 64 + which) < a.epoch; ++spins)
-      if (spins > (1u << 28)) { printf("agrs fused step: go-flag timeout (rank %d)\n", a.rank); __trap(); }
+      if (spins > kMaxSpins) { printf("agrs fused step: go-flag timeout (rank %d)\n", a.rank); __trap(); }
     __threadfence_system();
   }
   __syncthreads();
