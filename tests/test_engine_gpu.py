@@ -299,6 +299,63 @@ def test_mse_and_mean_ops(dev):
     assert O.rel_err(gm[0].data(), O.mean_bwd(p, np.ones(1, np.float32))) < 1e-6
 
 
+@pytest.mark.parametrize("B,C,H,Wd,co,k,s,p", [(1, 3, 9, 8, 4, 3, 1, 0),   # C_in = 3: the literal shared-filter / [KK, C] grouping quirks (D5)
+                                              (1, 2, 7, 7, 5, 2, 2, 1),   # stride 2, pad 1: dx keeps the padded size (TODO at operators.rs:427)
+                                              (5, 3, 10, 9, 6, 3, 1, 1),  # B > 1: the per-sample generalisation of col2im (D1)
+                                              (64, 1, 28, 28, 6, 5, 1, 0)])  # the LeNet geometry
+def test_conv2d_values_match_literal_oracle(dev, B, C, H, Wd, co, k, s, p):
+    """Conv2D forward AND backward values against the oracle's literal restatement of operators.rs:350-449, quirks included"""
+    rng = np.random.default_rng(B + C + H + k + p)
+    im = rng.standard_normal((B, C, H, Wd)).astype(np.float32)
+    filt = rng.standard_normal((k, k, co)).astype(np.float32)
+    bias = rng.standard_normal((co,)).astype(np.float32)
+    conv = F.Conv2D(C, co, k, s, p)
+    X, Fl, Bi = T(dev, im), T(dev, filt), T(dev, bias)
+    out = conv.forward([X.clone(), Fl.clone(), Bi.clone()])
+    want_out, col2d = O.conv2d_fwd(im, filt, bias, C, k, s, p)
+    assert out.shape() == list(want_out.shape)
+    assert O.rel_err(out.data(), want_out) < 1e-5
+    assert out.graph_info() == ("Conv2D", 4, 0)  # the cached col is the 4th variable (operators.rs:386-388)
+    g = rng.standard_normal(want_out.shape).astype(np.float32)
+    col_t = T(dev, col2d)
+    dx, dw, db = conv.backward([X, Fl, Bi, col_t], T(dev, g))
+    wdx, wdw, wdb = O.conv2d_bwd(im, filt, col2d, g, C, k, s, p, literal=False)
+    assert dx.shape() == list(wdx.shape) and dw.shape() == [k, k, co] and db.shape() == [co]
+    assert O.rel_err(dx.data(), wdx) < 1e-5 and O.rel_err(dw.data(), wdw) < 1e-5 and O.rel_err(db.data(), wdb) < 1e-5
+    if B == 1:  # at B = 1 the generalisation IS the literal code
+        ldx, ldw, ldb = O.conv2d_bwd(im, filt, col2d, g, C, k, s, p, literal=True)
+        assert np.array_equal(ldx, wdx) and np.array_equal(ldw, wdw)
+
+
+def test_identity_mean_graph_and_broadcast_arithmetic(dev):
+    """Identity shares storage and passes the gradient (operators.rs:274-286); Mean's backward is ones/size (:267-271);
+    ndarray broadcasting in the arithmetic: [B,O] op [O], [B,O] op [1,O], [B,O] op [B,1], [B,O] op [1,1]"""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((6, 5)).astype(np.float32)
+    X = T(dev, x)
+    y = F.Identity().forward([X.clone()])
+    assert y.data_ptr() == X.data_ptr() and y.graph_info()[0] == "Identity"
+    m = F.Mean().forward([y])
+    m.backward()
+    # Identity's output is a CLONE of its input: same data cell AND same grad cell (operators.rs:279).  The walk accumulates
+    # 1/size into it once as Mean's input and once more as Identity's input -- the literal reference gives 2/size, and so
+    # does the oracle.
+    OX = O.OTensor(x)
+    O.OpMean().forward([O.OpIdentity().forward([OX.clone()])]).backward()
+    assert np.allclose(OX.grad, 2.0 / 30) and np.allclose(X.grad().data(), OX.grad, rtol=1e-7)
+    a = T(dev, x)
+    for other in (rng.standard_normal(5), rng.standard_normal((1, 5)), rng.standard_normal((6, 1)), rng.standard_normal((1, 1))):
+        o = other.astype(np.float32)
+        assert np.array_equal((a + T(dev, o)).data(), x + o)
+        assert np.array_equal((a - T(dev, o)).data(), x - o)
+        assert np.array_equal((a * T(dev, o)).data(), x * o)
+    with pytest.raises(F.Panic, match="broadcast"):
+        a + T(dev, np.zeros((4,), np.float32))  # ndarray: could not broadcast [4] onto [6, 5]
+    b = T(dev, x)
+    b.add_(T(dev, np.ones(5, np.float32)))      # in place with a broadcast right-hand side keeps the address
+    assert np.array_equal(b.data(), x + 1)
+
+
 # ====================================================================== whole training loops vs the oracle
 def run_device_mlp(dev, x, t, ws, bs, act, lr, steps):
     model = W.build_mlp(dev, ws, bs, act)
