@@ -203,6 +203,30 @@ def cpu_reference_run(cfg, steps, warmup, target_s_per_step):
     return rows / dt, rows, dt, cpu_threads(), gfs
 
 
+def cpu_one_core_run(cfg, target_s):
+    """The same iteration through the single-threaded C restatement (oracle/oracle_c.c: matrixmultiply-style packed sgemm, the
+    reference's own pass structure) -- the reference is single-threaded, so this is the closer stand-in for `cargo run --release`.
+    Returns (samples/s, rows, seconds, calibration GF/s)."""
+    from oracle import oracle_c as C
+    from autograd_rs_b200 import workloads as W  # data generation only
+    n = 1024
+    a = np.random.default_rng(0).standard_normal((n, n)).astype(np.float32)
+    C.dot(a, a)
+    t0 = time.perf_counter()
+    C.dot(a, a)
+    gfs = 2.0 * n ** 3 / (time.perf_counter() - t0) / 1e9
+    rows = int(target_s * gfs * 1e9 / flops_per_sample(cfg))
+    rows = max(64, min(cfg["rows"], rows // 64 * 64))
+    ws, bs = W.mlp_init(cfg["layers"], cfg["width"], seed=0)
+    ws, bs = [np.ascontiguousarray(w, np.float32) for w in ws], [np.ascontiguousarray(b, np.float32) for b in bs]
+    x, t = W.mlp_batch(rows, cfg["width"], cfg["width"], seed=1)
+    t0 = time.perf_counter()
+    loss = C.mlp_step(ws, bs, x, t, cfg["act"], cfg["lr"])
+    dt = time.perf_counter() - t0
+    assert np.isfinite(loss)
+    return rows / dt, rows, dt, gfs
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -409,6 +433,10 @@ def run_b200_arm(args, cfg):
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"1 step on {rows} of {cfg['rows']} rows, same model, NumPy f32 restatement of the reference path (oracle/), "
                                           f"host BLAS {threads} threads ({gfs:.0f} GFLOP/s on a 1536^3 sgemm), {dt:.1f} s"}
+        v1, r1, d1, g1 = cpu_one_core_run(cfg, target_s=8.0)
+        line["cpu_baseline"]["one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                            "sample": f"1 step on {r1} of {cfg['rows']} rows, single-threaded C restatement (oracle/oracle_c.c, "
+                                                      f"{g1:.0f} GFLOP/s on a 1024^3 sgemm), {d1:.1f} s"}
     if dp is not None:
         dp.close()
     if rank == 0:
