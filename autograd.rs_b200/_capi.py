@@ -19,7 +19,7 @@ ADD, SUB, MUL = 0, 1, 2
 SMUL, SDIV, SRSUB, SADD = 0, 1, 2, 3
 BCAST_TRAILING, BCAST_LEADING = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SKINNY = 0, 1, 2, 3
-TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK, TUNE_TC_2CTA, TUNE_TC_SPLITK = 0, 1, 2, 3, 4, 5
+TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK, TUNE_TC_2CTA, TUNE_TC_SPLITK, TUNE_TC_CROSS = 0, 1, 2, 3, 4, 5, 6
 
 _lib = None
 
@@ -66,6 +66,7 @@ def lib():
             "agrs_set_gemm_path": [vp, i32],
             "agrs_last_gemm_path": [vp],
             "agrs_set_tuning": [vp, i32, i64],
+            "agrs_get_tuning": [vp, i32, C.POINTER(i64)],
             "agrs_peer_alloc": [vp, sz, C.POINTER(vp)],
             "agrs_peer_free": [vp, vp],
             "agrs_peer_export": [vp, vp, vp],

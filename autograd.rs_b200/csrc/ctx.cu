@@ -1,6 +1,7 @@
 // Context, stream-ordered memory pool and transfers of libagrs_b200.so.
 // Replaces CudaData{ptr} + Drop of the reference (src/tensor/storage.rs:5-14).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "agrs_internal.h"
@@ -33,6 +34,10 @@ static int ctx_init(int device, cudaStream_t stream, bool own, agrs_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
+  if (const char* e = getenv("AGRS_TC_CROSS")) {  // default of AGRS_TUNE_TC_CROSS (agrs.h)
+    const int v = atoi(e);
+    if (v >= 0 && v <= 2) ctx->tc_cross = v;
+  }
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }
   if (own) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }

@@ -35,9 +35,28 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
     case AGRS_TUNE_TC_2CTA:
       ctx->tc_2cta = value ? 1 : 0;
       return AGRS_OK;
+    case AGRS_TUNE_TC_CROSS:
+      AGRS_REQUIRE(ctx, value >= 0 && value <= 2, AGRS_ERR_INVALID, "AGRS_TUNE_TC_CROSS must be 0, 1 or 2");
+      ctx->tc_cross = int(value);
+      return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS:
       ctx->tc_min_flops = value;
       return AGRS_OK;
+  }
+  return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown tuning key %d", key);
+}
+
+int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, value, AGRS_ERR_INVALID, "agrs_get_tuning: null out");
+  switch (key) {
+    case AGRS_TUNE_TC_BN: *value = ctx->tc_bn; return AGRS_OK;
+    case AGRS_TUNE_TC_EXPLICIT_HI: *value = ctx->tc_explicit_hi; return AGRS_OK;
+    case AGRS_TUNE_TC_KCHUNK: *value = ctx->tc_kchunk; return AGRS_OK;
+    case AGRS_TUNE_TC_SPLITK: *value = ctx->tc_splitk; return AGRS_OK;
+    case AGRS_TUNE_TC_2CTA: *value = ctx->tc_2cta; return AGRS_OK;
+    case AGRS_TUNE_TC_CROSS: *value = ctx->tc_cross; return AGRS_OK;
+    case AGRS_TUNE_TC_MIN_MACS: *value = ctx->tc_min_flops; return AGRS_OK;
   }
   return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown tuning key %d", key);
 }

@@ -82,6 +82,84 @@ __device__ __forceinline__ float lo_of(float x) {
   return (lo == lo) ? lo : 0.f;                       // inf - inf: keep inf/NaN in the hi term only
 }
 
+// ---- cross terms in bf16 (CROSS = 1, 2) -----------------------------------------------------------------------------------
+// The two correction terms a_lo*b and a*b_lo are 2^-10 of the product, so 8 significant bits on each factor keep them to
+// ~2^-19 of the product -- and kind::f16 runs at twice the tf32 rate with half the operand bytes: a k-block costs
+// 4 (hi*hi, tf32) + 2 + 2 (bf16) MMA slots instead of 12.  The splitter warps therefore write, per k-block and operand, two
+// K-major bf16 tiles of [128 rows][32 k] (8 KB each): lo = bf16(x - trunc_tf32(x)) and x16 = bf16(x); the raw f32 tile still
+// feeds the hi*hi pass untouched.  The splitters transpose while they convert, so the bf16 tiles are K-major whatever the
+// storage order of the f32 operand.  Tile layouts (both canonical UMMA K-major forms):
+//   CROSS 1  SWIZZLE_64B : row r at r*64, its 16-byte chunk j (k = 8j..8j+7) at chunk slot j ^ ((r >> 1) & 3); SBO = 512
+//   CROSS 2  INTERLEAVE  : chunk j of row r at j*2048 + r*16 (core matrices of 8 rows x 16 B); SBO = 128, LBO = 2048
+constexpr uint32_t BF_TILE = BM * BK * 2;  // 8 KB
+static_assert(BM == BNH, "one splitter thread per row of A and per row of B");
+
+template <int CROSS>
+__device__ __forceinline__ uint32_t bf_chunk_offset(uint32_t row, uint32_t j) {
+  return CROSS == 1 ? row * 64u + ((j ^ ((row >> 1) & 3u)) << 4) : j * 2048u + row * 16u;
+}
+// descriptor of the i-th 16-wide K slice (kind::f16 UMMA_K) of a bf16 tile
+template <int CROSS>
+__device__ __forceinline__ uint64_t make_bf_desc(uint32_t tile, int i) {
+  const uint32_t addr = tile + (CROSS == 1 ? uint32_t(i) * 32u : uint32_t(i) * 4096u);
+  uint64_t d = 0;
+  d |= uint64_t((addr & 0x3FFFF) >> 4);
+  d |= uint64_t(CROSS == 1 ? 1u : (2048u >> 4)) << 16;          // LBO: unused with a swizzle / next 16-byte chunk of K
+  d |= uint64_t(CROSS == 1 ? (512u >> 4) : (128u >> 4)) << 32;  // SBO: next 8 rows
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(CROSS == 1 ? 4 : 0) << 61;                      // SWIZZLE_64B / no swizzle
+  return d;
+}
+// D = f32, A = B = bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float e0, float e1) {  // e0 at the lower address
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+  return r;
+}
+// One row (32 k) of a raw f32 operand tile -> the same row of its two bf16 tiles.
+//   raw K-major  tile: [128 rows][128 B], SWIZZLE_128B: 16-byte chunk c of row r sits in slot c ^ (r & 7)
+//   raw MN-major tile: 4 blocks of [32 k][32 rows], SWIZZLE_128B_ATOM_32B: 32-byte chunk c of k-line k sits in slot c ^ (k & 3)
+template <bool MN_MAJOR, int CROSS>
+__device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, uint32_t out_x, uint32_t row) {
+  float v[BK];
+  if (MN_MAJOR) {
+    const uint32_t base = raw + (row >> 5) * 4096u + (row & 7u) * 4u, c = (row & 31u) >> 3;
+#pragma unroll
+    for (uint32_t k = 0; k < uint32_t(BK); ++k)
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(base + k * 128u + ((c ^ (k & 3u)) << 5)));
+  } else {
+    const uint32_t base = raw + row * 128u;
+#pragma unroll
+    for (uint32_t c = 0; c < 8; ++c)
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3])
+                   : "r"(base + ((c ^ (row & 7u)) << 4)));
+  }
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    uint32_t lo[4], x[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float e0 = v[8 * j + 2 * p], e1 = v[8 * j + 2 * p + 1];
+      lo[p] = pack_bf16(lo_of(e0), lo_of(e1));
+      x[p] = pack_bf16(e0, e1);
+    }
+    const uint32_t off = bf_chunk_offset<CROSS>(row, j);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_x + off), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
+  }
+}
+
 // GEMM -> reduce-scatter (data-parallel weight gradients, csrc/fused_dp.cu): with SCATTER the epilogue also pushes every finished
 // 32-column piece of C to the rank that owns it -- element e = off + row*N + col of the flat parameter space belongs to rank
 // e / shard, which keeps one slot per source rank -- with P2P stores over NVLink, tile by tile, while the tensor cores are already
@@ -94,7 +172,7 @@ struct ScatterArgs {
   size_t off;       // float offset of C inside the flat parameter space (a multiple of 32)
 };
 
-template <bool A_MN, bool B_MN, bool SCATTER>
+template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C, int64_t ldc,
                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
@@ -212,17 +290,31 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tc_fence_after();
             if (lane == 0) {
               const uint32_t a_hi = smem_base + r * RAW_BYTES, b_hi = a_hi + A_BYTES;
-              const uint32_t a_lo = lo_base + l * RAW_BYTES, b_lo = a_lo + A_BYTES;
               const bool first_kb = (kb == c0);
+              if constexpr (CROSS == 0) {
+                const uint32_t a_lo = lo_base + l * RAW_BYTES, b_lo = a_lo + A_BYTES;
 #pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {
-                const uint64_t da_hi = make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>());
-                const uint64_t da_lo = make_smem_desc<A_MN>(a_lo + k * k_slice_bytes<A_MN>());
-                const uint64_t db_hi = make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>());
-                const uint64_t db_lo = make_smem_desc<B_MN>(b_lo + k * k_slice_bytes<B_MN>());
-                umma_tf32_2cta(d_tmem, da_lo, db_hi, idesc, (first_kb && k == 0) ? 0u : 1u);  // small terms first
-                umma_tf32_2cta(d_tmem, da_hi, db_lo, idesc, 1u);
-                umma_tf32_2cta(d_tmem, da_hi, db_hi, idesc, 1u);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  const uint64_t da_hi = make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>());
+                  const uint64_t da_lo = make_smem_desc<A_MN>(a_lo + k * k_slice_bytes<A_MN>());
+                  const uint64_t db_hi = make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>());
+                  const uint64_t db_lo = make_smem_desc<B_MN>(b_lo + k * k_slice_bytes<B_MN>());
+                  umma_tf32_2cta(d_tmem, da_lo, db_hi, idesc, (first_kb && k == 0) ? 0u : 1u);  // small terms first
+                  umma_tf32_2cta(d_tmem, da_hi, db_lo, idesc, 1u);
+                  umma_tf32_2cta(d_tmem, da_hi, db_hi, idesc, 1u);
+                }
+              } else {
+                // lo stage: [A lo | A x16 | B lo | B x16], 8 KB each, K-major bf16
+                const uint32_t a_lo = lo_base + l * RAW_BYTES, a_x = a_lo + BF_TILE, b_lo = a_x + BF_TILE, b_x = b_lo + BF_TILE;
+#pragma unroll
+                for (int i = 0; i < BK / 16; ++i) {  // cross terms first (they are the small ones), two 16-wide bf16 slices each
+                  umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_lo, i), make_bf_desc<CROSS>(b_x, i), kIdescBf16, (first_kb && i == 0) ? 0u : 1u);
+                  umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_x, i), make_bf_desc<CROSS>(b_lo, i), kIdescBf16, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  umma_tf32_2cta(d_tmem, make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>()),
+                                 make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>()), idesc, 1u);
               }
               umma_commit_pair(raw_free(r));  // both CTAs may refill this raw stage ...
               umma_commit_pair(lo_free(l));   // ... and this lo stage once the MMAs above have read them
@@ -255,18 +347,26 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t r = it % R, rph = (it / R) & 1u, l = it % L, lph = (it / L) & 1u;
         mbar_wait(raw_full(r), rph);
         mbar_wait(lo_free(l), lph ^ 1u);
-        const uint32_t src = smem_base + r * RAW_BYTES + tid * 16, dst = lo_base + l * RAW_BYTES + tid * 16;
-        float4 v[kPerThread];
+        if constexpr (CROSS == 0) {
+          const uint32_t src = smem_base + r * RAW_BYTES + tid * 16, dst = lo_base + l * RAW_BYTES + tid * 16;
+          float4 v[kPerThread];
 #pragma unroll
-        for (int i = 0; i < kPerThread; ++i)
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
-                       : "r"(src + i * kStride));
+          for (int i = 0; i < kPerThread; ++i)
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                         : "r"(src + i * kStride));
 #pragma unroll
-        for (int i = 0; i < kPerThread; ++i)
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + i * kStride), "f"(lo_of(v[i].x)), "f"(lo_of(v[i].y)),
-                       "f"(lo_of(v[i].z)), "f"(lo_of(v[i].w))
-                       : "memory");
+          for (int i = 0; i < kPerThread; ++i)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + i * kStride), "f"(lo_of(v[i].x)), "f"(lo_of(v[i].y)),
+                         "f"(lo_of(v[i].z)), "f"(lo_of(v[i].w))
+                         : "memory");
+        } else {
+          // thread tid of the group owns row tid of A and row tid of B for this k-block
+          static_assert(kGroupWarps * 32 == BM, "bf16 cross terms: one splitter thread per operand row");
+          const uint32_t raw = smem_base + r * RAW_BYTES, out = lo_base + l * RAW_BYTES;
+          split_row_bf16<A_MN, CROSS>(raw, out, out + BF_TILE, uint32_t(tid));
+          split_row_bf16<B_MN, CROSS>(raw + A_BYTES, out + 2 * BF_TILE, out + 3 * BF_TILE, uint32_t(tid));
+        }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(done_remote + 8u * l);
@@ -398,10 +498,10 @@ static int choose_splits(int64_t tiles, int64_t pairs, int64_t num_kb, int force
   return best;
 }
 
-template <bool A_MN, bool B_MN, bool SCATTER>
+template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
 static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
                   int64_t N, int64_t K, int kb_per_chunk, const ScatterArgs& sc) {
-  auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN, SCATTER>;
+  auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN, SCATTER, CROSS>;
   AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int64_t pairs = ctx->sm_count / 2;
@@ -447,14 +547,16 @@ static int gemm_tc_2cta_impl(agrs_ctx* ctx, int transA, int transB, int64_t M, i
   const int64_t num_kb = (K + tc::BK - 1) / tc::BK;
   const int kpc = ctx->tc_kchunk > 0 ? int((ctx->tc_kchunk + tc::BK - 1) / tc::BK) : int(num_kb);
   static const tc2::ScatterArgs none{};
-#define AGRS_PAIR(AM, BMJ)                                                                                          \
-  (sc ? tc2::launch<AM, BMJ, true>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc)                                     \
-      : tc2::launch<AM, BMJ, false>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none))
+#define AGRS_PAIR_X(AM, BMJ, X)                                                                                     \
+  (sc ? tc2::launch<AM, BMJ, true, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc)                                  \
+      : tc2::launch<AM, BMJ, false, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none))
+#define AGRS_PAIR(AM, BMJ) (ctx->tc_cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : ctx->tc_cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) : AGRS_PAIR_X(AM, BMJ, 0))
   if (A_MN && B_MN) return AGRS_PAIR(true, true);
   if (A_MN) return AGRS_PAIR(true, false);
   if (B_MN) return AGRS_PAIR(false, true);
   return AGRS_PAIR(false, false);
 #undef AGRS_PAIR
+#undef AGRS_PAIR_X
 }
 
 int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,

@@ -183,6 +183,13 @@ class Device:
         if rc:
             raise Panic(rc, _capi.lib().agrs_last_error(self.ctx_handle).decode())
 
+    def get_tuning(self, key):
+        v = C.c_int64()
+        rc = _capi.lib().agrs_get_tuning(self.ctx_handle, int(key), C.byref(v))
+        if rc:
+            raise Panic(rc, _capi.lib().agrs_last_error(self.ctx_handle).decode())
+        return int(v.value)
+
     def set_gemm_path(self, path):
         rc = _capi.lib().agrs_set_gemm_path(self.ctx_handle, int(path))
         if rc:

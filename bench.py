@@ -390,9 +390,13 @@ def run_b200_arm(args, cfg):
 
     # ---- roofline of the dominant kernel ----
     peaks = load_peaks()
-    # tf32 tensor rate = 1/2 of bf16 (nominal 1.1 vs 2.25 PFLOP/s dense); 3xTF32 issues 3 MMAs per algorithmic one:
-    # the f32-faithful peak is bf16/6.  The GEMMs run inside a long step -> sustained figure.
-    peak_alg = peaks["bf16_sustained"] / 2.0 / 3.0
+    # tf32 tensor rate = 1/2 of bf16 (nominal 1.1 vs 2.25 PFLOP/s dense).  Per algorithmic product the split GEMM issues
+    #   cross = 0: three tf32 MMAs                      -> 3 tf32 slots, f32-faithful peak = bf16/6
+    #   cross > 0: one tf32 MMA + two bf16 MMAs (1/2 slot each) -> 2 tf32 slots, peak = bf16/4
+    # The GEMMs run inside a long step -> sustained figure.
+    cross = dev.get_tuning(_capi.TUNE_TC_CROSS)
+    slots = 3.0 if cross == 0 else 2.0
+    peak_alg = peaks["bf16_sustained"] / 2.0 / slots
     roofline = None
     if g_n:
         ach = g_fl / (g_ms * 1e-3) / 1e12
@@ -404,17 +408,19 @@ def run_b200_arm(args, cfg):
             except Exception:
                 traffic = None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak_alg, "unit": "TFLOP/s", "frac": ach / peak_alg, "traffic": traffic,
-                    "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2 kind::tf32 x3)", "launches": g_n, "avg_launch_ms": g_ms / g_n,
-                    "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_tflops": 3 * ach,
-                    "gemm_share_of_step": g_ms / ms,
-                    "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / 3 (3xTF32)"}
+                    "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2: " +
+                              ("kind::tf32 x3)" if cross == 0 else f"kind::tf32 hi*hi + 2 x kind::f16 bf16 cross terms, tile layout {cross})"),
+                    "launches": g_n, "avg_launch_ms": g_ms / g_n,
+                    "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_equivalent_tflops": slots * ach,
+                    "gemm_share_of_step": g_ms / ms, "cross_terms": "tf32" if cross == 0 else "bf16",
+                    "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / {slots:.0f} (tf32-rate MMA slots per product)"}
         # context: what cuBLAS itself reaches on this pool's B200s for PLAIN tf32 (one MMA per product) -- tools/tf32_cublas_peak.py
         cub = os.path.join(ROOT, "profiles", "r1_cublas_peaks.json")
         if os.path.exists(cub):
             try:
                 c = json.load(open(cub))
                 roofline["cublas_tf32_tflops"] = {"burst": c["tf32"]["burst_tflops"], "sustained": c["tf32"]["sustained_tflops"]}
-                roofline["executed_frac_of_cublas_tf32_sustained"] = 3 * ach / c["tf32"]["sustained_tflops"]
+                roofline["executed_frac_of_cublas_tf32_sustained"] = slots * ach / c["tf32"]["sustained_tflops"]
                 roofline["cublas_f32_simt_tflops"] = c["f32_simt"]["sustained_tflops"]
             except Exception:
                 pass

@@ -97,9 +97,12 @@ enum agrs_tuning_key {
   AGRS_TUNE_TC_MIN_MACS = 2,    /* AUTO path: minimum M*N*K for the tcgen05 kernel */
   AGRS_TUNE_TC_KCHUNK = 3,      /* K elements accumulated in TMEM between round-to-nearest folds into C (0 = all of K; default 1024) */
   AGRS_TUNE_TC_2CTA = 4,        /* 1 (default): cta_group::2 pair kernel (256x256 tiles) when M > 128; 0: always the one-CTA kernel */
-  AGRS_TUNE_TC_SPLITK = 5       /* pair kernel: 0 (default) = pick the K split that fills the last wave of CTA pairs; n = force n splits */
+  AGRS_TUNE_TC_SPLITK = 5,      /* pair kernel: 0 (default) = pick the K split that fills the last wave of CTA pairs; n = force n splits */
+  AGRS_TUNE_TC_CROSS = 6        /* pair kernel, the two correction terms a_lo*b + a*b_lo: 0 = tf32 operands (3xTF32, ~1e-6), 1 / 2 = bf16
+                                   operands at twice the MMA rate (SWIZZLE_64B / unswizzled tiles; ~3e-6).  Default: env AGRS_TC_CROSS, else 0 */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
+AGRS_API int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value);
 
 /* ---- whole-step CUDA graphs (launch-bound configurations: fit_sine runs ~11 tiny kernels per step) ----
  * Between agrs_capture_begin and agrs_capture_end every launch, memset, copy, stream-ordered alloc/free and NCCL call made on

@@ -317,6 +317,52 @@ def test_gemm_tcgen05(ctx, M, N, Kd, ta, tb, pair, splitk):
         ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, 0)
 
 
+@pytest.mark.parametrize("M,N,Kd,ta,tb", [(256, 256, 32, 0, 1), (384, 1000, 520, 0, 1), (1000, 520, 3000, 1, 0), (200, 300, 100, 1, 1),
+                                         (2048, 1024, 1024, 0, 0), (132, 260, 4100, 1, 1), (4100, 132, 260, 1, 0), (512, 384, 96, 0, 0)])
+@pytest.mark.parametrize("cross", [1, 2])
+@pytest.mark.parametrize("splitk", [0, 2])
+def test_gemm_pair_bf16_cross_terms(ctx, M, N, Kd, ta, tb, cross, splitk):
+    """pair kernel with the two correction terms on bf16 operands (AGRS_TUNE_TC_CROSS 1: 64-byte-swizzled tiles, 2: unswizzled):
+    same 2e-5 bar as the all-tf32 split, on every operand-major combination (the splitter warps transpose MN-major operands)"""
+    rng = np.random.default_rng(M + 3 * N + 5 * Kd + cross)
+    ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, cross)
+    ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, splitk)
+    try:
+        for bias in (False, True):
+            gemm_case(ctx, rng, M, N, Kd, ta, tb, bias, K.GEMM_TCGEN05, 2e-5)
+            assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_TCGEN05
+    finally:
+        ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, 0)
+        ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, 0)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("cross", [0, 1, 2])
+@pytest.mark.parametrize("lo_side", ["a", "b"])
+def test_gemm_pair_cross_terms_exact(ctx, ta, tb, cross, lo_side):
+    """Known-answer test of the split itself.  One operand is s * (1 + c * 2^-12) with s in {+-1, +-2}, c in 0..3: its tf32 part is
+    s and its remainder s*c*2^-12 survives only through the correction term; the other operand holds small integers.  Every partial
+    sum is exactly representable, so the result must equal the f64 product BIT FOR BIT -- any misplaced element of a lo / bf16 tile
+    (swizzle, transpose, K slice, CTA half) changes it."""
+    M, N, Kd = 512, 384, 160
+    rng = np.random.default_rng(17 * cross + 2 * ta + tb)
+    s = rng.choice(np.array([-2.0, -1.0, 1.0, 2.0]), (M, Kd) if lo_side == "a" else (Kd, N))
+    c = rng.integers(0, 4, s.shape)
+    split = (s * (1.0 + c * 2.0 ** -12)).astype(np.float32)
+    ints = rng.integers(-3, 4, (Kd, N) if lo_side == "a" else (M, Kd)).astype(np.float32)
+    opA, opB = (split, ints) if lo_side == "a" else (ints, split)
+    truth = opA.astype(np.float64) @ opB.astype(np.float64)
+    assert np.array_equal(truth.astype(np.float32).astype(np.float64), truth)  # representable: the test is exact by construction
+    A = np.ascontiguousarray(opA.T) if ta else opA
+    B = np.ascontiguousarray(opB.T) if tb else opB
+    ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, cross)
+    try:
+        got = ctx.gemm(A, B, bool(ta), bool(tb), None, K.GEMM_TCGEN05)
+    finally:
+        ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, 0)
+    assert np.array_equal(got.astype(np.float64), truth), float(np.abs(got - truth).max())
+
+
 def test_gemm_tcgen05_special_values(ctx):
     """NaN and zeros propagate as in f32 arithmetic.  An inf operand gives a NON-FINITE result (inf or NaN, where plain f32
     gives inf): its product with the other operand's lo part is inf * 0 or -inf -- inherent to any hi/lo split scheme."""

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--bn", type=int, default=256)
     ap.add_argument("--kchunk", type=int, default=1024)
     ap.add_argument("--pair", type=int, default=1, help="1: cta_group::2 pair kernel, 0: one-CTA kernel")
+    ap.add_argument("--cross", type=int, default=0, help="pair kernel correction terms: 0 tf32, 1 bf16 (64B swizzle), 2 bf16 (no swizzle)")
     ap.add_argument("--iters", type=int, default=0, help="time this many launches after the check")
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
@@ -50,10 +51,11 @@ def main():
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_EXPLICIT_HI, int(a.explicit_hi))
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_KCHUNK, a.kchunk)
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_2CTA, a.pair)
+    ctx.call("agrs_set_tuning", _capi.TUNE_TC_CROSS, a.cross)
     path = {"tc": _capi.GEMM_TCGEN05, "simt": _capi.GEMM_SIMT, "auto": _capi.GEMM_AUTO}[a.path]
     got = ctx.gemm(A, B, bool(a.ta), bool(a.tb), bias, path).astype(np.float64)
     scale = np.abs(truth).max()
-    res = {"path": a.path, "ta": a.ta, "tb": a.tb, "M": M, "N": N, "K": K, "bias": a.bias, "explicit_hi": a.explicit_hi, "bn": a.bn, "kchunk": a.kchunk, "pair": a.pair,
+    res = {"path": a.path, "ta": a.ta, "tb": a.tb, "M": M, "N": N, "K": K, "bias": a.bias, "explicit_hi": a.explicit_hi, "bn": a.bn, "kchunk": a.kchunk, "pair": a.pair, "cross": a.cross,
            "rel_err_vs_f64": float(np.abs(got - truth).max() / scale),
            "f32_numpy_rel_err_vs_f64": float(np.abs(f32ref - truth).max() / scale),
            "rel_err_vs_f32": float(np.abs(got - f32ref).max() / scale)}
