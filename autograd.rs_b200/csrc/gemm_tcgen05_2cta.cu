@@ -29,8 +29,14 @@ constexpr int kSplitWarps = 8;
 constexpr int kSplitGroups = AGRS_SPLIT_GROUPS;  // groups of splitter warps that alternate k-blocks
 constexpr int BN = 256;   // pair-tile width
 constexpr int BNH = 128;  // columns of B staged per CTA
-constexpr int R = 4;      // raw (TMA) stages
-constexpr int L = 3;      // lo (splitter) stages
+#ifndef AGRS_PAIR_RAW_STAGES
+#define AGRS_PAIR_RAW_STAGES 4
+#endif
+#ifndef AGRS_PAIR_LO_STAGES
+#define AGRS_PAIR_LO_STAGES 3
+#endif
+constexpr int R = AGRS_PAIR_RAW_STAGES;  // raw (TMA) stages
+constexpr int L = AGRS_PAIR_LO_STAGES;   // lo (splitter) stages
 constexpr uint32_t A_BYTES = BM * BK * 4;    // 16 KB
 constexpr uint32_t B_BYTES = BNH * BK * 4;   // 16 KB
 constexpr uint32_t RAW_BYTES = A_BYTES + B_BYTES;
@@ -361,11 +367,15 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                          "f"(lo_of(v[i].z)), "f"(lo_of(v[i].w))
                          : "memory");
         } else {
-          // thread tid of the group owns row tid of A and row tid of B for this k-block
-          static_assert(kGroupWarps * 32 == BM, "bf16 cross terms: one splitter thread per operand row");
+          // the group's threads share the 128 rows of A and the 128 rows of B of this k-block (a warp always holds 32 consecutive rows)
+          static_assert((2 * BM) % (kGroupWarps * 32) == 0 && kGroupWarps * 32 <= 2 * BM, "bf16 cross terms: whole rows per splitter thread");
           const uint32_t raw = smem_base + r * RAW_BYTES, out = lo_base + l * RAW_BYTES;
-          split_row_bf16<A_MN, CROSS>(raw, out, out + BF_TILE, uint32_t(tid));
-          split_row_bf16<B_MN, CROSS>(raw + A_BYTES, out + 2 * BF_TILE, out + 3 * BF_TILE, uint32_t(tid));
+#pragma unroll
+          for (int item = tid; item < 2 * BM; item += kGroupWarps * 32) {
+            const uint32_t row = uint32_t(item) & uint32_t(BM - 1);
+            if (item < BM) split_row_bf16<A_MN, CROSS>(raw, out, out + BF_TILE, row);
+            else           split_row_bf16<B_MN, CROSS>(raw + A_BYTES, out + 2 * BF_TILE, out + 3 * BF_TILE, row);
+          }
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();

@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--pair", default="both")
     ap.add_argument("--sizes", default="256,512,1024,2048,4096,8192")
     ap.add_argument("--linear", action="store_true", help="also the Linear fwd/dX/dW shapes of C2 (8192x4096x4096) and C5 (8192x8192x8192)")
+    ap.add_argument("--linear-c2", action="store_true", help="only the three Linear shapes of C2")
     ap.add_argument("--odd", action="store_true", help="ragged shapes (partial tiles in M, N and K)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kchunk", type=int, default=1024)
@@ -70,8 +71,8 @@ def main():
     for n in [int(s) for s in a.sizes.split(",") if s]:
         for ta, tb in [(int(m[0]), int(m[1])) for m in a.majors.split(",")]:  # fwd X.W (NN), dX = G.W^T (NT), dW = X^T.G (TN)
             cases.append((n, n, n, ta, tb, False))
-    if a.linear:
-        for (m, n, k) in ((8192, 4096, 4096), (8192, 8192, 8192)):
+    if a.linear or a.linear_c2:
+        for (m, n, k) in (((8192, 4096, 4096),) if a.linear_c2 else ((8192, 4096, 4096), (8192, 8192, 8192))):
             cases += [(m, n, k, 0, 0, True), (m, k, n, 0, 1, False), (k, n, m, 1, 0, False)]
     if a.odd:
         cases += [(136, 72, 40, 0, 0, True), (200, 300, 100, 1, 1, False), (1000, 520, 3000, 1, 0, True), (257, 264, 36, 0, 1, False),
