@@ -30,17 +30,22 @@ constexpr int kSplitGroups = AGRS_SPLIT_GROUPS;  // groups of splitter warps tha
 constexpr int BN = 256;   // pair-tile width
 constexpr int BNH = 128;  // columns of B staged per CTA
 #ifndef AGRS_PAIR_RAW_STAGES
-#define AGRS_PAIR_RAW_STAGES 4
+#define AGRS_PAIR_RAW_STAGES 3
 #endif
 #ifndef AGRS_PAIR_LO_STAGES
 #define AGRS_PAIR_LO_STAGES 3
 #endif
 constexpr int R = AGRS_PAIR_RAW_STAGES;  // raw (TMA) stages
 constexpr int L = AGRS_PAIR_LO_STAGES;   // lo (splitter) stages
+// A splitter group waits on a stage barrier one phase after the phase it last saw complete only if the stage's previous user is not
+// newer than the group's own previous k-block (mbarrier parity waits alias two phases apart): groups <= ring depth, for both rings.
+static_assert(kSplitGroups <= R && kSplitGroups <= L, "splitter groups must not outnumber the stages of either ring");
 constexpr uint32_t A_BYTES = BM * BK * 4;    // 16 KB
 constexpr uint32_t B_BYTES = BNH * BK * 4;   // 16 KB
 constexpr uint32_t RAW_BYTES = A_BYTES + B_BYTES;
-constexpr uint32_t SMEM_BYTES = (R + L) * RAW_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr uint32_t EPI_TILE = 32 * 32 * 4;         // one 32 x 32 f32 piece of C staged for a TMA store
+constexpr uint32_t EPI_BYTES = 4 * 2 * EPI_TILE;   // two buffers per epilogue warp
+constexpr uint32_t SMEM_BYTES = (R + L) * RAW_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of 256 columns
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
@@ -81,11 +86,36 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                : "memory");
 }
 
+// ---- epilogue through shared memory and TMA ---------------------------------------------------------------------------------
+// A thread of an epilogue warp holds 32 consecutive columns of ONE row (tcgen05.ld 32x32b), so a direct st.global.v4 touches 32
+// different 128-byte lines per warp instruction: profiles/r1_gemm_bf16cross_ncu_summary.txt has those stores and the read-modify-
+// write of the K chunks at 44 % of the LSU data-pipe wavefronts, the pipe the splitter warps live on.  Instead each warp stages
+// its 32 x 32 piece in shared memory (128-byte-swizzled, conflict-free) and one lane hands it to the TMA: a tensor store for the
+// first K chunk, a tensor reduce-add (f32 add in L2, round-to-nearest, one writer per element: deterministic) for the later ones.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // at most N of this thread's bulk groups still read their shared-memory source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }  // ... and are performed
+
 __device__ __forceinline__ float lo_of(float x) {
   const uint32_t u = __float_as_uint(x);
   const float hi = __uint_as_float(u & 0xFFFFE000u);  // what the tensor core reads from the raw container
-  float lo = x - hi;                                  // exact; the tensor core truncates it to tf32 (2^-21 relative to x)
-  return (lo == lo) ? lo : 0.f;                       // inf - inf: keep inf/NaN in the hi term only
+  // exact; an inf input gives inf - inf = NaN here, so its products are NaN where plain f32 says inf (documented in agrs.h: the
+  // other correction term already multiplies inf by a lo part that is usually exactly zero)
+  return x - hi;
 }
 
 // ---- cross terms in bf16 (CROSS = 1, 2) -----------------------------------------------------------------------------------
@@ -182,11 +212,13 @@ template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C, int64_t ldc,
                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
-                   const __grid_constant__ ScatterArgs sc) {
+                   const __grid_constant__ ScatterArgs sc, const __grid_constant__ CUtensorMap tmap_c,
+                   const __grid_constant__ CUtensorMap tmap_w, int epi_tma) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
-  const uint32_t bar_base = lo_base + L * RAW_BYTES;
+  const uint32_t epi_base = lo_base + L * RAW_BYTES;
+  const uint32_t bar_base = epi_base + EPI_BYTES;
   auto raw_full = [&](int s) { return bar_base + 8u * s; };
   auto raw_free = [&](int s) { return bar_base + 8u * (R + s); };
   auto lo_free = [&](int s) { return bar_base + 8u * (2 * R + s); };
@@ -390,6 +422,72 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t tempty_remote = mapa_rank(tempty_bar(0), 0);
     int acc = 0;
     uint32_t acc_ph = 0;
+    if (!SCATTER && epi_tma) {
+      // ---- staged epilogue: TMEM -> registers -> swizzled shared memory -> TMA store / reduce-add (see tma_store_3d) ----
+      const uint32_t stage0 = epi_base + uint32_t(q) * (2 * EPI_TILE);
+      uint32_t issued = 0;  // pieces this warp has handed to the TMA (buffer = issued & 1)
+      for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+        const Work w = work_item(t);
+        const int64_t row0 = w.mb * 2 * BM + rank * BM + q * 32;
+        // split 0 produces C (with the bias); split s > 0 plane s-1 of the workspace [splits-1][M][N]
+        const CUtensorMap* const cmap = w.split == 0 ? &tmap_c : &tmap_w;
+        const int32_t plane = w.split == 0 ? 0 : w.split - 1;
+        const float* const bias_s = w.split == 0 ? bias : nullptr;
+        for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
+          mbar_wait(tfull_bar(acc), acc_ph);
+          tc_fence_after();
+          // the reductions of this chunk go to the addresses the previous chunk's pieces went to: those must have landed
+          if (ch > 0 && lane == 0) bulk_wait_all();
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_wait_ld();
+            const int64_t col0 = w.nb * BN + c * 32;
+            if (row0 < M && col0 < N) {  // warp-uniform; rows and columns past the edge are clipped by the tensor map
+              if (ch == 0 && bias_s) {
+                if (col0 + 32 <= N) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias_s + col0) + j);
+                    v[4 * j] = __float_as_uint(b.x + __uint_as_float(v[4 * j]));
+                    v[4 * j + 1] = __float_as_uint(b.y + __uint_as_float(v[4 * j + 1]));
+                    v[4 * j + 2] = __float_as_uint(b.z + __uint_as_float(v[4 * j + 2]));
+                    v[4 * j + 3] = __float_as_uint(b.w + __uint_as_float(v[4 * j + 3]));
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (col0 + j < N) v[j] = __float_as_uint(__ldg(bias_s + col0 + j) + __uint_as_float(v[j]));
+                }
+              }
+              const uint32_t buf = stage0 + (issued & 1u) * EPI_TILE;
+              if (lane == 0) bulk_wait_read<1>();  // the piece staged in this buffer two pieces ago has been read out
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j)  // row `lane` of the piece, 16-byte chunk j in slot j ^ (lane & 7): SWIZZLE_128B
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + uint32_t(lane) * 128u + (uint32_t(j ^ (lane & 7)) << 4)),
+                             "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                             : "memory");
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                if (ch == 0) tma_store_3d(cmap, buf, int32_t(col0), int32_t(row0), plane);
+                else         tma_reduce_add_3d(cmap, buf, int32_t(col0), int32_t(row0), plane);
+                bulk_commit();
+              }
+              ++issued;
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(tempty_remote + 8u * acc);
+          if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+        }
+      }
+      if (lane == 0) bulk_wait_all();  // shared memory stays valid, and C is complete, before the CTA leaves
+    } else
     for (int64_t t = pair; t < num_tiles; t += num_pairs) {
       const Work w = work_item(t);
       const int64_t nb = w.nb;
@@ -527,9 +625,18 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     if (rc) return rc;
     Cw = ctx->workspace;
   }
+  // staged TMA epilogue: C (and the split workspace) must be describable by a tensor map -- 16-byte aligned base and row pitch
+  CUtensorMap tc_map = ta, tw_map = ta;  // placeholders when unused
+  int epi_tma = 0;
+  if (!SCATTER && ctx->tc_epi_tma && (ldc & 3) == 0 && agrs_aligned16(C) && (splits == 1 || (N & 3) == 0)) {
+    int rc = encode_3d_out(ctx, &tc_map, C, uint64_t(N), uint64_t(M), 1, uint64_t(ldc));
+    if (!rc && splits > 1) rc = encode_3d_out(ctx, &tw_map, Cw, uint64_t(N), uint64_t(M), uint64_t(splits - 1), uint64_t(N));
+    if (rc) return rc;
+    epi_tma = 1;
+  }
   const int64_t items = tiles * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc);
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma);
   AGRS_LAUNCHED(ctx);
   if (splits > 1) {
     const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;

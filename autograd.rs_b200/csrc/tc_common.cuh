@@ -162,4 +162,19 @@ static inline int encode_2d(agrs_ctx* ctx, CUtensorMap* map, const float* base, 
   return AGRS_OK;
 }
 
+// 3-D f32 tensor map of an output [planes][rows][cols] (row pitch `ld` elements, planes `rows * ld` apart) for TMA stores of
+// 32 x 32 pieces staged 128-byte-swizzled in shared memory; pieces that cross the last row or column are clipped by the hardware
+static inline int encode_3d_out(agrs_ctx* ctx, CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t planes, uint64_t ld) {
+  cuuint64_t dims[3] = {cols, rows, planes};
+  cuuint64_t strides[2] = {ld * sizeof(float), rows * ld * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<PFN_encodeTiled>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AGRS_REQUIRE(ctx, r == CUDA_SUCCESS, AGRS_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d) cols=%llu rows=%llu planes=%llu ld=%llu", int(r),
+               (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)planes, (unsigned long long)ld);
+  return AGRS_OK;
+}
+
 }  // namespace tc

@@ -98,8 +98,10 @@ enum agrs_tuning_key {
   AGRS_TUNE_TC_KCHUNK = 3,      /* K elements accumulated in TMEM between round-to-nearest folds into C (0 = all of K; default 1024) */
   AGRS_TUNE_TC_2CTA = 4,        /* 1 (default): cta_group::2 pair kernel (256x256 tiles) when M > 128; 0: always the one-CTA kernel */
   AGRS_TUNE_TC_SPLITK = 5,      /* pair kernel: 0 (default) = pick the K split that fills the last wave of CTA pairs; n = force n splits */
-  AGRS_TUNE_TC_CROSS = 6        /* pair kernel, the two correction terms a_lo*b + a*b_lo: 0 = tf32 operands (3xTF32, ~1e-6), 1 / 2 = bf16
+  AGRS_TUNE_TC_CROSS = 6,       /* pair kernel, the two correction terms a_lo*b + a*b_lo: 0 = tf32 operands (3xTF32, ~1e-6), 1 / 2 = bf16
                                    operands at twice the MMA rate (SWIZZLE_64B / unswizzled tiles; ~3e-6).  Default: env AGRS_TC_CROSS, else 0 */
+  AGRS_TUNE_TC_EPI_TMA = 7      /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
+                                   folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
 AGRS_API int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value);
