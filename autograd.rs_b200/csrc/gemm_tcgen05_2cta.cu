@@ -30,10 +30,10 @@ constexpr int kSplitGroups = AGRS_SPLIT_GROUPS;  // groups of splitter warps tha
 constexpr int BN = 256;   // pair-tile width
 constexpr int BNH = 128;  // columns of B staged per CTA
 #ifndef AGRS_PAIR_RAW_STAGES
-#define AGRS_PAIR_RAW_STAGES 3
+#define AGRS_PAIR_RAW_STAGES 4
 #endif
 #ifndef AGRS_PAIR_LO_STAGES
-#define AGRS_PAIR_LO_STAGES 3
+#define AGRS_PAIR_LO_STAGES 2
 #endif
 constexpr int R = AGRS_PAIR_RAW_STAGES;  // raw (TMA) stages
 constexpr int L = AGRS_PAIR_LO_STAGES;   // lo (splitter) stages

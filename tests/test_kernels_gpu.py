@@ -1,6 +1,8 @@
 """GPU parity tests of the kernel-level C ABI (libagrs_b200.so) against the oracle.
 Bit-exact where the arithmetic is elementwise IEEE f32; tolerance (written per test) where a
 summation order or a transcendental differs.  Run with: pytest -m gpu (under gpurun)."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -299,7 +301,13 @@ def test_gemm_simt(ctx, M, N, Kd, ta, tb):
     assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_SIMT
 
 
-# ------------------------------------------------------------------ tcgen05 3xTF32 GEMMs (one-CTA and pair kernels, K splits)
+# ------------------------------------------------------------------ tcgen05 split GEMMs (one-CTA and pair kernels, K splits)
+def tuning(ctx, key):
+    v = ctypes.c_int64()
+    ctx.call("agrs_get_tuning", key, ctypes.byref(v))
+    return int(v.value)
+
+
 @pytest.mark.parametrize("M,N,Kd,ta,tb", [(256, 256, 32, 0, 1), (384, 1000, 520, 0, 1), (1000, 520, 3000, 1, 0), (200, 300, 100, 1, 1),
                                          (2048, 1024, 1024, 0, 0), (132, 260, 4100, 1, 1), (129, 8, 8, 0, 0), (4100, 132, 260, 1, 0)])
 @pytest.mark.parametrize("pair,splitk", [(0, 0), (1, 0), (1, 1), (1, 2), (1, 3)])
@@ -319,21 +327,43 @@ def test_gemm_tcgen05(ctx, M, N, Kd, ta, tb, pair, splitk):
 
 @pytest.mark.parametrize("M,N,Kd,ta,tb", [(256, 256, 32, 0, 1), (384, 1000, 520, 0, 1), (1000, 520, 3000, 1, 0), (200, 300, 100, 1, 1),
                                          (2048, 1024, 1024, 0, 0), (132, 260, 4100, 1, 1), (4100, 132, 260, 1, 0), (512, 384, 96, 0, 0)])
-@pytest.mark.parametrize("cross", [1, 2])
-@pytest.mark.parametrize("splitk", [0, 2])
-def test_gemm_pair_bf16_cross_terms(ctx, M, N, Kd, ta, tb, cross, splitk):
-    """pair kernel with the two correction terms on bf16 operands (AGRS_TUNE_TC_CROSS 1: 64-byte-swizzled tiles, 2: unswizzled):
-    same 2e-5 bar as the all-tf32 split, on every operand-major combination (the splitter warps transpose MN-major operands)"""
+@pytest.mark.parametrize("cross", [0, 1, 2])
+@pytest.mark.parametrize("splitk,epi_tma", [(0, 1), (2, 1), (0, 0), (2, 0)])
+def test_gemm_pair_cross_modes_and_epilogues(ctx, M, N, Kd, ta, tb, cross, splitk, epi_tma):
+    """pair kernel with the two correction terms on tf32 operands (AGRS_TUNE_TC_CROSS 0) or on bf16 operands (1: 64-byte-swizzled
+    tiles, the default; 2: unswizzled), with the staged TMA epilogue (tensor store + reduce-add across K chunks) and with the direct
+    one: same 2e-5 bar on every operand-major combination (the splitter warps transpose MN-major operands), ragged edges included"""
     rng = np.random.default_rng(M + 3 * N + 5 * Kd + cross)
+    default_cross = tuning(ctx, K.TUNE_TC_CROSS)
     ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, cross)
     ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, splitk)
+    ctx.call("agrs_set_tuning", K.TUNE_TC_EPI_TMA, epi_tma)
     try:
         for bias in (False, True):
             gemm_case(ctx, rng, M, N, Kd, ta, tb, bias, K.GEMM_TCGEN05, 2e-5)
             assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_TCGEN05
     finally:
-        ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, 0)
+        ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, default_cross)
         ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, 0)
+        ctx.call("agrs_set_tuning", K.TUNE_TC_EPI_TMA, 1)
+
+
+def test_gemm_pair_epilogues_agree_bitwise(ctx):
+    """the staged TMA epilogue (store, then reduce-add per K chunk in L2) and the direct one (read-modify-write from registers)
+    perform the same round-to-nearest f32 adds in the same order: identical bits, K chunks, bias and ragged edges included"""
+    rng = np.random.default_rng(99)
+    M, N, Kd = 700, 1000, 3000
+    A = rng.uniform(-1, 1, (M, Kd)).astype(np.float32)
+    B = rng.uniform(-1, 1, (Kd, N)).astype(np.float32)
+    bias = rng.uniform(-1, 1, N).astype(np.float32)
+    out = []
+    try:
+        for epi in (1, 0):
+            ctx.call("agrs_set_tuning", K.TUNE_TC_EPI_TMA, epi)
+            out.append(ctx.gemm(A, B, False, False, bias, K.GEMM_TCGEN05))
+    finally:
+        ctx.call("agrs_set_tuning", K.TUNE_TC_EPI_TMA, 1)
+    assert np.array_equal(out[0], out[1])
 
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
@@ -355,11 +385,12 @@ def test_gemm_pair_cross_terms_exact(ctx, ta, tb, cross, lo_side):
     assert np.array_equal(truth.astype(np.float32).astype(np.float64), truth)  # representable: the test is exact by construction
     A = np.ascontiguousarray(opA.T) if ta else opA
     B = np.ascontiguousarray(opB.T) if tb else opB
+    default_cross = tuning(ctx, K.TUNE_TC_CROSS)
     ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, cross)
     try:
         got = ctx.gemm(A, B, bool(ta), bool(tb), None, K.GEMM_TCGEN05)
     finally:
-        ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, 0)
+        ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, default_cross)
     assert np.array_equal(got.astype(np.float64), truth), float(np.abs(got - truth).max())
 
 
