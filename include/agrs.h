@@ -80,8 +80,10 @@ AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);     
  * transB=0: B is [K,N] (ldb>=N); transB=1: B is stored [N,K] (ldb>=K)   -- dX = G W^T (operators.rs:159)
  * so the reference's materialised t_clone() copies (storage.rs:84-88) never exist on the device.
  * bias != NULL fuses `+ b` of Linear::forward / Conv2D::forward (operators.rs:144, :379) into the epilogue.
- * Large aligned shapes run the TMA + tcgen05 3xTF32 kernel (f32-faithful: hi*hi + hi*lo + lo*hi; finite inputs: <= 1e-5 of
- * max|C|; NaN and zero propagate as in f32; an inf INPUT yields a non-finite result that may be NaN where f32 gives inf);
+ * Large aligned shapes run the TMA + tcgen05 split kernel (f32-faithful: x = hi + lo with hi the tf32 part; hi*hi on the tf32
+ * tensor pipe, the two correction terms lo*x + x*lo on bf16 operands by default; finite inputs: <= 1e-5 of max|C|; NaN and
+ * zero propagate as in f32; an inf INPUT yields a non-finite result that is NaN where f32 gives inf; sums folded across K
+ * chunks longer than AGRS_TUNE_TC_KCHUNK flush subnormal results to zero);
  * skinny outputs (N <= 32: the Conv2D lowering, Linear(3456,10)) run HBM-bound streaming kernels; everything else runs the
  * tiled SIMT f32 kernel.  All are CUDA; the choice never changes semantics. */
 AGRS_API int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
@@ -98,8 +100,9 @@ enum agrs_tuning_key {
   AGRS_TUNE_TC_KCHUNK = 3,      /* K elements accumulated in TMEM between round-to-nearest folds into C (0 = all of K; default 1024) */
   AGRS_TUNE_TC_2CTA = 4,        /* 1 (default): cta_group::2 pair kernel (256x256 tiles) when M > 128; 0: always the one-CTA kernel */
   AGRS_TUNE_TC_SPLITK = 5,      /* pair kernel: 0 (default) = pick the K split that fills the last wave of CTA pairs; n = force n splits */
-  AGRS_TUNE_TC_CROSS = 6,       /* pair kernel, the two correction terms a_lo*b + a*b_lo: 0 = tf32 operands (3xTF32, ~1e-6), 1 / 2 = bf16
-                                   operands at twice the MMA rate (SWIZZLE_64B / unswizzled tiles; ~3e-6).  Default: env AGRS_TC_CROSS, else 0 */
+  AGRS_TUNE_TC_CROSS = 6,       /* pair kernel, the two correction terms a_lo*b + a*b_lo: 0 = tf32 operands (3xTF32), 1 / 2 = bf16 operands
+                                   at twice the MMA rate (SWIZZLE_64B / unswizzled tiles); measured max error 9e-6 / 6e-6 of max|C|.
+                                   Default 1; env AGRS_TC_CROSS overrides it at context creation */
   AGRS_TUNE_TC_EPI_TMA = 7      /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
                                    folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
 };
