@@ -1,19 +1,20 @@
-// f32-faithful 3xTF32 GEMM, CTA-pair version: tcgen05.mma.cta_group::2 on a 256 x 256 pair tile.
+// f32-faithful split GEMM, CTA-pair version: tcgen05.mma.cta_group::2 on a 256 x 256 pair tile.
 //
 // Same contract as gemm_tcgen05.cu (Tensor::dot's CUDA arm, reference src/tensor/tensor.rs:319; the three GEMMs of
-// Linear::forward/backward, operators.rs:144,159,160) and the same numerics (hi = raw f32 container read by the tensor
-// core as tf32, lo = x - hi; a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulated in TMEM; K cut into chunks that the
-// epilogue folds into C with round-to-nearest adds).  What changes is the data flow, because the one-CTA kernel is
-// bound by shared-memory bandwidth and by its two-deep pipeline (profiles/r1_gemm_v1_ncu_full_summary.txt: tensor pipe
-// 47 % active):
+// Linear::forward/backward, operators.rs:144,159,160).  Numerics: hi = raw f32 container read by the tensor core as tf32,
+// lo = x - hi; a*b ~ a_lo*b + a*b_lo + a_hi*b_hi accumulated in TMEM, the two correction terms on bf16 operands
+// (template parameter CROSS = 1 / 2, the default) or on tf32 operands (CROSS = 0, "3xTF32"); K cut into chunks that the
+// epilogue folds into C with round-to-nearest adds.  Data flow (the one-CTA kernel is bound by shared-memory bandwidth and by
+// its two-deep pipeline, profiles/r1_gemm_v1_ncu_full_summary.txt: tensor pipe 47 % active):
 //   * a cluster of two CTAs (two SMs of one TPC) owns a 256 x 256 tile; each CTA stages 128 rows of A and 128 columns
 //     of B per 32-wide k-block, so every operand byte in shared memory feeds twice the math;
-//   * raw tiles (TMA) and lo tiles (splitter warps) live in separate rings: 4 raw stages cover the TMA latency, 3 lo
-//     stages cover the split, 224 KB of shared memory per CTA in total;
-//   * 8 splitter warps per CTA (two per scheduler) instead of 4.
+//   * raw f32 tiles (TMA) and lo / bf16 tiles (splitter warps) live in separate rings: 4 raw stages cover the TMA latency, 2
+//     splitter stages cover the split; with 32 KB of epilogue staging that is 224 KB of shared memory per CTA;
+//   * the epilogue hands 32 x 32 pieces to the TMA (tensor store, then reduce-add per later K chunk) instead of storing one row
+//     per lane from registers (see tma_store_3d).
 // Per CTA, 16 warps: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator,
 // warps 4-7 epilogue, warps 8-15 splitters.  Cross-CTA signalling: splitters and epilogue warps of both CTAs arrive on
-// the LEADER's mbarriers (release.cluster); the leader's tcgen05.commit multicasts to the same barrier in both CTAs.
+// the LEADER's mbarriers (CTA-scope release); the leader's tcgen05.commit multicasts to the same barrier in both CTAs.
 #include "tc_common.cuh"
 
 namespace tc2 {

@@ -11,7 +11,7 @@ minibatch rows sharded (weak scaling: 8192 rows per GPU), parameter gradients av
 One JSON line on stdout (rank 0):
   value      samples/s, whole job, inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks
   e2e        the same loop with X and T copied from pinned host memory every step and the loss read back every step
-  roofline   the dominant kernel (tcgen05 3xTF32 GEMM) timed live with CUDA-event pairs around every launch
+  roofline   the dominant kernel (tcgen05 split GEMM: tf32 hi*hi + bf16 correction terms) timed live with CUDA-event pairs around every launch
   cpu_baseline  the oracle (NumPy restatement of the reference's CPU path) on the host cores, bounded sample
 --impl reference times that CPU path alone (the Rust reference cannot be built here: no cargo/rustc in the image).
 """
