@@ -131,20 +131,24 @@ __device__ __forceinline__ float lo_of(float x) {
 constexpr uint32_t BF_TILE = BM * BK * 2;  // 8 KB
 static_assert(BM == BNH, "one splitter thread per row of A and per row of B");
 
+//   CROSS 3  "bf16x3": no tf32 pass at all -- x = x1 + x2 with x1 = bf16(x), x2 = bf16(x - x1); a*b ~ a2*b1 + a1*b2 + a1*b1, three
+//            bf16 MMAs = 6 slots per k-block instead of 8.  Same tiles as CROSS 1 (x2 in the lo tile, x1 in the x16 tile).
+//            Representation error ~4e-6 of max|C| instead of ~1e-6 (tools/split_numerics.py): opt-in.
 template <int CROSS>
 __device__ __forceinline__ uint32_t bf_chunk_offset(uint32_t row, uint32_t j) {
-  return CROSS == 1 ? row * 64u + ((j ^ ((row >> 1) & 3u)) << 4) : j * 2048u + row * 16u;
+  return CROSS != 2 ? row * 64u + ((j ^ ((row >> 1) & 3u)) << 4) : j * 2048u + row * 16u;
 }
 // descriptor of the i-th 16-wide K slice (kind::f16 UMMA_K) of a bf16 tile
 template <int CROSS>
 __device__ __forceinline__ uint64_t make_bf_desc(uint32_t tile, int i) {
-  const uint32_t addr = tile + (CROSS == 1 ? uint32_t(i) * 32u : uint32_t(i) * 4096u);
+  constexpr bool kSw64 = CROSS != 2;
+  const uint32_t addr = tile + (kSw64 ? uint32_t(i) * 32u : uint32_t(i) * 4096u);
   uint64_t d = 0;
   d |= uint64_t((addr & 0x3FFFF) >> 4);
-  d |= uint64_t(CROSS == 1 ? 1u : (2048u >> 4)) << 16;          // LBO: unused with a swizzle / next 16-byte chunk of K
-  d |= uint64_t(CROSS == 1 ? (512u >> 4) : (128u >> 4)) << 32;  // SBO: next 8 rows
+  d |= uint64_t(kSw64 ? 1u : (2048u >> 4)) << 16;          // LBO: unused with a swizzle / next 16-byte chunk of K
+  d |= uint64_t(kSw64 ? (512u >> 4) : (128u >> 4)) << 32;  // SBO: next 8 rows
   d |= uint64_t(1) << 46;
-  d |= uint64_t(CROSS == 1 ? 4 : 0) << 61;                      // SWIZZLE_64B / no swizzle
+  d |= uint64_t(kSw64 ? 4 : 0) << 61;                      // SWIZZLE_64B / no swizzle
   return d;
 }
 // D = f32, A = B = bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
@@ -188,8 +192,12 @@ __device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, ui
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const float e0 = v[8 * j + 2 * p], e1 = v[8 * j + 2 * p + 1];
-      lo[p] = pack_bf16(lo_of(e0), lo_of(e1));
       x[p] = pack_bf16(e0, e1);
+      if (CROSS == 3) {  // second bf16 term: what the first one left, exactly (a bf16 is the top half of an f32)
+        lo[p] = pack_bf16(e0 - __uint_as_float(x[p] << 16), e1 - __uint_as_float(x[p] & 0xFFFF0000u));
+      } else {
+        lo[p] = pack_bf16(lo_of(e0), lo_of(e1));
+      }
     }
     const uint32_t off = bf_chunk_offset<CROSS>(row, j);
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
@@ -349,11 +357,15 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 for (int i = 0; i < BK / 16; ++i) {  // cross terms first (they are the small ones), two 16-wide bf16 slices each
                   umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_lo, i), make_bf_desc<CROSS>(b_x, i), kIdescBf16, (first_kb && i == 0) ? 0u : 1u);
                   umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_x, i), make_bf_desc<CROSS>(b_lo, i), kIdescBf16, 1u);
+                  if constexpr (CROSS == 3)  // bf16x3: the leading term is bf16 too (x16 tiles hold x1 = bf16(x))
+                    umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_x, i), make_bf_desc<CROSS>(b_x, i), kIdescBf16, 1u);
                 }
+                if constexpr (CROSS != 3) {
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                  umma_tf32_2cta(d_tmem, make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>()),
-                                 make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>()), idesc, 1u);
+                  for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_tf32_2cta(d_tmem, make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>()),
+                                   make_smem_desc<B_MN>(b_hi + k * k_slice_bytes<B_MN>()), idesc, 1u);
+                }
               }
               umma_commit_pair(raw_free(r));  // both CTAs may refill this raw stage ...
               umma_commit_pair(lo_free(l));   // ... and this lo stage once the MMAs above have read them
@@ -668,7 +680,9 @@ static int gemm_tc_2cta_impl(agrs_ctx* ctx, int transA, int transB, int64_t M, i
 #define AGRS_PAIR_X(AM, BMJ, X)                                                                                     \
   (sc ? tc2::launch<AM, BMJ, true, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc)                                  \
       : tc2::launch<AM, BMJ, false, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none))
-#define AGRS_PAIR(AM, BMJ) (ctx->tc_cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : ctx->tc_cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) : AGRS_PAIR_X(AM, BMJ, 0))
+#define AGRS_PAIR(AM, BMJ)                                                                      \
+  (ctx->tc_cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : ctx->tc_cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) \
+   : ctx->tc_cross == 3 ? AGRS_PAIR_X(AM, BMJ, 3) : AGRS_PAIR_X(AM, BMJ, 0))
   if (A_MN && B_MN) return AGRS_PAIR(true, true);
   if (A_MN) return AGRS_PAIR(true, false);
   if (B_MN) return AGRS_PAIR(false, true);

@@ -395,7 +395,7 @@ def run_b200_arm(args, cfg):
     #   cross > 0: one tf32 MMA + two bf16 MMAs (1/2 slot each) -> 2 tf32 slots, peak = bf16/4
     # The GEMMs run inside a long step -> sustained figure.
     cross = dev.get_tuning(_capi.TUNE_TC_CROSS)
-    slots = 3.0 if cross == 0 else 2.0
+    slots = {0: 3.0, 3: 1.5}.get(cross, 2.0)  # cross = 3: three bf16 MMAs, no tf32 pass
     peak_alg = peaks["bf16_sustained"] / 2.0 / slots
     roofline = None
     if g_n:
@@ -409,11 +409,12 @@ def run_b200_arm(args, cfg):
                 traffic = None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak_alg, "unit": "TFLOP/s", "frac": ach / peak_alg, "traffic": traffic,
                     "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2: " +
-                              ("kind::tf32 x3)" if cross == 0 else f"kind::tf32 hi*hi + 2 x kind::f16 bf16 cross terms, tile layout {cross})"),
+                              ("kind::tf32 x3)" if cross == 0 else "3 x kind::f16 on bf16 pairs x1 + x2)" if cross == 3 else
+                               f"kind::tf32 hi*hi + 2 x kind::f16 bf16 cross terms, tile layout {cross})"),
                     "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_equivalent_tflops": slots * ach,
                     "gemm_share_of_step": g_ms / ms, "cross_terms": "tf32" if cross == 0 else "bf16",
-                    "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / {slots:.0f} (tf32-rate MMA slots per product)"}
+                    "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / {slots:g} (tf32-rate MMA slots per product)"}
         # context: what cuBLAS itself reaches on this pool's B200s for PLAIN tf32 (one MMA per product) -- tools/tf32_cublas_peak.py
         cub = os.path.join(ROOT, "profiles", "r1_cublas_peaks.json")
         if os.path.exists(cub):

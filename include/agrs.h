@@ -102,7 +102,8 @@ enum agrs_tuning_key {
   AGRS_TUNE_TC_SPLITK = 5,      /* pair kernel: 0 (default) = pick the K split that fills the last wave of CTA pairs; n = force n splits */
   AGRS_TUNE_TC_CROSS = 6,       /* pair kernel, the two correction terms a_lo*b + a*b_lo: 0 = tf32 operands (3xTF32), 1 / 2 = bf16 operands
                                    at twice the MMA rate (SWIZZLE_64B / unswizzled tiles); measured max error 9e-6 / 6e-6 of max|C|.
-                                   Default 1; env AGRS_TC_CROSS overrides it at context creation */
+                                   3 = no tf32 pass: x = bf16 + bf16, three bf16 products (6 MMA slots per k-block instead of 8,
+                                   representation error ~4e-6 instead of ~1e-6).  Default 1; env AGRS_TC_CROSS overrides it at context creation */
   AGRS_TUNE_TC_EPI_TMA = 7      /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
                                    folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
 };
