@@ -36,7 +36,7 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
       ctx->tc_2cta = value ? 1 : 0;
       return AGRS_OK;
     case AGRS_TUNE_TC_CROSS:
-      AGRS_REQUIRE(ctx, value >= 0 && value <= 3, AGRS_ERR_INVALID, "AGRS_TUNE_TC_CROSS must be 0, 1, 2 or 3");
+      AGRS_REQUIRE(ctx, value >= 0 && value <= 4, AGRS_ERR_INVALID, "AGRS_TUNE_TC_CROSS must be 0 .. 4");
       ctx->tc_cross = int(value);
       return AGRS_OK;
     case AGRS_TUNE_TC_EPI_TMA:

@@ -167,11 +167,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float e0, float e1) {  // e0 at th
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
   return r;
 }
-// One row (32 k) of a raw f32 operand tile -> the same row of its two bf16 tiles.
+__device__ __forceinline__ uint32_t pack_f16(float e0, float e1) {  // e0 at the lower address
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+  return r;
+}
+__device__ __forceinline__ void unpack_f16(uint32_t p, float& e0, float& e1) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(e0), "=f"(e1) : "r"(p));
+}
+// One row (32 k) of a raw f32 operand tile -> the same row of its two 16-bit tiles (`mult`: the row's scale, CROSS 4 only).
 //   raw K-major  tile: [128 rows][128 B], SWIZZLE_128B: 16-byte chunk c of row r sits in slot c ^ (r & 7)
 //   raw MN-major tile: 4 blocks of [32 k][32 rows], SWIZZLE_128B_ATOM_32B: 32-byte chunk c of k-line k sits in slot c ^ (k & 3)
 template <bool MN_MAJOR, int CROSS>
-__device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, uint32_t out_x, uint32_t row) {
+__device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, uint32_t out_x, uint32_t row, float mult) {
   float v[BK];
   if (MN_MAJOR) {
     const uint32_t base = raw + (row >> 5) * 4096u + (row & 7u) * 4u, c = (row & 31u) >> 3;
@@ -192,6 +200,14 @@ __device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, ui
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const float e0 = v[8 * j + 2 * p], e1 = v[8 * j + 2 * p + 1];
+      if (CROSS == 4) {  // fp16 pair of the scaled value: h = fp16(x'), l = fp16(x' - h)
+        const float s0 = e0 * mult, s1 = e1 * mult;
+        float h0, h1;
+        x[p] = pack_f16(s0, s1);
+        unpack_f16(x[p], h0, h1);
+        lo[p] = pack_f16(s0 - h0, s1 - h1);
+        continue;
+      }
       x[p] = pack_bf16(e0, e1);
       if (CROSS == 3) {  // second bf16 term: what the first one left, exactly (a bf16 is the top half of an f32)
         lo[p] = pack_bf16(e0 - __uint_as_float(x[p] << 16), e1 - __uint_as_float(x[p] & 0xFFFF0000u));
@@ -203,6 +219,85 @@ __device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, ui
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_x + off), "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]) : "memory");
   }
+}
+
+// ---- CROSS 4: "fp16x3" with operand scaling ---------------------------------------------------------------------------------
+// fp16 has tf32's 11 significant bits at twice the MMA rate but only 5 exponent bits.  The range comes from an exact power-of-two
+// scale per row of op(A) and per column of op(B): the row's largest magnitude is brought into [2^13, 2^14), after which
+// x' = h + l with h = fp16(x'), l = fp16(x' - h) carries 22 bits, and a*b ~ l_a*h_b + h_a*l_b + h_a*h_b is three fp16 MMAs
+// (6 slots per k-block, like bf16x3) with a representation error of 7e-8 of max|C| (tools/split_numerics.py).  The epilogue
+// undoes the two scales (exact).  Two small kernels find the magnitudes first: k_absmax_rows / k_absmax_cols write, per row or
+// column, the largest |x| as its bit pattern (unsigned compare == float compare for magnitudes; NaN sorts above inf and so
+// propagates).  Tiles: h in the x16 slot, l in the lo slot, layout of CROSS 1.
+__device__ __forceinline__ void scale_of_max(uint32_t max_bits, float& mult, float& inv) {
+  uint32_t e = max_bits >> 23;            // biased exponent of the largest magnitude
+  e = e < 14u ? 14u : (e > 254u ? 254u : e);
+  mult = __uint_as_float((267u - e) << 23);  // 2^(140 - e): max * mult in [2^13, 2^14)
+  inv = __uint_as_float((e - 13u) << 23);    // 2^(e - 140)
+}
+constexpr uint32_t kIdescF16 = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);  // D f32, A = B = fp16, K-major
+// epilogue side: undo the scales on the 32 accumulators a thread holds (one row, columns col0 .. col0+31)
+__device__ __forceinline__ void unscale_piece(uint32_t (&v)[32], float inv_a, const uint32_t* __restrict__ b_max, int64_t col0, int64_t N) {
+  if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(b_max + col0) & 15u) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(b_max + col0) + j);
+      float mu, i0, i1, i2, i3;
+      scale_of_max(m.x, mu, i0);
+      scale_of_max(m.y, mu, i1);
+      scale_of_max(m.z, mu, i2);
+      scale_of_max(m.w, mu, i3);
+      v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) * inv_a * i0);
+      v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) * inv_a * i1);
+      v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) * inv_a * i2);
+      v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) * inv_a * i3);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float mu, ib;
+      scale_of_max(col0 + j < N ? __ldg(b_max + col0 + j) : 0u, mu, ib);
+      v[j] = __float_as_uint(__uint_as_float(v[j]) * inv_a * ib);
+    }
+  }
+}
+
+// out[r] = max_c |X[r*ld + c]| as bits; one block per row
+__global__ void __launch_bounds__(256) k_absmax_rows(const float* __restrict__ X, int64_t rows, int64_t cols, int64_t ld, uint32_t* __restrict__ out) {
+  __shared__ uint32_t part[8];
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* row = X + r * ld;
+    uint32_t m = 0;
+    if ((ld & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0) {
+      for (int64_t c = threadIdx.x * 4; c + 3 < cols; c += 1024) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + c));
+        m = max(max(m, v.x & 0x7FFFFFFFu), max(max(v.y & 0x7FFFFFFFu, v.z & 0x7FFFFFFFu), v.w & 0x7FFFFFFFu));
+      }
+      for (int64_t c = (cols & ~int64_t(3)) + threadIdx.x; c < cols; c += 256) m = max(m, __float_as_uint(__ldg(row + c)) & 0x7FFFFFFFu);
+    } else {
+      for (int64_t c = threadIdx.x; c < cols; c += 256) m = max(m, __float_as_uint(__ldg(row + c)) & 0x7FFFFFFFu);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w) m = max(m, part[w]);
+      out[r] = m;
+    }
+    __syncthreads();
+  }
+}
+// out[c] = max_r |X[r*ld + c]| as bits (out zeroed beforehand); blockIdx.x: 256-column strip, blockIdx.y: slab of rows
+__global__ void __launch_bounds__(256) k_absmax_cols(const float* __restrict__ X, int64_t rows, int64_t cols, int64_t ld, int64_t slab,
+                                                     uint32_t* __restrict__ out) {
+  const int64_t c = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t r0 = int64_t(blockIdx.y) * slab, r1 = r0 + slab < rows ? r0 + slab : rows;
+  uint32_t m = 0;
+  for (int64_t r = r0; r < r1; ++r) m = max(m, __float_as_uint(__ldg(X + r * ld + c)) & 0x7FFFFFFFu);
+  atomicMax(out + c, m);  // a maximum does not depend on the order: deterministic
 }
 
 // GEMM -> reduce-scatter (data-parallel weight gradients, csrc/fused_dp.cu): with SCATTER the epilogue also pushes every finished
@@ -222,7 +317,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C, int64_t ldc,
                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
                    const __grid_constant__ ScatterArgs sc, const __grid_constant__ CUtensorMap tmap_c,
-                   const __grid_constant__ CUtensorMap tmap_w, int epi_tma) {
+                   const __grid_constant__ CUtensorMap tmap_w, int epi_tma, const uint32_t* __restrict__ a_max,
+                   const uint32_t* __restrict__ b_max) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
@@ -353,14 +449,15 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               } else {
                 // lo stage: [A lo | A x16 | B lo | B x16], 8 KB each, K-major bf16
                 const uint32_t a_lo = lo_base + l * RAW_BYTES, a_x = a_lo + BF_TILE, b_lo = a_x + BF_TILE, b_x = b_lo + BF_TILE;
+                constexpr uint32_t idesc16 = CROSS == 4 ? kIdescF16 : kIdescBf16;
 #pragma unroll
-                for (int i = 0; i < BK / 16; ++i) {  // cross terms first (they are the small ones), two 16-wide bf16 slices each
-                  umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_lo, i), make_bf_desc<CROSS>(b_x, i), kIdescBf16, (first_kb && i == 0) ? 0u : 1u);
-                  umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_x, i), make_bf_desc<CROSS>(b_lo, i), kIdescBf16, 1u);
-                  if constexpr (CROSS == 3)  // bf16x3: the leading term is bf16 too (x16 tiles hold x1 = bf16(x))
-                    umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_x, i), make_bf_desc<CROSS>(b_x, i), kIdescBf16, 1u);
+                for (int i = 0; i < BK / 16; ++i) {  // cross terms first (they are the small ones), two 16-wide slices each
+                  umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_lo, i), make_bf_desc<CROSS>(b_x, i), idesc16, (first_kb && i == 0) ? 0u : 1u);
+                  umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_x, i), make_bf_desc<CROSS>(b_lo, i), idesc16, 1u);
+                  if constexpr (CROSS >= 3)  // bf16x3 / fp16x3: the leading term is 16-bit too (x16 tiles hold the first piece)
+                    umma_bf16_2cta(d_tmem, make_bf_desc<CROSS>(a_x, i), make_bf_desc<CROSS>(b_x, i), idesc16, 1u);
                 }
-                if constexpr (CROSS != 3) {
+                if constexpr (CROSS < 3) {
 #pragma unroll
                   for (int k = 0; k < BK / UMMA_K; ++k)
                     umma_tf32_2cta(d_tmem, make_smem_desc<A_MN>(a_hi + k * k_slice_bytes<A_MN>()),
@@ -391,8 +488,22 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     constexpr int kPerThread = RAW_BYTES / (kGroupWarps * 32 * 16);  // float4 per thread per stage
     constexpr uint32_t kStride = kGroupWarps * 32 * 16;
     uint32_t it = 0;  // k-blocks since kernel start: ring positions are it % R and it % L
+    constexpr int kItems = CROSS == 0 ? 1 : (2 * BM) / (kGroupWarps * 32);  // operand rows per splitter thread and k-block
     for (int64_t t = pair; t < num_tiles; t += num_pairs) {
       const Work w = work_item(t);
+      float mult[kItems];
+#pragma unroll
+      for (int i = 0; i < kItems; ++i) mult[i] = 1.f;
+      if constexpr (CROSS == 4) {  // the scales of this thread's rows of A and of B for this tile
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) {
+          const int item = tid + i * kGroupWarps * 32;
+          const int64_t g = item < BM ? w.mb * 2 * BM + rank * BM + item : w.nb * BN + rank * BNH + (item - BM);
+          const uint32_t bits = item < BM ? (g < M ? __ldg(a_max + g) : 0u) : (g < N ? __ldg(b_max + g) : 0u);
+          float inv;
+          scale_of_max(bits, mult[i], inv);
+        }
+      }
       for (int kb = w.kb0; kb < w.kb1; ++kb, ++it) {
         if (int(it % kSplitGroups) != grp) continue;
         const uint32_t r = it % R, rph = (it / R) & 1u, l = it % L, lph = (it / L) & 1u;
@@ -416,10 +527,11 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           static_assert((2 * BM) % (kGroupWarps * 32) == 0 && kGroupWarps * 32 <= 2 * BM, "bf16 cross terms: whole rows per splitter thread");
           const uint32_t raw = smem_base + r * RAW_BYTES, out = lo_base + l * RAW_BYTES;
 #pragma unroll
-          for (int item = tid; item < 2 * BM; item += kGroupWarps * 32) {
+          for (int i = 0; i < kItems; ++i) {
+            const int item = tid + i * kGroupWarps * 32;
             const uint32_t row = uint32_t(item) & uint32_t(BM - 1);
-            if (item < BM) split_row_bf16<A_MN, CROSS>(raw, out, out + BF_TILE, row);
-            else           split_row_bf16<B_MN, CROSS>(raw + A_BYTES, out + 2 * BF_TILE, out + 3 * BF_TILE, row);
+            if (item < BM) split_row_bf16<A_MN, CROSS>(raw, out, out + BF_TILE, row, mult[i]);
+            else           split_row_bf16<B_MN, CROSS>(raw + A_BYTES, out + 2 * BF_TILE, out + 3 * BF_TILE, row, mult[i]);
           }
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -446,6 +558,11 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const CUtensorMap* const cmap = w.split == 0 ? &tmap_c : &tmap_w;
         const int32_t plane = w.split == 0 ? 0 : w.split - 1;
         const float* const bias_s = w.split == 0 ? bias : nullptr;
+        float inv_a = 1.f;
+        if constexpr (CROSS == 4) {
+          float mu;
+          scale_of_max(row0 + lane < M ? __ldg(a_max + row0 + lane) : 0u, mu, inv_a);
+        }
         for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
           mbar_wait(tfull_bar(acc), acc_ph);
           tc_fence_after();
@@ -459,6 +576,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tmem_wait_ld();
             const int64_t col0 = w.nb * BN + c * 32;
             if (row0 < M && col0 < N) {  // warp-uniform; rows and columns past the edge are clipped by the tensor map
+              if constexpr (CROSS == 4) unscale_piece(v, inv_a, b_max, col0, N);
               if (ch == 0 && bias_s) {
                 if (col0 + 32 <= N) {
 #pragma unroll
@@ -510,6 +628,11 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int64_t lds = w.split == 0 ? ldc : N;
       const float* const bias_s = w.split == 0 ? bias : nullptr;
       const bool vec_s = w.split == 0 ? vec_ok : vec_w;
+      float inv_a = 1.f;
+      if constexpr (CROSS == 4) {
+        float mu;
+        scale_of_max(row < M ? __ldg(a_max + row) : 0u, mu, inv_a);
+      }
       for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
@@ -521,6 +644,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tmem_wait_ld();
           const int64_t col0 = nb * BN + c * 32;
           if (row < M && col0 < N) {
+            if constexpr (CROSS == 4) unscale_piece(v, inv_a, b_max, col0, N);
             float* dst = Cs + row * lds + col0;
             float* push = nullptr;  // where the finished piece also goes: this rank's slot at the piece's owner
             if (SCATTER && c0 + kb_per_chunk >= w.kb1) {
@@ -621,7 +745,7 @@ static int choose_splits(int64_t tiles, int64_t pairs, int64_t num_kb, int force
 
 template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
 static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
-                  int64_t N, int64_t K, int kb_per_chunk, const ScatterArgs& sc) {
+                  int64_t N, int64_t K, int kb_per_chunk, const ScatterArgs& sc, const float* A, int64_t lda, const float* B, int64_t ldb) {
   auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN, SCATTER, CROSS>;
   AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
@@ -632,11 +756,37 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     const int64_t kps = (num_kb + splits - 1) / splits;
     splits = int((num_kb + kps - 1) / kps);
   }
+  // workspace = [row magnitudes of op(A) | column magnitudes of op(B)] (CROSS 4 only) followed by the split-K partial planes
+  const size_t a_slots = (size_t(M) + 63) / 64 * 64, b_slots = (size_t(N) + 63) / 64 * 64;
+  const size_t scale_bytes = CROSS == 4 ? (a_slots + b_slots) * sizeof(uint32_t) : 0;
+  const size_t part_bytes = splits > 1 ? size_t(splits - 1) * size_t(M) * size_t(N) * sizeof(float) : 0;
   float* Cw = nullptr;
-  if (splits > 1) {
-    int rc = agrs_ensure_workspace(ctx, size_t(splits - 1) * size_t(M) * size_t(N) * sizeof(float));
+  uint32_t *a_max = nullptr, *b_max = nullptr;
+  if (scale_bytes + part_bytes) {
+    int rc = agrs_ensure_workspace(ctx, scale_bytes + part_bytes);
     if (rc) return rc;
-    Cw = ctx->workspace;
+    Cw = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->workspace) + scale_bytes);
+  }
+  if (CROSS == 4) {
+    a_max = reinterpret_cast<uint32_t*>(ctx->workspace);
+    b_max = a_max + a_slots;
+    // op(A) row m: a row of A stored [M, K], a column of A stored [K, M]; op(B) column n: a column of B stored [K, N], a row of [N, K]
+    auto absmax = [&](const float* X, bool along_columns, int64_t vecs, int64_t ld, uint32_t* out) -> int {
+      if (along_columns) {  // X is [K rows][vecs columns]
+        AGRS_CUDA(ctx, cudaMemsetAsync(out, 0, size_t(vecs) * sizeof(uint32_t), ctx->stream));
+        const int64_t slab = 32;
+        dim3 grid(unsigned((vecs + 255) / 256), unsigned((K + slab - 1) / slab));
+        k_absmax_cols<<<grid, 256, 0, ctx->stream>>>(X, K, vecs, ld, slab, out);
+      } else {              // X is [vecs rows][K columns]
+        const int64_t cap = int64_t(ctx->sm_count) * 16;
+        k_absmax_rows<<<unsigned(vecs < cap ? vecs : cap), 256, 0, ctx->stream>>>(X, vecs, K, ld, out);
+      }
+      AGRS_LAUNCHED(ctx);
+      return AGRS_OK;
+    };
+    int rc = absmax(A, A_MN, M, lda, a_max);
+    if (!rc) rc = absmax(B, B_MN, N, ldb, b_max);
+    if (rc) return rc;
   }
   // staged TMA epilogue: C (and the split workspace) must be describable by a tensor map -- 16-byte aligned base and row pitch
   CUtensorMap tc_map = ta, tw_map = ta;  // placeholders when unused
@@ -649,7 +799,7 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   }
   const int64_t items = tiles * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma);
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max);
   AGRS_LAUNCHED(ctx);
   if (splits > 1) {
     const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
@@ -678,11 +828,11 @@ static int gemm_tc_2cta_impl(agrs_ctx* ctx, int transA, int transB, int64_t M, i
   const int kpc = ctx->tc_kchunk > 0 ? int((ctx->tc_kchunk + tc::BK - 1) / tc::BK) : int(num_kb);
   static const tc2::ScatterArgs none{};
 #define AGRS_PAIR_X(AM, BMJ, X)                                                                                     \
-  (sc ? tc2::launch<AM, BMJ, true, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc)                                  \
-      : tc2::launch<AM, BMJ, false, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none))
+  (sc ? tc2::launch<AM, BMJ, true, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc, A, lda, B, ldb)                  \
+      : tc2::launch<AM, BMJ, false, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none, A, lda, B, ldb))
 #define AGRS_PAIR(AM, BMJ)                                                                      \
   (ctx->tc_cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : ctx->tc_cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) \
-   : ctx->tc_cross == 3 ? AGRS_PAIR_X(AM, BMJ, 3) : AGRS_PAIR_X(AM, BMJ, 0))
+   : ctx->tc_cross == 3 ? AGRS_PAIR_X(AM, BMJ, 3) : ctx->tc_cross == 4 ? AGRS_PAIR_X(AM, BMJ, 4) : AGRS_PAIR_X(AM, BMJ, 0))
   if (A_MN && B_MN) return AGRS_PAIR(true, true);
   if (A_MN) return AGRS_PAIR(true, false);
   if (B_MN) return AGRS_PAIR(false, true);

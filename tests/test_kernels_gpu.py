@@ -327,7 +327,7 @@ def test_gemm_tcgen05(ctx, M, N, Kd, ta, tb, pair, splitk):
 
 @pytest.mark.parametrize("M,N,Kd,ta,tb", [(256, 256, 32, 0, 1), (384, 1000, 520, 0, 1), (1000, 520, 3000, 1, 0), (200, 300, 100, 1, 1),
                                          (2048, 1024, 1024, 0, 0), (132, 260, 4100, 1, 1), (4100, 132, 260, 1, 0), (512, 384, 96, 0, 0)])
-@pytest.mark.parametrize("cross", [0, 1, 2, 3])
+@pytest.mark.parametrize("cross", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("splitk,epi_tma", [(0, 1), (2, 1), (0, 0), (2, 0)])
 def test_gemm_pair_cross_modes_and_epilogues(ctx, M, N, Kd, ta, tb, cross, splitk, epi_tma):
     """pair kernel with the two correction terms on tf32 operands (AGRS_TUNE_TC_CROSS 0) or on bf16 operands (1: 64-byte-swizzled
@@ -367,7 +367,7 @@ def test_gemm_pair_epilogues_agree_bitwise(ctx):
 
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("cross", [0, 1, 2, 3])
+@pytest.mark.parametrize("cross", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("lo_side", ["a", "b"])
 def test_gemm_pair_cross_terms_exact(ctx, ta, tb, cross, lo_side):
     """Known-answer test of the split itself.  One operand is s * (1 + c * 2^-12) with s in {+-1, +-2}, c in 0..3: its tf32 part is
