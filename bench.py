@@ -395,7 +395,7 @@ def run_b200_arm(args, cfg):
     #   cross > 0: one tf32 MMA + two bf16 MMAs (1/2 slot each) -> 2 tf32 slots, peak = bf16/4
     # The GEMMs run inside a long step -> sustained figure.
     cross = dev.get_tuning(_capi.TUNE_TC_CROSS)
-    slots = {0: 3.0, 3: 1.5}.get(cross, 2.0)  # cross = 3: three bf16 MMAs, no tf32 pass
+    slots = {0: 3.0, 3: 1.5, 4: 1.5}.get(cross, 2.0)  # cross = 3 / 4: three bf16 / fp16 MMAs, no tf32 pass
     peak_alg = peaks["bf16_sustained"] / 2.0 / slots
     roofline = None
     if g_n:
@@ -410,6 +410,7 @@ def run_b200_arm(args, cfg):
         roofline = {"bound": "tensor", "achieved": ach, "peak": peak_alg, "unit": "TFLOP/s", "frac": ach / peak_alg, "traffic": traffic,
                     "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2: " +
                               ("kind::tf32 x3)" if cross == 0 else "3 x kind::f16 on bf16 pairs x1 + x2)" if cross == 3 else
+                               "3 x kind::f16 on scaled fp16 pairs h + l, plus two absmax kernels per launch)" if cross == 4 else
                                f"kind::tf32 hi*hi + 2 x kind::f16 bf16 cross terms, tile layout {cross})"),
                     "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_equivalent_tflops": slots * ach,

@@ -103,7 +103,9 @@ enum agrs_tuning_key {
   AGRS_TUNE_TC_CROSS = 6,       /* pair kernel, the two correction terms a_lo*b + a*b_lo: 0 = tf32 operands (3xTF32), 1 / 2 = bf16 operands
                                    at twice the MMA rate (SWIZZLE_64B / unswizzled tiles); measured max error 9e-6 / 6e-6 of max|C|.
                                    3 = no tf32 pass: x = bf16 + bf16, three bf16 products (6 MMA slots per k-block instead of 8,
-                                   representation error ~4e-6 instead of ~1e-6).  Default 1; env AGRS_TC_CROSS overrides it at context creation */
+                                   representation error ~4e-6 instead of ~1e-6).  4 = x scaled per row of op(A) / column of op(B) by an
+                                   exact power of two, then fp16 + fp16: three fp16 products, representation error ~7e-8, preceded by two
+                                   small absmax kernels per launch.  Default 1; env AGRS_TC_CROSS overrides it at context creation */
   AGRS_TUNE_TC_EPI_TMA = 7      /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
                                    folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
 };

@@ -331,7 +331,8 @@ def test_gemm_tcgen05(ctx, M, N, Kd, ta, tb, pair, splitk):
 @pytest.mark.parametrize("splitk,epi_tma", [(0, 1), (2, 1), (0, 0), (2, 0)])
 def test_gemm_pair_cross_modes_and_epilogues(ctx, M, N, Kd, ta, tb, cross, splitk, epi_tma):
     """pair kernel with the two correction terms on tf32 operands (AGRS_TUNE_TC_CROSS 0) or on bf16 operands (1: 64-byte-swizzled
-    tiles, the default; 2: unswizzled), with the staged TMA epilogue (tensor store + reduce-add across K chunks) and with the direct
+    tiles, the default; 2: unswizzled), as three bf16 products (3) or three fp16 products of row/column-scaled operands (4),
+    with the staged TMA epilogue (tensor store + reduce-add across K chunks) and with the direct
     one: same 2e-5 bar on every operand-major combination (the splitter warps transpose MN-major operands), ragged edges included"""
     rng = np.random.default_rng(M + 3 * N + 5 * Kd + cross)
     default_cross = tuning(ctx, K.TUNE_TC_CROSS)
