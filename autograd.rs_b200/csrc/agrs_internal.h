@@ -29,6 +29,7 @@ struct agrs_ctx {
   int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
   int tc_cross = 1;        // pair kernel correction terms: 0 tf32, 1 bf16 (SWIZZLE_64B tiles), 2 bf16 (unswizzled tiles)
   int tc_epi_tma = 1;      // pair kernel epilogue: 1 staged in shared memory + TMA store / reduce-add, 0 direct st.global from registers
+  int tc_reuse_scales = 0; // cross mode 4, measurement aid: 1 = reuse the operand magnitudes of the previous launch (same operands only)
   int64_t tc_min_flops = 1LL << 24;  // AUTO path: below this many MACs the SIMT kernel wins on launch+fill latency
   // small scratch for reductions (block partials + completion counter), allocated once
   float* scratch = nullptr;

@@ -42,6 +42,9 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
     case AGRS_TUNE_TC_EPI_TMA:
       ctx->tc_epi_tma = value ? 1 : 0;
       return AGRS_OK;
+    case AGRS_TUNE_TC_REUSE_SCALES:
+      ctx->tc_reuse_scales = value ? 1 : 0;
+      return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS:
       ctx->tc_min_flops = value;
       return AGRS_OK;
@@ -60,6 +63,7 @@ int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value) {
     case AGRS_TUNE_TC_2CTA: *value = ctx->tc_2cta; return AGRS_OK;
     case AGRS_TUNE_TC_CROSS: *value = ctx->tc_cross; return AGRS_OK;
     case AGRS_TUNE_TC_EPI_TMA: *value = ctx->tc_epi_tma; return AGRS_OK;
+    case AGRS_TUNE_TC_REUSE_SCALES: *value = ctx->tc_reuse_scales; return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS: *value = ctx->tc_min_flops; return AGRS_OK;
   }
   return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown tuning key %d", key);

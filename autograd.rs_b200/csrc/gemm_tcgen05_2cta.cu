@@ -784,8 +784,9 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
       AGRS_LAUNCHED(ctx);
       return AGRS_OK;
     };
-    int rc = absmax(A, A_MN, M, lda, a_max);
-    if (!rc) rc = absmax(B, B_MN, N, ldb, b_max);
+    // measurement aid (AGRS_TUNE_TC_REUSE_SCALES): skip the two passes and use what the previous launch left in the workspace
+    int rc = ctx->tc_reuse_scales ? AGRS_OK : absmax(A, A_MN, M, lda, a_max);
+    if (!rc && !ctx->tc_reuse_scales) rc = absmax(B, B_MN, N, ldb, b_max);
     if (rc) return rc;
   }
   // staged TMA epilogue: C (and the split workspace) must be describable by a tensor map -- 16-byte aligned base and row pitch

@@ -106,8 +106,10 @@ enum agrs_tuning_key {
                                    representation error ~4e-6 instead of ~1e-6).  4 = x scaled per row of op(A) / column of op(B) by an
                                    exact power of two, then fp16 + fp16: three fp16 products, representation error ~7e-8, preceded by two
                                    small absmax kernels per launch.  Default 1; env AGRS_TC_CROSS overrides it at context creation */
-  AGRS_TUNE_TC_EPI_TMA = 7      /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
+  AGRS_TUNE_TC_EPI_TMA = 7,     /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
                                    folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
+  AGRS_TUNE_TC_REUSE_SCALES = 8 /* cross mode 4, measurement aid: 1 = skip the absmax kernels and reuse the operand magnitudes the previous
+                                   launch left in the workspace -- only meaningful when the operands have not changed.  Default 0 */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
 AGRS_API int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value);

@@ -14,6 +14,9 @@ import autograd_rs_b200  # noqa: F401,E402
 from autograd_rs_b200 import _capi  # noqa: E402
 
 
+REUSE_SCALES = False
+
+
 def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias=False, splitk=0):
     A = rng.uniform(-1, 1, (K, M) if ta else (M, K)).astype(np.float32)
     B = rng.uniform(-1, 1, (N, K) if tb else (K, N)).astype(np.float32)
@@ -48,6 +51,16 @@ def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias
         ctx.call("agrs_timer_end", C.byref(ms))
         res["ms"] = ms.value / iters
         res["tflops"] = 2.0 * M * N * K / (res["ms"] * 1e-3) / 1e12
+        if REUSE_SCALES:  # cross mode 4 without its absmax passes: the magnitudes of the launches above are still in the workspace
+            ctx.call("agrs_set_tuning", _capi.TUNE_TC_REUSE_SCALES, 1)
+            ctx.call("agrs_timer_begin")
+            for _ in range(iters):
+                ctx.call("agrs_gemm_f32", *args)
+            ctx.call("agrs_timer_end", C.byref(ms))
+            ctx.call("agrs_set_tuning", _capi.TUNE_TC_REUSE_SCALES, 0)
+            res["ms_reused_scales"] = ms.value / iters
+            res["tflops_reused_scales"] = 2.0 * M * N * K / (res["ms_reused_scales"] * 1e-3) / 1e12
+            res["rel_err_reused_scales_vs_first"] = float(np.abs(ctx.to_host(dC, (M, N)) - got).max() / max(np.abs(got).max(), 1e-30))
     ctx.call("agrs_set_gemm_path", _capi.GEMM_AUTO)
     return res
 
@@ -58,12 +71,15 @@ def main():
     ap.add_argument("--sizes", default="256,512,1024,2048,4096,8192")
     ap.add_argument("--linear", action="store_true", help="also the Linear fwd/dX/dW shapes of C2 (8192x4096x4096) and C5 (8192x8192x8192)")
     ap.add_argument("--linear-c2", action="store_true", help="only the three Linear shapes of C2")
+    ap.add_argument("--reuse-scales", action="store_true", help="cross mode 4: also time the kernel without its absmax passes")
     ap.add_argument("--odd", action="store_true", help="ragged shapes (partial tiles in M, N and K)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kchunk", type=int, default=1024)
     ap.add_argument("--splitk", default="0", help="comma list of forced K splits for the pair kernel (0 = automatic)")
     ap.add_argument("--majors", default="00,01,10", help="ta tb pairs for the square sizes: 00 = X.W, 01 = G.W^T, 10 = X^T.G, 11")
     a = ap.parse_args()
+    global REUSE_SCALES
+    REUSE_SCALES = a.reuse_scales
     pairs = [0, 1] if a.pair == "both" else [int(a.pair)]
     ctx = _capi.Ctx(0)
     rng = np.random.default_rng(0)
