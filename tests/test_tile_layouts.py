@@ -1,0 +1,14 @@
+"""Host model of the pair GEMM's shared-memory tile layouts (tools/tile_layout_check.py): swizzle decode of the raw TMA tiles,
+the K-major 16-bit tiles against the canonical UMMA read order, the epilogue staging against SWIZZLE_128B, bank conflicts.
+CPU only."""
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_splitter_and_epilogue_address_algebra():
+    spec = importlib.util.spec_from_file_location("tile_layout_check", os.path.join(ROOT, "tools", "tile_layout_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check() == []
