@@ -441,10 +441,13 @@ def run_b200_arm(args, cfg):
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"1 step on {rows} of {cfg['rows']} rows, same model, NumPy f32 restatement of the reference path (oracle/), "
                                           f"host BLAS {threads} threads ({gfs:.0f} GFLOP/s on a 1536^3 sgemm), {dt:.1f} s"}
-        v1, r1, d1, g1 = cpu_one_core_run(cfg, target_s=8.0)
-        line["cpu_baseline"]["one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
-                                            "sample": f"1 step on {r1} of {cfg['rows']} rows, single-threaded C restatement (oracle/oracle_c.c, "
-                                                      f"{g1:.0f} GFLOP/s on a 1024^3 sgemm), {d1:.1f} s"}
+        try:
+            v1, r1, d1, g1 = cpu_one_core_run(cfg, target_s=8.0)
+            line["cpu_baseline"]["one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                                "sample": f"1 step on {r1} of {cfg['rows']} rows, single-threaded C restatement (oracle/oracle_c.c, "
+                                                          f"{g1:.0f} GFLOP/s on a 1024^3 sgemm), {d1:.1f} s"}
+        except (OSError, RuntimeError, subprocess.CalledProcessError) as e:  # no compiler on the box and no prebuilt library
+            line["cpu_baseline"]["one_core"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if dp is not None:
         dp.close()
     if rank == 0:
