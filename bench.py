@@ -414,7 +414,9 @@ def run_b200_arm(args, cfg):
                                f"kind::tf32 hi*hi + 2 x kind::f16 bf16 cross terms, tile layout {cross})"),
                     "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_equivalent_tflops": slots * ach,
-                    "gemm_share_of_step": g_ms / ms, "cross_terms": "tf32" if cross == 0 else "bf16",
+                    "gemm_share_of_step": g_ms / ms, "cross_terms": {0: "tf32", 3: "bf16 x3", 4: "fp16 x3 scaled"}.get(cross, "bf16"),
+                    # the same fraction against the BURST bf16 figure: what ncu's tensor-pipe-active percentage corresponds to
+                    "frac_of_burst_peak": ach / (peaks["bf16_burst"] / 2.0 / slots),
                     "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / {slots:g} (tf32-rate MMA slots per product)"}
         # context: what cuBLAS itself reaches on this pool's B200s for PLAIN tf32 (one MMA per product) -- tools/tf32_cublas_peak.py
         cub = os.path.join(ROOT, "profiles", "r1_cublas_peaks.json")
