@@ -42,3 +42,31 @@ def test_row_scaling_keeps_badly_scaled_rows_faithful():
     for name in ("fp16 x3, row/column scaled", "tf32 + 2 x bf16 (cross 1, default)", "bf16 x3"):
         assert float((np.abs(res[name][0] - truth) / rowscale).max()) < 2e-5, name
     assert float((np.abs(res["fp16 x3, row/column scaled"][0] - truth) / rowscale).max()) < 5e-7
+
+
+def scale_of_max(max_bits):
+    """host copy of scale_of_max() in csrc/gemm_tcgen05_2cta.cu (cross mode 4): (mult, inv) as float32"""
+    e = min(max(int(max_bits) >> 23, 14), 254)
+    mult = np.array([(267 - e) << 23], np.uint32).view(np.float32)[0]
+    inv = np.array([(e - 13) << 23], np.uint32).view(np.float32)[0]
+    return mult, inv
+
+
+def test_fp16_scale_bit_formulas():
+    """the power-of-two scale taken from the bit pattern of a row's largest magnitude: scaled maximum in [2^13, 2^14) (inside fp16's
+    65504), mult * inv == 1 exactly, both factors normal floats for every possible maximum (zero, subnormal, huge, inf, NaN)"""
+    rng = np.random.default_rng(2)
+    mags = np.concatenate([np.exp2(rng.uniform(-110, 126, 2000)), [1.0, 1.9999999, 2.0, 3.0e38, 1e-30]]).astype(np.float32)
+    for m in mags:
+        mult, inv = scale_of_max(m.view(np.uint32))
+        s = np.float32(m) * mult
+        assert np.float32(2.0 ** 13) <= s < np.float32(2.0 ** 14), (m, s)
+        assert mult * inv == np.float32(1.0)
+    for bits in (0x00000000, 0x00000001, 0x007FFFFF, 0x06800000, 0x7F7FFFFF, 0x7F800000, 0x7FC00000):  # 0, subnormals, 2^-114, max, inf, NaN
+        mult, inv = scale_of_max(bits)
+        assert np.isfinite(mult) and np.isfinite(inv) and mult > 0 and inv > 0
+        assert mult * inv == np.float32(1.0)
+        assert (int(np.float32(mult).view(np.uint32)) >> 23) not in (0, 255) and (int(np.float32(inv).view(np.uint32)) >> 23) not in (0, 255)
+        m = np.array([bits], np.uint32).view(np.float32)[0]
+        if np.isfinite(m):
+            assert abs(float(m) * float(mult)) < 2.0 ** 14  # never beyond fp16's range
