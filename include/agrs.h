@@ -82,8 +82,9 @@ AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);     
  * bias != NULL fuses `+ b` of Linear::forward / Conv2D::forward (operators.rs:144, :379) into the epilogue.
  * Large aligned shapes run the TMA + tcgen05 split kernel (f32-faithful: x = hi + lo with hi the tf32 part; hi*hi on the tf32
  * tensor pipe, the two correction terms lo*x + x*lo on bf16 operands by default; finite inputs: <= 1e-5 of max|C|; NaN and
- * zero propagate as in f32; an inf INPUT yields a non-finite result that is NaN where f32 gives inf; sums folded across K
- * chunks longer than AGRS_TUNE_TC_KCHUNK flush subnormal results to zero);
+ * zero propagate as in f32; an inf INPUT -- or a finite one above bf16's largest value, 3.39e38, the top 0.4 % of f32's last
+ * binade -- yields a non-finite result that is NaN where f32 gives inf; sums folded across K chunks longer than
+ * AGRS_TUNE_TC_KCHUNK flush subnormal results to zero);
  * skinny outputs (N <= 32: the Conv2D lowering, Linear(3456,10)) run HBM-bound streaming kernels; everything else runs the
  * tiled SIMT f32 kernel.  All are CUDA; the choice never changes semantics. */
 AGRS_API int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
