@@ -1,7 +1,5 @@
-"""NOT collected yet (lives outside tests/): GPU test of padded leading dimensions through agrs_gemm_f32 on every path.
-Written when the round's GPU budget was spent; run it on a B200 first
-    python -m pytest tools/pending_tests/test_gemm_padded_ld.py -m gpu -q
-and move it into tests/ once green."""
+"""GPU test of padded leading dimensions through agrs_gemm_f32 on every GEMM path (tcgen05 pair and one-CTA kernels with both
+epilogues, SIMT, skinny): lda / ldb / ldc larger than the extents."""
 import numpy as np
 import pytest
 
