@@ -221,6 +221,52 @@ __device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, ui
   }
 }
 
+#ifdef AGRS_SPLIT_EARLY_CONVERT
+// Build-time variant (tools/build_pair_variants.sh, 4th field): the same row conversion cut in two, so that the splitter loop can
+// read and convert a row as soon as its raw tile has landed and wait for the destination stage only before the stores -- the
+// chain "stage free -> split written"  then holds the stores alone.  Not part of the default build.
+template <bool MN_MAJOR, int CROSS>
+__device__ __forceinline__ void convert_row_16(uint32_t raw, uint32_t row, float mult, uint32_t (&lo)[16], uint32_t (&x)[16]) {
+  float v[BK];
+  if (MN_MAJOR) {
+    const uint32_t base = raw + (row >> 5) * 4096u + (row & 7u) * 4u, c = (row & 31u) >> 3;
+#pragma unroll
+    for (uint32_t k = 0; k < uint32_t(BK); ++k)
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(base + k * 128u + ((c ^ (k & 3u)) << 5)));
+  } else {
+    const uint32_t base = raw + row * 128u;
+#pragma unroll
+    for (uint32_t c = 0; c < 8; ++c)
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3])
+                   : "r"(base + ((c ^ (row & 7u)) << 4)));
+  }
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const float e0 = v[2 * p], e1 = v[2 * p + 1];
+    if (CROSS == 4) {
+      const float s0 = e0 * mult, s1 = e1 * mult;
+      float h0, h1;
+      x[p] = pack_f16(s0, s1);
+      unpack_f16(x[p], h0, h1);
+      lo[p] = pack_f16(s0 - h0, s1 - h1);
+    } else {
+      x[p] = pack_bf16(e0, e1);
+      lo[p] = CROSS == 3 ? pack_bf16(e0 - __uint_as_float(x[p] << 16), e1 - __uint_as_float(x[p] & 0xFFFF0000u)) : pack_bf16(lo_of(e0), lo_of(e1));
+    }
+  }
+}
+template <int CROSS>
+__device__ __forceinline__ void store_row_16(uint32_t out_lo, uint32_t out_x, uint32_t row, const uint32_t (&lo)[16], const uint32_t (&x)[16]) {
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    const uint32_t off = bf_chunk_offset<CROSS>(row, j);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_lo + off), "r"(lo[4 * j]), "r"(lo[4 * j + 1]), "r"(lo[4 * j + 2]), "r"(lo[4 * j + 3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_x + off), "r"(x[4 * j]), "r"(x[4 * j + 1]), "r"(x[4 * j + 2]), "r"(x[4 * j + 3]) : "memory");
+  }
+}
+#endif
+
 // ---- CROSS 4: "fp16x3" with operand scaling ---------------------------------------------------------------------------------
 // fp16 has tf32's 11 significant bits at twice the MMA rate but only 5 exponent bits.  The range comes from an exact power-of-two
 // scale per row of op(A) and per column of op(B): the row's largest magnitude is brought into [2^13, 2^14), after which
@@ -508,6 +554,31 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (int(it % kSplitGroups) != grp) continue;
         const uint32_t r = it % R, rph = (it / R) & 1u, l = it % L, lph = (it / L) & 1u;
         mbar_wait(raw_full(r), rph);
+#ifdef AGRS_SPLIT_EARLY_CONVERT
+        if constexpr (CROSS != 0) {  // variant build: convert from the raw tile first, wait for the destination stage afterwards
+          const uint32_t raw = smem_base + r * RAW_BYTES, out = lo_base + l * RAW_BYTES;
+          uint32_t lo16[kItems][16], x16[kItems][16];
+#pragma unroll
+          for (int i = 0; i < kItems; ++i) {
+            const int item = tid + i * kGroupWarps * 32;
+            const uint32_t row = uint32_t(item) & uint32_t(BM - 1);
+            if (item < BM) convert_row_16<A_MN, CROSS>(raw, row, mult[i], lo16[i], x16[i]);
+            else           convert_row_16<B_MN, CROSS>(raw + A_BYTES, row, mult[i], lo16[i], x16[i]);
+          }
+          mbar_wait(lo_free(l), lph ^ 1u);
+#pragma unroll
+          for (int i = 0; i < kItems; ++i) {
+            const int item = tid + i * kGroupWarps * 32;
+            const uint32_t row = uint32_t(item) & uint32_t(BM - 1);
+            if (item < BM) store_row_16<CROSS>(out, out + BF_TILE, row, lo16[i], x16[i]);
+            else           store_row_16<CROSS>(out + 2 * BF_TILE, out + 3 * BF_TILE, row, lo16[i], x16[i]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(done_remote + 8u * l);
+          continue;
+        }
+#endif
         mbar_wait(lo_free(l), lph ^ 1u);
         if constexpr (CROSS == 0) {
           const uint32_t src = smem_base + r * RAW_BYTES + tid * 16, dst = lo_base + l * RAW_BYTES + tid * 16;

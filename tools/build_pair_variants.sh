@@ -1,17 +1,20 @@
 #!/bin/bash
 # Builds libagrs_b200 variants that differ only in the pair GEMM's pipeline shape (raw ring R, lo ring L, splitter groups G) into
-# build_variants/ (git-ignored, shipped to the GPU box) for tools/gpu_pair_variants.sh.  Usage: tools/build_pair_variants.sh "4 3 2" "5 2 2" ...
+# build_variants/ (git-ignored, shipped to the GPU box) for tools/gpu_pair_variants.sh / tools/gpu_round2_first.sh.
+# Usage: tools/build_pair_variants.sh "4 2 2" "4 2 1" "4 2 1 1" ...   (a 4th field of 1 adds -DAGRS_SPLIT_EARLY_CONVERT: name suffix E)
 set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" > /dev/null
 mkdir -p build_variants
 OBJ=autograd.rs_b200/build
 for v in "$@"; do
-  set -- $v; R=$1; L=$2; G=$3
-  o=build_variants/pair_R${R}L${L}G${G}.o
+  set -- $v; R=$1; L=$2; G=$3; E=${4:-0}
+  tag=R${R}L${L}G${G}; extra=""
+  if [ "$E" = "1" ]; then tag=${tag}E; extra="-DAGRS_SPLIT_EARLY_CONVERT=1"; fi
+  o=build_variants/pair_${tag}.o
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr \
-    -I include -I autograd.rs_b200/csrc -DAGRS_PAIR_RAW_STAGES=$R -DAGRS_PAIR_LO_STAGES=$L -DAGRS_SPLIT_GROUPS=$G \
+    -I include -I autograd.rs_b200/csrc -DAGRS_PAIR_RAW_STAGES=$R -DAGRS_PAIR_LO_STAGES=$L -DAGRS_SPLIT_GROUPS=$G $extra \
     -c autograd.rs_b200/csrc/gemm_tcgen05_2cta.cu -o $o
-  nvcc -shared -o build_variants/libagrs_b200_R${R}L${L}G${G}.so $(ls $OBJ/*.o | grep -v gemm_tcgen05_2cta.o) $o -gencode arch=compute_100a,code=sm_100a
-  echo "built build_variants/libagrs_b200_R${R}L${L}G${G}.so"
+  nvcc -shared -o build_variants/libagrs_b200_${tag}.so $(ls $OBJ/*.o | grep -v gemm_tcgen05_2cta.o) $o -gencode arch=compute_100a,code=sm_100a
+  echo "built build_variants/libagrs_b200_${tag}.so"
 done
