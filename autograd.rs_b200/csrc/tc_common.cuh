@@ -122,7 +122,10 @@ __device__ __forceinline__ float split_lo(float x, float& hi) {
 }
 
 __device__ __forceinline__ void tile_coords(int64_t t, int64_t m_tiles, int64_t n_tiles, int64_t& mb, int64_t& nb) {
-  constexpr int64_t GROUP_M = 8;  // walk 8 row-blocks per column sweep: concurrent CTAs share A rows and B columns in L2
+#ifndef AGRS_TILE_GROUP_M
+#define AGRS_TILE_GROUP_M 8
+#endif
+  constexpr int64_t GROUP_M = AGRS_TILE_GROUP_M;  // walk 8 row-blocks per column sweep: concurrent CTAs share A rows and B columns in L2
   int64_t per_group = GROUP_M * n_tiles;
   int64_t g = t / per_group, r = t % per_group;
   int64_t first = g * GROUP_M;
