@@ -42,7 +42,7 @@ struct agrs_ctx {
   float* workspace = nullptr;
   size_t workspace_bytes = 0;
   // live GEMM timing (agrs_profile_*): event pairs recorded around launches while enabled
-  struct ProfRec { cudaEvent_t start, stop; double flops; int path; };
+  struct ProfRec { cudaEvent_t start = nullptr, stop = nullptr; double flops = 0; int path = 0; };
   cudaEvent_t timer_a = nullptr, timer_b = nullptr;  // agrs_timer_*
   // agrs_capture_*: while capturing, allocations made inside the capture are tracked; frees of older buffers are deferred
   bool capturing = false;
@@ -95,6 +95,9 @@ int agrs_fail(agrs_ctx* ctx, int code, const char* fmt, ...);
   } while (0)
 
 int agrs_ensure_workspace(agrs_ctx* ctx, size_t nbytes);
+// event pair around one GEMM launch while agrs_profile_enable is on (gemm.cu)
+int agrs_prof_begin(agrs_ctx* ctx, int path, double flops, agrs_ctx::ProfRec* rec);
+int agrs_prof_end(agrs_ctx* ctx, const agrs_ctx::ProfRec& rec);
 
 // gemm back ends (gemm_simt.cu / gemm_tcgen05.cu)
 int agrs_gemm_simt(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,

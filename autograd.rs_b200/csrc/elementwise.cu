@@ -58,9 +58,9 @@ struct PowiOp {  // f32::powi: repeated multiplication (exp >= 0) or reciprocal 
 struct Sq { __device__ float operator()(float a) const { return a * a; } };
 struct FillOp { float v; };
 
-// ---- unary: out[i] = f(a[i]) ----
+// ---- unary: out[i] = f(a[i]) ----  (out may BE a: powi_inplace, *= scalar, /= scalar run in place -- no __restrict__ here)
 template <class F>
-__global__ void __launch_bounds__(kThreads) k_unary_v4(F f, float* __restrict__ out, const float* __restrict__ a, size_t n4) {
+__global__ void __launch_bounds__(kThreads) k_unary_v4(F f, float* out, const float* a, size_t n4) {
   size_t stride = size_t(gridDim.x) * kThreads;
   size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
   for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {

@@ -12,6 +12,25 @@ static cudaEvent_t take_event(agrs_ctx* ctx) {
   return e;
 }
 
+// live GEMM timing (agrs_profile_*): an event pair around one launch, shared with agrs_gemm_f32_scatter (gemm_tcgen05_2cta.cu)
+int agrs_prof_begin(agrs_ctx* ctx, int path, double flops, agrs_ctx::ProfRec* rec) {
+  *rec = agrs_ctx::ProfRec{};
+  if (!ctx->profiling) return AGRS_OK;
+  rec->path = path;
+  rec->flops = flops;
+  rec->start = take_event(ctx);
+  rec->stop = take_event(ctx);
+  AGRS_REQUIRE(ctx, rec->start && rec->stop, AGRS_ERR_CUDA, "agrs_gemm_f32: cannot create timing events");
+  AGRS_CUDA(ctx, cudaEventRecord(rec->start, ctx->stream));
+  return AGRS_OK;
+}
+int agrs_prof_end(agrs_ctx* ctx, const agrs_ctx::ProfRec& rec) {
+  if (!rec.start) return AGRS_OK;
+  AGRS_CUDA(ctx, cudaEventRecord(rec.stop, ctx->stream));
+  ctx->prof.push_back(rec);
+  return AGRS_OK;
+}
+
 extern "C" {
 
 int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
@@ -100,24 +119,14 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
     use_skinny = skinny_ok;
   }
   ctx->last_gemm_path = use_tc ? AGRS_GEMM_TCGEN05 : (use_skinny ? AGRS_GEMM_SKINNY : AGRS_GEMM_SIMT);
-  agrs_ctx::ProfRec rec{};
-  if (ctx->profiling) {
-    rec.path = ctx->last_gemm_path;
-    rec.flops = 2.0 * double(M) * double(N) * double(K);
-    rec.start = take_event(ctx);
-    rec.stop = take_event(ctx);
-    AGRS_REQUIRE(ctx, rec.start && rec.stop, AGRS_ERR_CUDA, "agrs_gemm_f32: cannot create timing events");
-    AGRS_CUDA(ctx, cudaEventRecord(rec.start, ctx->stream));
-  }
+  agrs_ctx::ProfRec rec;
+  if (int prc = agrs_prof_begin(ctx, ctx->last_gemm_path, 2.0 * double(M) * double(N) * double(K), &rec)) return prc;
   const bool pair = use_tc && ctx->tc_2cta && M > 128;
   int rc = use_skinny ? agrs_gemm_skinny(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
          : pair   ? agrs_gemm_tc_2cta(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
          : use_tc ? agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
                   : agrs_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
-  if (ctx->profiling) {
-    AGRS_CUDA(ctx, cudaEventRecord(rec.stop, ctx->stream));
-    ctx->prof.push_back(rec);
-  }
+  if (int prc = agrs_prof_end(ctx, rec)) return prc;
   return rc;
 }
 

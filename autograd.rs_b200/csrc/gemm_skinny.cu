@@ -312,7 +312,10 @@ bool agrs_gemm_skinny_eligible(int transA, int transB, int64_t M, int64_t N, int
 int agrs_gemm_skinny(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
                      int64_t ldb, float* C, int64_t ldc, const float* bias) {
   const int n = int(N);
-  if (transA && M * N <= 160 && K >= 4096) {  // tn_small
+  // tn_small stages kTnRows rows of A and of B: 1 KB of dynamic shared memory per (M + N).  It is only taken while that fits the
+  // 48 KB every kernel gets without an opt-in (next to its 0.7 KB of static arrays); wider shapes (Linear(100, 1): M + N = 101)
+  // go to k_gemm_tn below.
+  if (transA && M * N <= 160 && K >= 4096 && M + N <= 46) {  // tn_small
     const int64_t blocks_wanted = int64_t(ctx->sm_count) * 4, max_blocks = (K + kTnRows - 1) / kTnRows;
     int64_t blocks = blocks_wanted < max_blocks ? blocks_wanted : max_blocks;
     int64_t rpb = ((K + blocks - 1) / blocks + kTnRows - 1) / kTnRows * kTnRows;

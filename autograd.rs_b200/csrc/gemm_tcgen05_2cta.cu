@@ -940,7 +940,11 @@ extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int6
   const bool wants_split = tc2::choose_splits(tiles, ctx->sm_count / 2, (K + tc::BK - 1) / tc::BK, ctx->tc_splitk) > 1;
   if (fused_ok && !wants_split) {
     ctx->last_gemm_path = AGRS_GEMM_TCGEN05;
-    return gemm_tc_2cta_impl(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias, &sc);
+    agrs_ctx::ProfRec rec;  // timed like every other GEMM launch (bench.py's roofline counts all of them)
+    if (int prc = agrs_prof_begin(ctx, AGRS_GEMM_TCGEN05, 2.0 * double(M) * double(N) * double(K), &rec)) return prc;
+    const int grc = gemm_tc_2cta_impl(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias, &sc);
+    if (int prc = agrs_prof_end(ctx, rec)) return prc;
+    return grc;
   }
   int rc = agrs_gemm_f32(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias);
   if (rc) return rc;

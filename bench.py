@@ -160,47 +160,80 @@ def cpu_sample_rows(cfg, target_s):
     n = 1536
     a = np.random.default_rng(0).standard_normal((n, n)).astype(np.float32)
     a @ a
-    t0 = time.perf_counter()
-    a @ a
-    gfs = 2.0 * n ** 3 / (time.perf_counter() - t0) / 1e9
+    a @ a          # the BLAS thread pool is up (the first calls after a thread-count change run at a fraction of the speed)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        a @ a
+        best = min(best, time.perf_counter() - t0)
+    gfs = 2.0 * n ** 3 / best / 1e9
     rows = int(target_s * gfs * 1e9 / flops_per_sample(cfg))
     rows = max(64, min(cfg["rows"], rows // 64 * 64))
     return rows, gfs
 
 
-def cpu_reference_run(cfg, steps, warmup, target_s_per_step):
-    """The reference's CPU path (oracle restatement, NumPy f32 + the host BLAS with all its threads) on a bounded
-    sample: `rows` of the batch, same model.  Returns (samples/s, rows, seconds per step, threads, calibration GF/s)."""
-    from oracle import oracle_np as O
-    from autograd_rs_b200 import workloads as W  # data generation only (NumPy RNG); no device code runs here
-    rows, gfs = cpu_sample_rows(cfg, target_s_per_step)
-    ws, bs = W.mlp_init(cfg["layers"], cfg["width"], seed=0)
-    x, t = W.mlp_batch(rows, cfg["width"], cfg["width"], seed=1)
-    layers = [O.OLinearLayer(w, b) for w, b in zip(ws, bs)]
-    act = {"relu": O.OpReLU, "sigmoid": O.OpSigmoid}[cfg["act"]]
-    params = [p for l in layers for p in l.parameters()]
-    X, T = O.OTensor(x), O.OTensor(t, requires_grad=False)
+def set_blas_threads(n=None):
+    """Give the host BLAS every core whatever the launcher exported: torchrun sets OMP_NUM_THREADS=1 for its workers, which
+    would make the CPU arm 4-5x slower at N > 1 than at N = 1 for no reason that has to do with the GPUs."""
+    n = n or os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n, user_api="blas")
+    except Exception:
+        pass
+    return cpu_threads()
 
-    def step():
-        h = X.clone()
-        for i, l in enumerate(layers):
+
+class OracleMLP:
+    """The reference's CPU path (oracle restatement, NumPy f32 + host BLAS) for one MLP configuration, one training iteration
+    at a time; `hold_grads` keeps the parameter gradients of the last backward so the parity block can compare them."""
+
+    def __init__(self, cfg, ws, bs, x, t):
+        from oracle import oracle_np as O
+        self.O, self.cfg = O, cfg
+        self.layers = [O.OLinearLayer(w.copy(), b.copy()) for w, b in zip(ws, bs)]
+        self.act = {"relu": O.OpReLU, "sigmoid": O.OpSigmoid}[cfg["act"]]
+        self.params = [p for l in self.layers for p in l.parameters()]
+        self.X, self.T = O.OTensor(x), O.OTensor(t, requires_grad=False)
+        self.grads = None
+
+    def step(self, hold_grads=False):
+        O = self.O
+        h = self.X.clone()
+        for i, l in enumerate(self.layers):
             h = l.forward(h)
-            if i + 1 < len(layers):
-                h = act().forward([h])
-        loss = O.OpMSE().forward([h, T.clone()])
+            if i + 1 < len(self.layers):
+                h = self.act().forward([h])
+        loss = O.OpMSE().forward([h, self.T.clone()])
         loss.backward()
-        O.sgd(params, cfg["lr"])
-        O.model_zero_grad(params)
+        if hold_grads:
+            self.grads = [np.array(p.grad, copy=True) for p in self.params]
+        O.sgd(self.params, self.cfg["lr"])
+        O.model_zero_grad(self.params)
         return float(loss.data[0, 0])
 
+
+def cpu_reference_run(cfg, steps, warmup, target_s_per_step, hold_grads=False):
+    """The reference's CPU path on a bounded sample: `rows` of the batch, same model, every BLAS thread.
+    Returns a dict: samples/s, rows, seconds per step, threads, calibration GF/s, first loss (+ the stepper when hold_grads)."""
+    from autograd_rs_b200 import workloads as W  # data generation only (NumPy RNG); no device code runs here
+    threads = set_blas_threads()
+    rows, gfs = cpu_sample_rows(cfg, target_s_per_step)
+    ws, bs = W.mlp_init(cfg["layers"], cfg["width"], seed=0)
+    x, t = W.mlp_batch(cfg["rows"], cfg["width"], cfg["width"], seed=1)  # rank 0's batch of the timed arm: its first `rows` rows
+    om = OracleMLP(cfg, ws, bs, x[:rows], t[:rows])
+    del ws, bs
+    first = None
     for _ in range(warmup):
-        step()
+        l = om.step()
+        first = l if first is None else first
     t0 = time.perf_counter()
-    for _ in range(steps):
-        loss = step()
+    for i in range(steps):
+        loss = om.step(hold_grads=hold_grads and i == 0 and warmup == 0)
+        first = loss if first is None else first
     dt = (time.perf_counter() - t0) / max(steps, 1)
     assert np.isfinite(loss)
-    return rows / dt, rows, dt, cpu_threads(), gfs
+    return {"value": rows / dt, "rows": rows, "dt": dt, "threads": threads, "gfs": gfs, "loss0": first, "oracle": om if hold_grads else None}
 
 
 def cpu_one_core_run(cfg, target_s):
@@ -231,68 +264,229 @@ def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, rows, dt, threads, gfs = cpu_reference_run(cfg, args.steps, args.warmup, target_s_per_step=2.0)
+    r = cpu_reference_run(cfg, args.steps, args.warmup, target_s_per_step=2.0)
+    val, rows, dt, threads = r["value"], r["rows"], r["dt"], r["threads"]
     sample = f"{rows} of {cfg['rows']} rows per step, same {cfg['layers']}x{cfg['width']} {cfg['act']} MLP, NumPy f32 restatement (oracle/), host BLAS {threads} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, cfg, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "the Rust reference cannot be compiled in this image (no cargo/rustc); its ndarray/matrixmultiply path is single-threaded, this port uses every BLAS thread"},
+                         "note": "the Rust reference cannot be compiled in this image (no cargo/rustc); its ndarray/matrixmultiply path is single-threaded, "
+                                 "this port uses every BLAS thread (set explicitly: the same count at every --gpus N, whatever OMP_NUM_THREADS the launcher exports)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:  # the single-threaded figure (what `cargo run --release` of the reference would use: Cargo.toml enables no threading)
+        v1, r1, d1, g1 = cpu_one_core_run(cfg, target_s=6.0)
+        line["cpu_baseline"]["one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                            "sample": f"1 step on {r1} of {cfg['rows']} rows, single-threaded C restatement (oracle/oracle_c.c, {g1:.0f} GFLOP/s on a 1024^3 sgemm), {d1:.1f} s"}
+    except (OSError, RuntimeError, subprocess.CalledProcessError) as e:
+        line["cpu_baseline"]["one_core"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     emit(line)
 
 
 def workload_config(args, cfg, world):
-    return {"workload": f"{args.config}: {cfg['layers']} x Linear({cfg['width']},{cfg['width']}) + {cfg['act']} between, MSELoss, SGD; "
-                        f"{cfg['rows']} rows per GPU ({ {'mlp4096': 'BASELINE.json configs[1]', 'mlp8192': 'BASELINE.json configs[4], per-GPU shard'}.get(args.config, 'test-size') })",
-            "rows_per_gpu": cfg["rows"], "global_batch": cfg["rows"] * world, "width": cfg["width"], "layers": cfg["layers"],
-            "activation": cfg["act"], "lr": cfg["lr"], "parallelism": f"dp{world}",
-            "gradient_exchange": ("none" if world == 1 else ("fused over NVLink peer memory: reduce-scatter pushed from the dW GEMM epilogue / scatter kernel, then one slot-sum + SGD + all-gather kernel" if getattr(args, "fused", False)
-                                                              else "NCCL all-reduce(avg) per parameter" + ("" if getattr(args, "no_overlap", False) else ", overlapped with backward"))),
-            "l2": "working set (activations + weights, > 2 GB) is larger than the 126 MB L2; no flush needed"}
+    return workload_config_for(args.config, cfg, world, getattr(args, "fused", False), getattr(args, "no_overlap", False))
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def run_b200_arm(args, cfg):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            sys.exit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py --gpus {args.gpus} ...")
-        args.gpus = world
+class Job:
+    """what every part of the B200 arm needs: device, ranks, the launcher's collectives"""
 
-    import autograd_rs_b200  # noqa: F401
-    from autograd_rs_b200 import _capi, frontend as F, workloads as W
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        from autograd_rs_b200 import frontend as F
+        self.dev = F.Device(self.local)
 
-    dist = None
-    if world > 1:
+    def barrier(self):
+        self.dev.sync()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, v):
+        if self.dist is None:
+            return v
         import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        tt = torch.tensor([v], dtype=torch.float64, device=f"cuda:{self.local}")
+        self.dist.all_reduce(tt, op=self.dist.ReduceOp.MAX)
+        return float(tt.item())
 
-    dev = F.Device(local)
-    dp = None
+    def all_gather_bytes(self, h):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, h)
+        return out
+
+    def data_parallel(self, params, fused, overlap=True):
+        """DataParallel over this job's ranks (None on one GPU); returns (dp, fused actually in use)"""
+        if self.world == 1:
+            return None, False
+        from autograd_rs_b200 import frontend as F
+        ids = [F.comm_unique_id() if self.rank == 0 else None]   # an NCCL id is good for ONE communicator
+        self.dist.broadcast_object_list(ids, src=0)
+        dp = F.DataParallel(self.dev, self.world, self.rank, ids[0], params, overlap=overlap)
+        if fused and not dp.enable_fused(self.all_gather_bytes):     # collective decision: all ranks or none
+            fused = False
+            if self.rank == 0:
+                print(f"fused peer-memory optimiser unavailable ({dp.fused_error}); using the NCCL exchange", file=sys.stderr)
+        return dp, fused
+
+    def replicas_identical(self, arrays):
+        """every rank holds the same bytes (MIN == MAX over ranks, element-wise)"""
+        import torch
+        for a in arrays:
+            tt = torch.from_numpy(np.ascontiguousarray(a)).cuda(self.local)
+            lo, hi = tt.clone(), tt.clone()
+            self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN)
+            self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                return False
+        return True
+
+
+def dp_parity(job):
+    """N > 1, before anything is timed: the ranks train a small MLP on disjoint shards of ONE global batch through both gradient
+    exchanges (NCCL all-reduce overlapped with backward; fused peer-memory reduce-scatter + SGD + all-gather), rank 0 runs the
+    oracle on the whole global batch.  Every loss (mean of the shard means) and every final weight must be within 1e-4 of the
+    single-device oracle (north star) and the replicas bit-identical -- otherwise the bench stops here."""
+    from autograd_rs_b200 import frontend as F, workloads as W
+    world, rank, dev = job.world, job.rank, job.dev
+    layers, width, rows, steps, lr = 3, 512, 256 * world, 4, 1e-4
+    ws, bs = W.mlp_init(layers, width, seed=3)
+    x, t = W.mlp_batch(rows, width, width, seed=4)          # the global batch, identical on every rank
+    b, e = F.shard_rows(rows, world, rank)
+    want = None
+    if rank == 0:
+        from oracle import oracle_np as O
+        want, olayers = O.mlp_train(x, t, ws, bs, "sigmoid", lr, steps, np.float32)
+        oparams = [q.data for l in olayers for q in l.parameters()]
+    out = {"workload": f"{layers} x Linear({width},{width}) + sigmoid, global batch {rows} in {world} shards, {steps} steps, lr {lr}",
+           "tolerance": 1e-4, "paths": {}}
+    for name, fused in (("nccl", False), ("fused", True)):
+        model = W.build_mlp(dev, ws, bs, "sigmoid")
+        dp, fused_on = job.data_parallel(model.parameters(), fused)
+        tr = W.Trainer(model, lr, dp=dp)
+        X, T = F.Tensor.from_numpy(dev, x[b:e]), F.Tensor.from_numpy(dev, t[b:e])
+        T.requires_grad = False
+        losses = []
+        for _ in range(steps):
+            loss = tr.step(X, T)
+            dp.mean_scalar(loss)
+            losses.append(loss.item())
+        params = [p.data() for p in model.parameters()]
+        same = job.replicas_identical(params)
+        rec = {"replicas_bit_identical": bool(same), "fused_in_use": bool(fused_on)}
+        if rank == 0:
+            rec["max_rel_err_loss"] = max(abs(a - c) / abs(c) for a, c in zip(losses, want))
+            rec["max_rel_err_weights"] = max(O.rel_err(p, q) for p, q in zip(params, oparams))
+            rec["ok"] = bool(same and rec["max_rel_err_loss"] < 1e-4 and rec["max_rel_err_weights"] < 1e-4)
+        out["paths"][name] = rec
+        dp.close()
+        del tr, model, X, T, loss
+        job.barrier()
+    ok = [all(r.get("ok", False) for r in out["paths"].values()) if rank == 0 else True]
+    job.dist.broadcast_object_list(ok, src=0)
+    out["ok"] = bool(ok[0])
+    return out
+
+
+def gpu_gradients_of_first_step(job, cfg, ws, bs, x, t):
+    """forward -> MSE -> backward on a fresh model holding the given weights; returns (loss, [parameter gradients])"""
+    from autograd_rs_b200 import frontend as F, workloads as W
+    dev = job.dev
+    model = W.build_mlp(dev, ws, bs, cfg["act"])
+    X, T = F.Tensor.from_numpy(dev, x), F.Tensor.from_numpy(dev, t)
+    T.requires_grad = False
+    pred = model.forward([X.clone()])
+    loss = F.nn.MeanSquaredError().forward([pred, T.clone()])
+    loss.backward()
+    grads = [p.grad().data() for p in model.parameters()]
+    return loss.item(), grads
+
+
+def oracle_parity(job, cfg, target_s):
+    """N = 1: one iteration of the oracle on a bounded sample of the timed batch (the same call is the cpu_baseline timing), and the
+    device path on exactly those rows and weights: step-0 loss and every parameter gradient, max|a-b| / max|b| per tensor <= 1e-4."""
+    from autograd_rs_b200 import workloads as W
+    r = cpu_reference_run(cfg, steps=1, warmup=0, target_s_per_step=target_s, hold_grads=True)
+    om, rows = r.pop("oracle"), r["rows"]
+    ws, bs = W.mlp_init(cfg["layers"], cfg["width"], seed=0)
+    x, t = W.mlp_batch(cfg["rows"], cfg["width"], cfg["width"], seed=1)
+    loss, grads = gpu_gradients_of_first_step(job, cfg, ws, bs, x[:rows], t[:rows])
+    errs = [om.O.rel_err(g.reshape(-1), og.reshape(-1)) for g, og in zip(grads, om.grads)]
+    el = abs(loss - r["loss0"]) / abs(r["loss0"])
+    par = {"rows": rows, "of_rows": cfg["rows"], "loss_device": loss, "loss_oracle": r["loss0"], "rel_err_loss": el,
+           "max_rel_err_param_grads": max(errs), "tensors_compared": len(errs), "tolerance": 1e-4,
+           "ok": bool(el < 1e-4 and max(errs) < 1e-4),
+           "what": "step-0 loss and all dW / db of the timed model on the first `rows` rows of the timed batch: device vs the f32 oracle (oracle/oracle_np.py)"}
+    return par, r
+
+
+def gemm_roofline(dev, g_n, g_ms, g_fl, step_ms_total):
+    """roofline block of the dominant kernel from the live event-pair timings of every GEMM launch in the timed region"""
+    from autograd_rs_b200 import _capi
+    peaks = load_peaks()
+    # tf32 tensor rate = 1/2 of bf16 (nominal 1.1 vs 2.25 PFLOP/s dense).  Per algorithmic product the split GEMM issues
+    #   cross = 0: three tf32 MMAs                      -> 3 tf32 slots, f32-faithful peak = bf16/6
+    #   cross = 1/2: one tf32 MMA + two bf16 MMAs (1/2 slot each) -> 2 tf32 slots, peak = bf16/4
+    #   cross = 3/4: three bf16 / fp16 MMAs             -> 1.5 tf32 slots, peak = bf16/3
+    # The GEMMs run inside a long step -> sustained figure.
+    cross = dev.get_tuning(_capi.TUNE_TC_CROSS)
+    slots = {0: 3.0, 3: 1.5, 4: 1.5}.get(cross, 2.0)
+    peak_alg = peaks["bf16_sustained"] / 2.0 / slots
+    if not g_n:
+        return None
+    ach = g_fl / (g_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": ach, "peak": peak_alg, "unit": "TFLOP/s", "frac": ach / peak_alg, "traffic": traffic,
+                "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2: " +
+                          ("kind::tf32 x3)" if cross == 0 else "3 x kind::f16 on bf16 pairs x1 + x2)" if cross == 3 else
+                           "3 x kind::f16 on power-of-two-scaled fp16 pairs h + l)" if cross == 4 else
+                           f"kind::tf32 hi*hi + 2 x kind::f16 bf16 cross terms, tile layout {cross})"),
+                "launches": g_n, "avg_launch_ms": g_ms / g_n,
+                "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_equivalent_tflops": slots * ach,
+                "gemm_share_of_step": g_ms / step_ms_total, "cross_terms": {0: "tf32", 3: "bf16 x3", 4: "fp16 x3 scaled"}.get(cross, "bf16"),
+                # the same fraction against the BURST bf16 figure: what ncu's tensor-pipe-active percentage corresponds to
+                "frac_of_burst_peak": ach / (peaks["bf16_burst"] / 2.0 / slots),
+                "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / {slots:g} (tf32-rate MMA slots per product)"}
+    # context: what cuBLAS itself reaches on this pool's B200s for PLAIN tf32 (one MMA per product) -- tools/tf32_cublas_peak.py
+    cub = os.path.join(ROOT, "profiles", "r1_cublas_peaks.json")
+    if os.path.exists(cub):
+        try:
+            c = json.load(open(cub))
+            roofline["cublas_tf32_tflops"] = {"burst": c["tf32"]["burst_tflops"], "sustained": c["tf32"]["sustained_tflops"]}
+            roofline["executed_frac_of_cublas_tf32_sustained"] = slots * ach / c["tf32"]["sustained_tflops"]
+            roofline["cublas_f32_simt_tflops"] = c["f32_simt"]["sustained_tflops"]
+        except Exception:
+            pass
+    return roofline
+
+
+def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
+    """Build the model of `cfg` on every rank, warm up, time `steps` training iterations device-resident (and end to end when
+    asked).  Returns the measurements as a dict; rank-independent values are maxima over ranks."""
+    from autograd_rs_b200 import _capi, frontend as F, workloads as W
+    args, dev, rank, world = job.args, job.dev, job.rank, job.world
     ws, bs = W.mlp_init(cfg["layers"], cfg["width"], seed=0)            # identical on every rank (replicated parameters)
     model = W.build_mlp(dev, ws, bs, cfg["act"])
     del ws, bs
-    if world > 1:
-        ids = [F.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        dp = F.DataParallel(dev, world, rank, ids[0], model.parameters(), overlap=not args.no_overlap)
-        if args.fused:
-            def all_gather_bytes(h):
-                out = [None] * world
-                dist.all_gather_object(out, h)
-                return out
-            if not dp.enable_fused(all_gather_bytes):   # collective decision: all ranks or none
-                args.fused = False
-                if rank == 0:
-                    print(f"fused peer-memory optimiser unavailable ({dp.fused_error}); using the NCCL exchange", file=sys.stderr)
+    dp, fused_on = job.data_parallel(model.parameters(), args.fused, overlap=not args.no_overlap)
     tr = W.Trainer(model, cfg["lr"], dp=dp)
 
     x, t = W.mlp_batch(cfg["rows"], cfg["width"], cfg["width"], seed=1, rank=rank)  # this rank's shard of the global batch
@@ -305,54 +499,42 @@ def run_b200_arm(args, cfg):
     X.copy_from_numpy(hx, blocking=True)
     T.copy_from_numpy(ht, blocking=True)
 
-    def barrier():
-        dev.sync()
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        import torch
-        tt = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
     # ---- device-resident throughput ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        sampler.wait_ready()
-    barrier()
+    job.barrier()
     pool_high = tr.reserve_pool(X, T)   # one untimed iteration sizes the memory pool: no pool growth inside the timed regions
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         loss = tr.step(X, T)
-    barrier()
+    job.barrier()
     dev.profile_enable(True)
     dev.profile_gemm(_capi.GEMM_TCGEN05)
     dev.profile_gemm(_capi.GEMM_SIMT)
     n0 = dev.launches()
     w0 = time.time()
     dev.timer_begin()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = tr.step(X, T)
     ms = dev.timer_end()
-    sampler.window(w0, time.time())
-    barrier()
+    if sampler is not None:
+        sampler.window(w0, time.time())
+    job.barrier()
     launches = dev.launches() - n0
     dev.profile_enable(False)
     g_n, g_ms, g_fl = dev.profile_gemm(_capi.GEMM_TCGEN05)
     s_n, s_ms, s_fl = dev.profile_gemm(_capi.GEMM_SIMT)
-    ms = max_over_ranks(ms)
+    ms_local = ms
+    ms = job.max_over_ranks(ms)
     final_loss = loss.item()
     assert np.isfinite(final_loss), "training diverged"
-    value = cfg["rows"] * world * args.steps / (ms * 1e-3)
+    res = {"value": cfg["rows"] * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "algorithmic_tflops_per_gpu": flops_per_sample(cfg) * cfg["rows"] * steps / (ms * 1e-3) / 1e12,
+           "final_loss": final_loss, "pool_used_high_bytes": pool_high, "gpu_launches": launches,
+           "roofline": gemm_roofline(dev, g_n, g_ms, g_fl, ms_local), "simt_gemm": {"launches": s_n, "ms": s_ms},
+           "fused": fused_on, "config": workload_config_for(name, cfg, world, fused_on, args.no_overlap)}
 
     # ---- end to end: host buffers in, loss out, every step ----
     # Every step's X and T come from pinned host memory (268 MB) and its loss goes back to the host.  The copy of step i+1
     # runs on the copy stream while step i computes (two device input slots); the loss read blocks once per step.
-    e2e = None
-    if not args.no_e2e:
+    if do_e2e:
         X2, T2 = F.Tensor.zeros(dev, hx.shape), F.Tensor.zeros(dev, ht.shape)
         T2.requires_grad = False
         slots = [(X, T), (X2, T2)]
@@ -371,78 +553,96 @@ def run_b200_arm(args, cfg):
             return lv
 
         e2e_loop(2)
-        barrier()
+        job.barrier()
         t0 = time.perf_counter()
         w0 = time.time()
         dev.timer_begin()
-        lv = e2e_loop(args.steps)
+        lv = e2e_loop(steps)
         ms_e = dev.timer_end()
         wall_e = (time.perf_counter() - t0) * 1e3
-        sampler.window(w0, time.time())
-        ms_e = max_over_ranks(max(ms_e, wall_e))
+        if sampler is not None:
+            sampler.window(w0, time.time())
+        ms_e = job.max_over_ranks(max(ms_e, wall_e))
         assert np.isfinite(lv)
-        e2e = {"value": cfg["rows"] * world * args.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + ht.nbytes),
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps,
-               "how": "X,T copied from pinned host memory every step on a copy stream (double-buffered, overlapping the previous step), loss read back every step"}
+        res["e2e"] = {"value": cfg["rows"] * world * steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + ht.nbytes),
+                      "d2h_bytes_per_step": 4, "ms_per_step": ms_e / steps,
+                      "how": "X,T copied from pinned host memory every step on a copy stream (double-buffered, overlapping the previous step), loss read back every step"}
         del X2, T2, slots
+    if dp is not None:
+        dp.close()
+    del tr, model, X, T, loss
+    job.barrier()
+    return res
 
-    clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel ----
-    peaks = load_peaks()
-    # tf32 tensor rate = 1/2 of bf16 (nominal 1.1 vs 2.25 PFLOP/s dense).  Per algorithmic product the split GEMM issues
-    #   cross = 0: three tf32 MMAs                      -> 3 tf32 slots, f32-faithful peak = bf16/6
-    #   cross > 0: one tf32 MMA + two bf16 MMAs (1/2 slot each) -> 2 tf32 slots, peak = bf16/4
-    # The GEMMs run inside a long step -> sustained figure.
-    cross = dev.get_tuning(_capi.TUNE_TC_CROSS)
-    slots = {0: 3.0, 3: 1.5, 4: 1.5}.get(cross, 2.0)  # cross = 3 / 4: three bf16 / fp16 MMAs, no tf32 pass
-    peak_alg = peaks["bf16_sustained"] / 2.0 / slots
-    roofline = None
-    if g_n:
-        ach = g_fl / (g_ms * 1e-3) / 1e12
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
-        roofline = {"bound": "tensor", "achieved": ach, "peak": peak_alg, "unit": "TFLOP/s", "frac": ach / peak_alg, "traffic": traffic,
-                    "kernel": "tc2::k_gemm_3xtf32_2cta (tcgen05.mma.cta_group::2: " +
-                              ("kind::tf32 x3)" if cross == 0 else "3 x kind::f16 on bf16 pairs x1 + x2)" if cross == 3 else
-                               "3 x kind::f16 on scaled fp16 pairs h + l, plus two absmax kernels per launch)" if cross == 4 else
-                               f"kind::tf32 hi*hi + 2 x kind::f16 bf16 cross terms, tile layout {cross})"),
-                    "launches": g_n, "avg_launch_ms": g_ms / g_n,
-                    "algorithmic_flops_per_launch": g_fl / g_n, "executed_tf32_equivalent_tflops": slots * ach,
-                    "gemm_share_of_step": g_ms / ms, "cross_terms": {0: "tf32", 3: "bf16 x3", 4: "fp16 x3 scaled"}.get(cross, "bf16"),
-                    # the same fraction against the BURST bf16 figure: what ncu's tensor-pipe-active percentage corresponds to
-                    "frac_of_burst_peak": ach / (peaks["bf16_burst"] / 2.0 / slots),
-                    "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s / 2 (tf32 rate) / {slots:g} (tf32-rate MMA slots per product)"}
-        # context: what cuBLAS itself reaches on this pool's B200s for PLAIN tf32 (one MMA per product) -- tools/tf32_cublas_peak.py
-        cub = os.path.join(ROOT, "profiles", "r1_cublas_peaks.json")
-        if os.path.exists(cub):
-            try:
-                c = json.load(open(cub))
-                roofline["cublas_tf32_tflops"] = {"burst": c["tf32"]["burst_tflops"], "sustained": c["tf32"]["sustained_tflops"]}
-                roofline["executed_frac_of_cublas_tf32_sustained"] = slots * ach / c["tf32"]["sustained_tflops"]
-                roofline["cublas_f32_simt_tflops"] = c["f32_simt"]["sustained_tflops"]
-            except Exception:
-                pass
+def workload_config_for(name, cfg, world, fused, no_overlap):
+    return {"workload": f"{name}: {cfg['layers']} x Linear({cfg['width']},{cfg['width']}) + {cfg['act']} between, MSELoss, SGD; "
+                        f"{cfg['rows']} rows per GPU ({ {'mlp4096': 'BASELINE.json configs[1]', 'mlp8192': 'BASELINE.json configs[4], per-GPU shard'}.get(name, 'test-size') })",
+            "rows_per_gpu": cfg["rows"], "global_batch": cfg["rows"] * world, "width": cfg["width"], "layers": cfg["layers"],
+            "activation": cfg["act"], "lr": cfg["lr"], "parallelism": f"dp{world}",
+            "gradient_exchange": ("none" if world == 1 else ("fused over NVLink peer memory: reduce-scatter pushed from the dW GEMM epilogue / scatter kernel, then one slot-sum + SGD + all-gather kernel" if fused
+                                                              else "NCCL all-reduce(avg) per parameter" + ("" if no_overlap else ", overlapped with backward"))),
+            "l2": "working set (activations + weights, > 2 GB) is larger than the 126 MB L2; no flush needed"}
+
+
+def run_b200_arm(args, cfg):
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_env != args.gpus:
+        if world_env == 1 and args.gpus > 1:
+            sys.exit(f"--gpus {args.gpus} needs torchrun: python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py --gpus {args.gpus} ...")
+        args.gpus = world_env
+
+    import autograd_rs_b200  # noqa: F401
+    from autograd_rs_b200 import workloads as W
+    job = Job(args)
+    rank, world = job.rank, job.world
+
+    # ---- parity gates, before anything is timed ----
+    parity = {}
+    if world > 1 and not args.no_parity:
+        parity["data_parallel"] = dp_parity(job)
+        if not parity["data_parallel"]["ok"]:
+            if rank == 0:
+                emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "error": "data-parallel parity failed; nothing was timed", "parity": parity})
+            sys.exit(1)
+
+    sampler = ClockSampler(job.local) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+        sampler.wait_ready()
+
+    head = time_config(job, args.config, cfg, args.steps, args.warmup, sampler, do_e2e=not args.no_e2e)
+
+    # ---- the north star's scaling configuration next to the headline: mlp8192 (BASELINE.json configs[4]), a few steps ----
+    also = {}
+    if args.config == "mlp4096" and not args.no_also:
+        c5 = dict(W.CONFIGS["mlp8192"])
+        r5 = time_config(job, "mlp8192", c5, steps=args.also_steps, warmup=2, sampler=sampler, do_e2e=False)
+        also["mlp8192"] = {"metric": METRIC, "unit": UNIT, **r5}
+    clocks = sampler.stop() if sampler is not None else None
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, world),
-        "algorithmic_tflops_per_gpu": flops_per_sample(cfg) * cfg["rows"] * args.steps / (ms * 1e-3) / 1e12,
-        "final_loss": final_loss, "pool_used_high_bytes": pool_high, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-        "simt_gemm": {"launches": s_n, "ms": s_ms},
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": head["config"], "algorithmic_tflops_per_gpu": head["algorithmic_tflops_per_gpu"],
+        "final_loss": head["final_loss"], "pool_used_high_bytes": head["pool_used_high_bytes"], "clocks": clocks, "e2e": head.get("e2e"),
+        "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "simt_gemm": head["simt_gemm"],
     }
+    if also:
+        line["also"] = also
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        val, rows, dt, threads, gfs = cpu_reference_run(cfg, steps=1, warmup=0, target_s_per_step=15.0)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"1 step on {rows} of {cfg['rows']} rows, same model, NumPy f32 restatement of the reference path (oracle/), "
-                                          f"host BLAS {threads} threads ({gfs:.0f} GFLOP/s on a 1536^3 sgemm), {dt:.1f} s"}
+        # one oracle iteration on a bounded sample: the CPU baseline AND the checker of the timed model's first step
+        par, r = oracle_parity(job, cfg, target_s=15.0)
+        parity[args.config] = par
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                                "sample": f"1 step on {r['rows']} of {cfg['rows']} rows, same model, NumPy f32 restatement of the reference path (oracle/), "
+                                          f"host BLAS {r['threads']} threads ({r['gfs']:.0f} GFLOP/s on a 1536^3 sgemm), {r['dt']:.1f} s"}
+        if "mlp8192" in also:
+            par5, r5 = oracle_parity(job, dict(W.CONFIGS["mlp8192"]), target_s=4.0)
+            parity["mlp8192"] = par5
+            also["mlp8192"]["cpu_baseline"] = {"value": r5["value"], "unit": UNIT, "cores": r5["threads"], "kind": "port",
+                                               "sample": f"1 step on {r5['rows']} of 8192 rows, {r5['dt']:.1f} s"}
         try:
             v1, r1, d1, g1 = cpu_one_core_run(cfg, target_s=8.0)
             line["cpu_baseline"]["one_core"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
@@ -450,14 +650,18 @@ def run_b200_arm(args, cfg):
                                                           f"{g1:.0f} GFLOP/s on a 1024^3 sgemm), {d1:.1f} s"}
         except (OSError, RuntimeError, subprocess.CalledProcessError) as e:  # no compiler on the box and no prebuilt library
             line["cpu_baseline"]["one_core"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
-    if dp is not None:
-        dp.close()
+    if parity:
+        parity["ok"] = all(v.get("ok", False) for v in parity.values() if isinstance(v, dict))
+        line["parity"] = parity
     if rank == 0:
         emit(line)
-    del tr, model, X, T, loss
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        if parity and not parity["ok"]:
+            print("PARITY FAILED: " + json.dumps(parity), file=sys.stderr)
+    if job.dist is not None:
+        job.dist.barrier()
+        job.dist.destroy_process_group()
+    if rank == 0 and parity and not parity["ok"]:
+        sys.exit(1)
 
 
 def main():
@@ -469,6 +673,9 @@ def main():
     ap.add_argument("--config", default="mlp4096", choices=["mlp4096", "mlp8192", "mlp_small"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the data-parallel parity gate that runs before the timing")
+    ap.add_argument("--no-also", action="store_true", help="headline only: do not time mlp8192 (BASELINE configs[4]) after mlp4096")
+    ap.add_argument("--also-steps", type=int, default=3)
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce gradients after backward instead of during it")
     ap.add_argument("--fused", action="store_true", help="N > 1: one fused reduce-scatter + SGD + all-gather kernel over NVLink peer memory "
                                                          "instead of NCCL all-reduce + SGD (the default)")

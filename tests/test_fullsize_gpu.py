@@ -100,3 +100,95 @@ def test_conv_lowering_properties_c3_size(ctx):
     col = ctx.to_host(dcol, (B, Ho * Ho, k * k))
     for i, j in ((0, 0), (2, 3), (4, 4)):
         assert np.array_equal(col[:, :, i * k + j].reshape(B, Ho, Ho), im[:, 0, i:i + Ho, j:j + Ho])
+
+
+# ------------------------------------------------------------------ full-size configurations against the oracle
+from autograd_rs_b200 import frontend as F  # noqa: E402
+from autograd_rs_b200 import workloads as W  # noqa: E402
+from oracle import oracle_np as O  # noqa: E402
+
+TOL = 1e-4  # BASELINE.json north star
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = F.Device(0)
+    yield d
+    d.close()
+
+
+@pytest.mark.parametrize("n,ta,tb", [(8192, 0, 0), (8192, 1, 0), (16384, 0, 0), (16384, 0, 1)])
+def test_gemm_cube_8192_and_16384_sampled_vs_f64(ctx, n, ta, tb):
+    """C4's upper end: n^3 through the default path, 40 sampled rows of C within 2e-5 of the f64 product (contract 1e-4) and the
+    whole result finite.  16384^3 is 2 x 1 GB of operands and 8.8 TFLOP."""
+    rng = np.random.default_rng(n + ta + 2 * tb)
+    A = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    B = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    dA, dB, dC = ctx.to_device(A), ctx.to_device(B), ctx.empty(n * n)
+    dev_gemm(ctx, dA, dB, dC, n, n, n, ta, tb, n, n)
+    assert ctx.L.agrs_last_gemm_path(ctx.h) == K.GEMM_TCGEN05
+    C = ctx.to_host(dC, (n, n))
+    rows = np.unique(np.concatenate([[0, 1, n - 1], rng.integers(0, n, 37)]))
+    opA = (A.T if ta else A)[rows].astype(np.float64)
+    truth = opA @ (B.T if tb else B).astype(np.float64)
+    assert np.abs(C[rows] - truth).max() / np.abs(truth).max() < 2e-5
+    assert np.isfinite(C).all()
+
+
+def test_lenet_c3_full_batch_tracks_oracle(dev):
+    """C3 at its full batch (BASELINE configs[2]: im[1024,1,28,28] -> Conv2D(1,6,5) -> ReLU -> Flatten -> Linear(3456,10) -> MSE):
+    two training iterations, every loss, every parameter and the input gradient within 1e-4 of the oracle."""
+    rng = np.random.default_rng(31)
+    B = 1024
+    im = rng.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32)
+    t = rng.uniform(0, 1, (B, 10)).astype(np.float32)
+    fb = W.kaiming_bound((5, 5, 6))
+    filt = rng.uniform(-fb, fb, (5, 5, 6)).astype(np.float32)
+    cbias = rng.uniform(-0.1, 0.1, (6,)).astype(np.float32)
+    w = rng.uniform(-0.05, 0.05, (3456, 10)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (1, 10)).astype(np.float32)
+    lr, steps = 1e-3, 2
+    model = W.build_lenet(dev, filt, cbias, w, b)
+    tr = W.Trainer(model, lr)
+    X, Tt = F.Tensor.from_numpy(dev, im), F.Tensor.from_numpy(dev, t)
+    Tt.requires_grad = False
+    got = [tr.step(X, Tt).item() for _ in range(steps)]
+    conv, lin = O.OConvLayer(filt.copy(), cbias.copy(), 1), O.OLinearLayer(w.copy(), b.copy())
+    params = conv.parameters() + lin.parameters()
+    OX, OT = O.OTensor(im), O.OTensor(t, requires_grad=False)
+    want = []
+    for _ in range(steps):
+        h = O.OpFlatten().forward([O.OpReLU().forward([conv.forward(OX.clone())])])
+        loss = O.OpMSE().forward([lin.forward(h), OT.clone()])
+        want.append(float(loss.data[0, 0]))
+        loss.backward()
+        O.sgd(params, lr)
+        O.model_zero_grad(params)
+    assert max(abs(a - c) / abs(c) for a, c in zip(got, want)) < TOL
+    for p, op in zip(model.parameters(), params):
+        assert O.rel_err(p.data(), op.data) < TOL
+    assert O.rel_err(X.grad().data(), OX.grad) < TOL
+
+
+def test_sigmoid_layer_8192_wide_fwd_bwd_vs_oracle(dev):
+    """One layer pair of C5 at its full width (Linear(8192,8192) -> Sigmoid -> Linear(8192,8192) -> MSE) on 512 rows: prediction,
+    loss, input gradient and all four parameter gradients within 1e-4 of the f32 oracle."""
+    ws, bs = W.mlp_init(2, 8192, seed=41)
+    x, t = W.mlp_batch(512, 8192, 8192, seed=42)
+    model = W.build_mlp(dev, ws, bs, "sigmoid")
+    X, Tt = F.Tensor.from_numpy(dev, x), F.Tensor.from_numpy(dev, t)
+    Tt.requires_grad = False
+    pred = model.forward([X.clone()])
+    loss = F.nn.MeanSquaredError().forward([pred, Tt.clone()])
+    loss.backward()
+    ol = [O.OLinearLayer(w, b) for w, b in zip(ws, bs)]
+    OX, OT = O.OTensor(x), O.OTensor(t, requires_grad=False)
+    h = O.OpSigmoid().forward([ol[0].forward(OX.clone())])
+    opred = ol[1].forward(h)
+    oloss = O.OpMSE().forward([opred, OT.clone()])
+    oloss.backward()
+    assert abs(loss.item() - float(oloss.data[0, 0])) / abs(float(oloss.data[0, 0])) < TOL
+    assert O.rel_err(pred.data(), opred.data) < TOL
+    assert O.rel_err(X.grad().data(), OX.grad) < TOL
+    for p, op in zip(model.parameters(), [q for l in ol for q in l.parameters()]):
+        assert O.rel_err(p.grad().data(), op.grad) < TOL

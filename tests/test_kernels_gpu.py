@@ -421,6 +421,8 @@ def test_gemm_tcgen05_special_values(ctx):
     (25, 6, 200000, 1, 0),    # conv dw: col^T . g                (tn kernel, split K + ticket fold)
     (3456, 10, 1024, 1, 0),   # Linear dW: x^T . g                (tn kernel)
     (33, 16, 7, 1, 0), (1, 1, 1, 1, 0), (100, 9, 64, 1, 0),
+    (100, 1, 8192, 1, 0),     # dW of Linear(100, 1), batch 8192: M*N <= 160 but too wide for tn_small's staging
+    (160, 1, 4096, 1, 0), (40, 4, 5000, 1, 0), (45, 1, 4096, 1, 0), (46, 1, 4096, 1, 0),
 ])
 def test_gemm_skinny(ctx, M, N, Kd, ta, tb):
     rng = np.random.default_rng(M + 7 * N + Kd)
