@@ -64,6 +64,10 @@ def lib():
             "agrs_fill_f32": [vp, vp, f32, sz],
             "agrs_gemm_f32": [vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp],
             "agrs_set_gemm_path": [vp, i32],
+            "agrs_gemm_operand_absmax": [vp, vp, vp],
+            "agrs_gemm_wants_absmax": [vp, i64, i64, i64],
+            "agrs_absmax_f32": [vp, vp, sz, vp],
+            "agrs_next_output_absmax": [vp, vp],
             "agrs_last_gemm_path": [vp],
             "agrs_set_tuning": [vp, i32, i64],
             "agrs_get_tuning": [vp, i32, C.POINTER(i64)],

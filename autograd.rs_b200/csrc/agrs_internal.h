@@ -27,9 +27,15 @@ struct agrs_ctx {
   int tc_2cta = 1;         // use the cta_group::2 pair kernel when the problem has more than one 128-row block
   int tc_splitk = 0;       // pair kernel: 0 = choose the K split that fills the last wave, n > 0 = force n splits
   int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
-  int tc_cross = 1;        // pair kernel correction terms: 0 tf32, 1 bf16 (SWIZZLE_64B tiles), 2 bf16 (unswizzled tiles)
+  int tc_cross = 5;        // pair kernel split scheme (AGRS_TUNE_TC_CROSS): 0 tf32 x3, 1 / 2 tf32 + bf16 cross terms, 3 bf16 x3, 4 fp16 x3 scaled,
+                           // 5 (default) = 4 when the caller announced operand magnitudes, else 1
   int tc_epi_tma = 1;      // pair kernel epilogue: 1 staged in shared memory + TMA store / reduce-add, 0 direct st.global from registers
   int tc_reuse_scales = 0; // cross mode 4, measurement aid: 1 = reuse the operand magnitudes of the previous launch (same operands only)
+  // operand magnitudes for the next GEMM call (agrs_gemm_operand_absmax) and the slot the next elementwise launch reports into
+  // (agrs_next_output_absmax); both are consumed by the call they apply to
+  const uint32_t* gemm_a_mx = nullptr;
+  const uint32_t* gemm_b_mx = nullptr;
+  uint32_t* next_out_mx = nullptr;
   int64_t tc_min_flops = 1LL << 24;  // AUTO path: below this many MACs the SIMT kernel wins on launch+fill latency
   // small scratch for reductions (block partials + completion counter), allocated once
   float* scratch = nullptr;

@@ -36,7 +36,7 @@ static int ctx_init(int device, cudaStream_t stream, bool own, agrs_ctx** out) {
   ctx->cc_minor = prop.minor;
   if (const char* e = getenv("AGRS_TC_CROSS")) {  // default of AGRS_TUNE_TC_CROSS (agrs.h)
     const int v = atoi(e);
-    if (v >= 0 && v <= 4) ctx->tc_cross = v;
+    if (v >= 0 && v <= 5) ctx->tc_cross = v;
   }
   if (const char* e = getenv("AGRS_TC_EPI_TMA")) ctx->tc_epi_tma = atoi(e) ? 1 : 0;  // default of AGRS_TUNE_TC_EPI_TMA
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }

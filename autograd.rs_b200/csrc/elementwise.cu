@@ -13,6 +13,22 @@ constexpr int kBlocksPerSM = 8;
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 
+// ---- optional by-product: the largest finite |out[i]| as its bit pattern (agrs_next_output_absmax) ----
+// The split GEMM's fp16 mode scales each operand by a power of two taken from its largest magnitude; a producer that already
+// touches every element reports it for free instead of a separate pass over the tensor.  Non-finite values are left out (the
+// scale must serve the finite ones; inf / NaN stay non-finite whatever the scale).  Unsigned compare == float compare for
+// magnitudes, and a maximum does not depend on the order: deterministic.
+__device__ __forceinline__ uint32_t mag_bits(float v) {
+  const uint32_t b = __float_as_uint(v) & 0x7FFFFFFFu;
+  return b < 0x7F800000u ? b : 0u;
+}
+__device__ __forceinline__ uint32_t mag4(uint32_t m, float4 r) { return max(max(m, mag_bits(r.x)), max(max(mag_bits(r.y), mag_bits(r.z)), mag_bits(r.w))); }
+__device__ __forceinline__ void mag_commit(uint32_t m, uint32_t* slot) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(slot, m);
+}
+
 // ---- functors (semantics cited from the reference) ----
 struct ReluFwd {  // functional_ndarray.rs:14-22: x > 0 ? x : 0  (-0.0, NaN -> +0.0)
   __device__ float operator()(float x) const { return x > 0.f ? x : 0.f; }
@@ -59,10 +75,11 @@ struct Sq { __device__ float operator()(float a) const { return a * a; } };
 struct FillOp { float v; };
 
 // ---- unary: out[i] = f(a[i]) ----  (out may BE a: powi_inplace, *= scalar, /= scalar run in place -- no __restrict__ here)
-template <class F>
-__global__ void __launch_bounds__(kThreads) k_unary_v4(F f, float* out, const float* a, size_t n4) {
+template <class F, bool MX>
+__global__ void __launch_bounds__(kThreads) k_unary_v4(F f, float* out, const float* a, size_t n4, uint32_t* mx) {
   size_t stride = size_t(gridDim.x) * kThreads;
   size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+  uint32_t m = 0;
   for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
     float4 v[kUnroll];
 #pragma unroll
@@ -70,26 +87,37 @@ __global__ void __launch_bounds__(kThreads) k_unary_v4(F f, float* out, const fl
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       float4 r = make_float4(f(v[u].x), f(v[u].y), f(v[u].z), f(v[u].w));
+      if (MX) m = mag4(m, r);
       st4(out + 4 * (i + u * stride), r);
     }
   }
   for (; i < n4; i += stride) {
     float4 v = ld4(a + 4 * i);
-    st4(out + 4 * i, make_float4(f(v.x), f(v.y), f(v.z), f(v.w)));
+    float4 r = make_float4(f(v.x), f(v.y), f(v.z), f(v.w));
+    if (MX) m = mag4(m, r);
+    st4(out + 4 * i, r);
   }
+  if (MX) mag_commit(m, mx);
 }
-template <class F>
-__global__ void k_unary_s(F f, float* out, const float* a, size_t begin, size_t n) {
+template <class F, bool MX>
+__global__ void k_unary_s(F f, float* out, const float* a, size_t begin, size_t n, uint32_t* mx) {
   size_t i = begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = f(a[i]);
+  uint32_t m = 0;
+  for (; i < n; i += stride) {
+    const float r = f(a[i]);
+    if (MX) m = max(m, mag_bits(r));
+    out[i] = r;
+  }
+  if (MX) mag_commit(m, mx);
 }
 
 // ---- binary, same length: out[i] = f(a[i], b[i]) ----
-template <class F>
-__global__ void __launch_bounds__(kThreads) k_binary_v4(F f, float* out, const float* a, const float* __restrict__ b, size_t n4) {
+template <class F, bool MX>
+__global__ void __launch_bounds__(kThreads) k_binary_v4(F f, float* out, const float* a, const float* __restrict__ b, size_t n4, uint32_t* mx) {
   size_t stride = size_t(gridDim.x) * kThreads;
   size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+  uint32_t m = 0;
   for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
     float4 x[kUnroll], y[kUnroll];
 #pragma unroll
@@ -98,19 +126,31 @@ __global__ void __launch_bounds__(kThreads) k_binary_v4(F f, float* out, const f
       y[u] = ld4(b + 4 * (i + u * stride));
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      st4(out + 4 * (i + u * stride), make_float4(f(x[u].x, y[u].x), f(x[u].y, y[u].y), f(x[u].z, y[u].z), f(x[u].w, y[u].w)));
+    for (int u = 0; u < kUnroll; ++u) {
+      float4 r = make_float4(f(x[u].x, y[u].x), f(x[u].y, y[u].y), f(x[u].z, y[u].z), f(x[u].w, y[u].w));
+      if (MX) m = mag4(m, r);
+      st4(out + 4 * (i + u * stride), r);
+    }
   }
   for (; i < n4; i += stride) {
     float4 x = ld4(a + 4 * i), y = ld4(b + 4 * i);
-    st4(out + 4 * i, make_float4(f(x.x, y.x), f(x.y, y.y), f(x.z, y.z), f(x.w, y.w)));
+    float4 r = make_float4(f(x.x, y.x), f(x.y, y.y), f(x.z, y.z), f(x.w, y.w));
+    if (MX) m = mag4(m, r);
+    st4(out + 4 * i, r);
   }
+  if (MX) mag_commit(m, mx);
 }
-template <class F>
-__global__ void k_binary_s(F f, float* out, const float* a, const float* b, size_t begin, size_t n) {
+template <class F, bool MX>
+__global__ void k_binary_s(F f, float* out, const float* a, const float* b, size_t begin, size_t n, uint32_t* mx) {
   size_t i = begin + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) out[i] = f(a[i], b[i]);
+  uint32_t m = 0;
+  for (; i < n; i += stride) {
+    const float r = f(a[i], b[i]);
+    if (MX) m = max(m, mag_bits(r));
+    out[i] = r;
+  }
+  if (MX) mag_commit(m, mx);
 }
 
 // ---- binary with broadcast rhs ----
@@ -162,16 +202,28 @@ int grid_for(agrs_ctx* ctx, size_t work_items, int per_thread) {
   return int(blocks);
 }
 
+// the slot of a pending agrs_next_output_absmax request, zeroed on the stream and consumed (one request serves one call)
+int take_mx(agrs_ctx* ctx, uint32_t** slot) {
+  *slot = ctx->next_out_mx;
+  ctx->next_out_mx = nullptr;
+  if (*slot) AGRS_CUDA(ctx, cudaMemsetAsync(*slot, 0, sizeof(uint32_t), ctx->stream));
+  return AGRS_OK;
+}
+
 template <class F>
 int launch_unary(agrs_ctx* ctx, F f, float* out, const float* a, size_t n) {
+  uint32_t* mx = nullptr;
+  if (int rc = take_mx(ctx, &mx)) return rc;
   if (n == 0) return AGRS_OK;
   size_t n4 = (agrs_aligned16(out) && agrs_aligned16(a)) ? n / 4 : 0;
   if (n4) {
-    k_unary_v4<F><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, n4);
+    if (mx) k_unary_v4<F, true><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, n4, mx);
+    else    k_unary_v4<F, false><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, n4, nullptr);
     AGRS_LAUNCHED(ctx);
   }
   if (n4 * 4 < n) {
-    k_unary_s<F><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, n4 * 4, n);
+    if (mx) k_unary_s<F, true><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, n4 * 4, n, mx);
+    else    k_unary_s<F, false><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, n4 * 4, n, nullptr);
     AGRS_LAUNCHED(ctx);
   }
   return AGRS_OK;
@@ -179,23 +231,49 @@ int launch_unary(agrs_ctx* ctx, F f, float* out, const float* a, size_t n) {
 
 template <class F>
 int launch_binary(agrs_ctx* ctx, F f, float* out, const float* a, const float* b, size_t n) {
+  uint32_t* mx = nullptr;
+  if (int rc = take_mx(ctx, &mx)) return rc;
   if (n == 0) return AGRS_OK;
   size_t n4 = (agrs_aligned16(out) && agrs_aligned16(a) && agrs_aligned16(b)) ? n / 4 : 0;
   if (n4) {
-    k_binary_v4<F><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, b, n4);
+    if (mx) k_binary_v4<F, true><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, b, n4, mx);
+    else    k_binary_v4<F, false><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(f, out, a, b, n4, nullptr);
     AGRS_LAUNCHED(ctx);
   }
   if (n4 * 4 < n) {
-    k_binary_s<F><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, b, n4 * 4, n);
+    if (mx) k_binary_s<F, true><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, b, n4 * 4, n, mx);
+    else    k_binary_s<F, false><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(f, out, a, b, n4 * 4, n, nullptr);
     AGRS_LAUNCHED(ctx);
   }
   return AGRS_OK;
+}
+
+// out[0] = bits of the largest finite |x[i]| : the stand-alone pass, for tensors no producer reported on (uploads, foreign writers)
+template <bool V4>
+__global__ void __launch_bounds__(kThreads) k_absmax(const float* __restrict__ x, size_t begin, size_t n, uint32_t* mx) {
+  const size_t stride = size_t(gridDim.x) * kThreads;
+  uint32_t m = 0;
+  if (V4) {
+    size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < n; i += kUnroll * stride) {
+      float4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u] = ld4(x + 4 * (i + u * stride));
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) m = mag4(m, v[u]);
+    }
+    for (; i < n; i += stride) m = mag4(m, ld4(x + 4 * i));
+  } else {
+    for (size_t i = begin + size_t(blockIdx.x) * kThreads + threadIdx.x; i < n; i += stride) m = max(m, mag_bits(x[i]));
+  }
+  mag_commit(m, mx);
 }
 
 template <class F>
 int launch_bcast(agrs_ctx* ctx, F f, float* out, const float* a, const float* b, size_t n, size_t nb, int bmode) {
   if (n == 0) return AGRS_OK;
   if (nb == n) return launch_binary(ctx, f, out, a, b, n);
+  AGRS_REQUIRE(ctx, !ctx->next_out_mx, AGRS_ERR_UNSUPPORTED, "agrs_next_output_absmax: broadcast forms do not report magnitudes");
   AGRS_REQUIRE(ctx, nb > 0 && n % nb == 0, AGRS_ERR_SHAPE, "cannot broadcast %zu elements onto %zu", nb, n);
   if (bmode == AGRS_BCAST_TRAILING && nb % 4 == 0 && nb / 4 < (size_t(1) << 31) && agrs_aligned16(out) && agrs_aligned16(a) &&
       agrs_aligned16(b)) {
@@ -211,6 +289,29 @@ int launch_bcast(agrs_ctx* ctx, F f, float* out, const float* a, const float* b,
 }  // namespace
 
 extern "C" {
+
+int agrs_next_output_absmax(agrs_ctx* ctx, uint32_t* out_bits) {
+  AGRS_CHECK_CTX(ctx);
+  ctx->next_out_mx = out_bits;
+  return AGRS_OK;
+}
+
+int agrs_absmax_f32(agrs_ctx* ctx, const float* x, size_t n, uint32_t* out_bits) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out_bits && (n == 0 || x), AGRS_ERR_INVALID, "agrs_absmax_f32: null pointer");
+  AGRS_CUDA(ctx, cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), ctx->stream));
+  if (n == 0) return AGRS_OK;
+  const size_t n4 = agrs_aligned16(x) ? n / 4 : 0;
+  if (n4) {
+    k_absmax<true><<<grid_for(ctx, n4, kUnroll), kThreads, 0, ctx->stream>>>(x, 0, n4, out_bits);
+    AGRS_LAUNCHED(ctx);
+  }
+  if (n4 * 4 < n) {
+    k_absmax<false><<<grid_for(ctx, n - n4 * 4, 1), kThreads, 0, ctx->stream>>>(x, n4 * 4, n, out_bits);
+    AGRS_LAUNCHED(ctx);
+  }
+  return AGRS_OK;
+}
 
 int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n) {
   AGRS_CHECK_CTX(ctx);

@@ -55,7 +55,7 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
       ctx->tc_2cta = value ? 1 : 0;
       return AGRS_OK;
     case AGRS_TUNE_TC_CROSS:
-      AGRS_REQUIRE(ctx, value >= 0 && value <= 4, AGRS_ERR_INVALID, "AGRS_TUNE_TC_CROSS must be 0 .. 4");
+      AGRS_REQUIRE(ctx, value >= 0 && value <= 5, AGRS_ERR_INVALID, "AGRS_TUNE_TC_CROSS must be 0 .. 5");
       ctx->tc_cross = int(value);
       return AGRS_OK;
     case AGRS_TUNE_TC_EPI_TMA:
@@ -91,6 +91,9 @@ int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value) {
 int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                   const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias) {
   AGRS_CHECK_CTX(ctx);
+  // magnitudes announced for this call (agrs_gemm_operand_absmax): consumed here whatever path the call takes
+  const uint32_t *a_mx = ctx->gemm_a_mx, *b_mx = ctx->gemm_b_mx;
+  ctx->gemm_a_mx = ctx->gemm_b_mx = nullptr;
   AGRS_REQUIRE(ctx, M >= 0 && N >= 0 && K >= 0, AGRS_ERR_INVALID, "agrs_gemm_f32: negative extent");
   if (M == 0 || N == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, C && (K == 0 || (A && B)), AGRS_ERR_INVALID, "agrs_gemm_f32: null pointer");
@@ -122,12 +125,30 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   agrs_ctx::ProfRec rec;
   if (int prc = agrs_prof_begin(ctx, ctx->last_gemm_path, 2.0 * double(M) * double(N) * double(K), &rec)) return prc;
   const bool pair = use_tc && ctx->tc_2cta && M > 128;
+  if (pair) {
+    ctx->gemm_a_mx = a_mx;
+    ctx->gemm_b_mx = b_mx;
+  }
   int rc = use_skinny ? agrs_gemm_skinny(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
          : pair   ? agrs_gemm_tc_2cta(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
          : use_tc ? agrs_gemm_tc(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias)
                   : agrs_gemm_simt(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias);
+  ctx->gemm_a_mx = ctx->gemm_b_mx = nullptr;
   if (int prc = agrs_prof_end(ctx, rec)) return prc;
   return rc;
+}
+
+int agrs_gemm_operand_absmax(agrs_ctx* ctx, const uint32_t* a_bits, const uint32_t* b_bits) {
+  AGRS_CHECK_CTX(ctx);
+  ctx->gemm_a_mx = a_bits;
+  ctx->gemm_b_mx = b_bits;
+  return AGRS_OK;
+}
+
+int agrs_gemm_wants_absmax(agrs_ctx* ctx, int64_t M, int64_t N, int64_t K) {
+  if (!ctx || ctx->sticky || (ctx->tc_cross != 4 && ctx->tc_cross != 5) || !ctx->tc_2cta) return 0;
+  if (ctx->gemm_path == AGRS_GEMM_TCGEN05) return M > 128;
+  return ctx->gemm_path == AGRS_GEMM_AUTO && M > 128 && N >= 32 && K >= 32 && (M * N) * K >= ctx->tc_min_flops;
 }
 
 int agrs_profile_enable(agrs_ctx* ctx, int on) {

@@ -221,10 +221,14 @@ __device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, ui
   }
 }
 
-#ifdef AGRS_SPLIT_EARLY_CONVERT
-// Build-time variant (tools/build_pair_variants.sh, 4th field): the same row conversion cut in two, so that the splitter loop can
-// read and convert a row as soon as its raw tile has landed and wait for the destination stage only before the stores -- the
-// chain "stage free -> split written"  then holds the stores alone.  Not part of the default build.
+#ifndef AGRS_SPLIT_EARLY_CONVERT
+#define AGRS_SPLIT_EARLY_CONVERT 1
+#endif
+#if AGRS_SPLIT_EARLY_CONVERT
+// The row conversion cut in two (default; -DAGRS_SPLIT_EARLY_CONVERT=0 builds the one-piece loop): the splitter reads and converts
+// a row as soon as its raw tile has landed and waits for the destination stage only before the stores -- the chain "stage free ->
+// split written" then holds the stores alone.  Measured +3 % in the fp16 mode, +0..1 % with bf16 cross terms
+// (profiles/r2_gemm_pipeline_variants.txt).
 template <bool MN_MAJOR, int CROSS>
 __device__ __forceinline__ void convert_row_16(uint32_t raw, uint32_t row, float mult, uint32_t (&lo)[16], uint32_t (&x)[16]) {
   float v[BK];
@@ -283,7 +287,14 @@ __device__ __forceinline__ void scale_of_max(uint32_t max_bits, float& mult, flo
 }
 constexpr uint32_t kIdescF16 = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((2 * BM) >> 4) << 24);  // D f32, A = B = fp16, K-major
 // epilogue side: undo the scales on the 32 accumulators a thread holds (one row, columns col0 .. col0+31)
-__device__ __forceinline__ void unscale_piece(uint32_t (&v)[32], float inv_a, const uint32_t* __restrict__ b_max, int64_t col0, int64_t N) {
+__device__ __forceinline__ void unscale_piece(uint32_t (&v)[32], float inv_a, const uint32_t* __restrict__ b_max, int64_t col0, int64_t N, int mx_scalar) {
+  if (mx_scalar) {  // one magnitude for the whole of op(B): the same two exact power-of-two factors for every element
+    float mu, ib;
+    scale_of_max(__ldg(b_max), mu, ib);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * inv_a * ib);
+    return;
+  }
   if (col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(b_max + col0) & 15u) == 0)) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -364,7 +375,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
                    const __grid_constant__ ScatterArgs sc, const __grid_constant__ CUtensorMap tmap_c,
                    const __grid_constant__ CUtensorMap tmap_w, int epi_tma, const uint32_t* __restrict__ a_max,
-                   const uint32_t* __restrict__ b_max) {
+                   const uint32_t* __restrict__ b_max, int mx_scalar) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
@@ -545,7 +556,9 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int i = 0; i < kItems; ++i) {
           const int item = tid + i * kGroupWarps * 32;
           const int64_t g = item < BM ? w.mb * 2 * BM + rank * BM + item : w.nb * BN + rank * BNH + (item - BM);
-          const uint32_t bits = item < BM ? (g < M ? __ldg(a_max + g) : 0u) : (g < N ? __ldg(b_max + g) : 0u);
+          // mx_scalar: one magnitude per operand (kept by the host engine with the tensor), otherwise one per row / column
+          const uint32_t bits = mx_scalar ? __ldg(item < BM ? a_max : b_max)
+                                          : (item < BM ? (g < M ? __ldg(a_max + g) : 0u) : (g < N ? __ldg(b_max + g) : 0u));
           float inv;
           scale_of_max(bits, mult[i], inv);
         }
@@ -554,7 +567,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (int(it % kSplitGroups) != grp) continue;
         const uint32_t r = it % R, rph = (it / R) & 1u, l = it % L, lph = (it / L) & 1u;
         mbar_wait(raw_full(r), rph);
-#ifdef AGRS_SPLIT_EARLY_CONVERT
+#if AGRS_SPLIT_EARLY_CONVERT
         if constexpr (CROSS != 0) {  // variant build: convert from the raw tile first, wait for the destination stage afterwards
           const uint32_t raw = smem_base + r * RAW_BYTES, out = lo_base + l * RAW_BYTES;
           uint32_t lo16[kItems][16], x16[kItems][16];
@@ -632,7 +645,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         float inv_a = 1.f;
         if constexpr (CROSS == 4) {
           float mu;
-          scale_of_max(row0 + lane < M ? __ldg(a_max + row0 + lane) : 0u, mu, inv_a);
+          scale_of_max(mx_scalar ? __ldg(a_max) : (row0 + lane < M ? __ldg(a_max + row0 + lane) : 0u), mu, inv_a);
         }
         for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
           mbar_wait(tfull_bar(acc), acc_ph);
@@ -647,7 +660,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tmem_wait_ld();
             const int64_t col0 = w.nb * BN + c * 32;
             if (row0 < M && col0 < N) {  // warp-uniform; rows and columns past the edge are clipped by the tensor map
-              if constexpr (CROSS == 4) unscale_piece(v, inv_a, b_max, col0, N);
+              if constexpr (CROSS == 4) unscale_piece(v, inv_a, b_max, col0, N, mx_scalar);
               if (ch == 0 && bias_s) {
                 if (col0 + 32 <= N) {
 #pragma unroll
@@ -702,7 +715,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       float inv_a = 1.f;
       if constexpr (CROSS == 4) {
         float mu;
-        scale_of_max(row < M ? __ldg(a_max + row) : 0u, mu, inv_a);
+        scale_of_max(mx_scalar ? __ldg(a_max) : (row < M ? __ldg(a_max + row) : 0u), mu, inv_a);
       }
       for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
         mbar_wait(tfull_bar(acc), acc_ph);
@@ -715,7 +728,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tmem_wait_ld();
           const int64_t col0 = nb * BN + c * 32;
           if (row < M && col0 < N) {
-            if constexpr (CROSS == 4) unscale_piece(v, inv_a, b_max, col0, N);
+            if constexpr (CROSS == 4) unscale_piece(v, inv_a, b_max, col0, N, mx_scalar);
             float* dst = Cs + row * lds + col0;
             float* push = nullptr;  // where the finished piece also goes: this rank's slot at the piece's owner
             if (SCATTER && c0 + kb_per_chunk >= w.kb1) {
@@ -829,7 +842,9 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   }
   // workspace = [row magnitudes of op(A) | column magnitudes of op(B)] (CROSS 4 only) followed by the split-K partial planes
   const size_t a_slots = (size_t(M) + 63) / 64 * 64, b_slots = (size_t(N) + 63) / 64 * 64;
-  const size_t scale_bytes = CROSS == 4 ? (a_slots + b_slots) * sizeof(uint32_t) : 0;
+  // cross mode 4 with magnitudes supplied by the caller (agrs_gemm_operand_absmax: one per operand): no passes, no scale region
+  const bool ext_mx = CROSS == 4 && ctx->gemm_a_mx && ctx->gemm_b_mx;
+  const size_t scale_bytes = CROSS == 4 && !ext_mx ? (a_slots + b_slots) * sizeof(uint32_t) : 0;
   const size_t part_bytes = splits > 1 ? size_t(splits - 1) * size_t(M) * size_t(N) * sizeof(float) : 0;
   float* Cw = nullptr;
   uint32_t *a_max = nullptr, *b_max = nullptr;
@@ -838,7 +853,10 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     if (rc) return rc;
     Cw = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->workspace) + scale_bytes);
   }
-  if (CROSS == 4) {
+  if (ext_mx) {
+    a_max = const_cast<uint32_t*>(ctx->gemm_a_mx);
+    b_max = const_cast<uint32_t*>(ctx->gemm_b_mx);
+  } else if (CROSS == 4) {
     a_max = reinterpret_cast<uint32_t*>(ctx->workspace);
     b_max = a_max + a_slots;
     // op(A) row m: a row of A stored [M, K], a column of A stored [K, M]; op(B) column n: a column of B stored [K, N], a row of [N, K]
@@ -871,7 +889,7 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   }
   const int64_t items = tiles * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max);
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0);
   AGRS_LAUNCHED(ctx);
   if (splits > 1) {
     const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
@@ -899,12 +917,15 @@ static int gemm_tc_2cta_impl(agrs_ctx* ctx, int transA, int transB, int64_t M, i
   const int64_t num_kb = (K + tc::BK - 1) / tc::BK;
   const int kpc = ctx->tc_kchunk > 0 ? int((ctx->tc_kchunk + tc::BK - 1) / tc::BK) : int(num_kb);
   static const tc2::ScatterArgs none{};
+  // mode 5 (the default): the fp16 split when the caller announced the operands' magnitudes (the host engine keeps one per
+  // buffer, reported by the kernel that wrote it), bf16 correction terms when it did not -- no magnitude passes either way
+  const int cross = ctx->tc_cross == 5 ? (ctx->gemm_a_mx && ctx->gemm_b_mx ? 4 : 1) : ctx->tc_cross;
 #define AGRS_PAIR_X(AM, BMJ, X)                                                                                     \
   (sc ? tc2::launch<AM, BMJ, true, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc, A, lda, B, ldb)                  \
       : tc2::launch<AM, BMJ, false, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none, A, lda, B, ldb))
 #define AGRS_PAIR(AM, BMJ)                                                                      \
-  (ctx->tc_cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : ctx->tc_cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) \
-   : ctx->tc_cross == 3 ? AGRS_PAIR_X(AM, BMJ, 3) : ctx->tc_cross == 4 ? AGRS_PAIR_X(AM, BMJ, 4) : AGRS_PAIR_X(AM, BMJ, 0))
+  (cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) \
+   : cross == 3 ? AGRS_PAIR_X(AM, BMJ, 3) : cross == 4 ? AGRS_PAIR_X(AM, BMJ, 4) : AGRS_PAIR_X(AM, BMJ, 0))
   if (A_MN && B_MN) return AGRS_PAIR(true, true);
   if (A_MN) return AGRS_PAIR(true, false);
   if (B_MN) return AGRS_PAIR(false, true);
@@ -924,6 +945,8 @@ void agrs_fused_scatter_target(const agrs_fused* f, float* const** bases, int* w
 extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                                      const float* B, int64_t ldb, float* C, const float* bias, agrs_fused* f, size_t off) {
   AGRS_CHECK_CTX(ctx);
+  const uint32_t *a_mx = ctx->gemm_a_mx, *b_mx = ctx->gemm_b_mx;  // agrs_gemm_operand_absmax: consumed by this call
+  ctx->gemm_a_mx = ctx->gemm_b_mx = nullptr;
   AGRS_REQUIRE(ctx, f, AGRS_ERR_INVALID, "agrs_gemm_f32_scatter: null exchange");
   tc2::ScatterArgs sc{};
   float* const* bases = nullptr;
@@ -942,10 +965,15 @@ extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int6
     ctx->last_gemm_path = AGRS_GEMM_TCGEN05;
     agrs_ctx::ProfRec rec;  // timed like every other GEMM launch (bench.py's roofline counts all of them)
     if (int prc = agrs_prof_begin(ctx, AGRS_GEMM_TCGEN05, 2.0 * double(M) * double(N) * double(K), &rec)) return prc;
+    ctx->gemm_a_mx = a_mx;
+    ctx->gemm_b_mx = b_mx;
     const int grc = gemm_tc_2cta_impl(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias, &sc);
+    ctx->gemm_a_mx = ctx->gemm_b_mx = nullptr;
     if (int prc = agrs_prof_end(ctx, rec)) return prc;
     return grc;
   }
+  ctx->gemm_a_mx = a_mx;
+  ctx->gemm_b_mx = b_mx;
   int rc = agrs_gemm_f32(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, N, bias);
   if (rc) return rc;
   return agrs_fused_scatter_f32(f, C, off, size_t(M) * size_t(N));

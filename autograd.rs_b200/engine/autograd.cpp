@@ -23,6 +23,8 @@ Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bia
   const bool fa = ta != a.data->transposed, fb = tb != b.data->transposed;  // memory-level flags
   // memory row pitch: A stored [M,K] (fa=0) -> K, stored [K,M] (fa=1) -> M; B stored [K,N] (fb=0) -> N, [N,K] (fb=1) -> K
   auto out = std::make_shared<Storage>(a.dev(), Shape{M, N});
+  if (a.dev()->gemm_wants_magnitudes(M, N, K))  // fp16 split mode: one magnitude per operand, kept with the buffer
+    a.dev()->check(agrs_gemm_operand_absmax(a.dev()->ctx(), a.data->buf->magnitude(), b.data->buf->magnitude()));
   if (scatter_to) {
     // data-parallel weight gradient: GEMM -> reduce-scatter in one kernel, the epilogue pushes each tile to its owner over NVLink
     a.dev()->check(agrs_gemm_f32_scatter(a.dev()->ctx(), fa, fb, M, N, K, a.data->rptr(), fa ? M : K, b.data->rptr(), fb ? K : N,
@@ -49,6 +51,7 @@ Tensor fresh_like(const Tensor& x) { return Tensor(std::make_shared<Storage>(x.d
 Tensor fwd(const ReLU&, std::vector<Tensor>& xs) {
   auto x = contig(xs.at(0).data);
   auto out = std::make_shared<Storage>(x->dev(), x->shape);
+  out->expect_magnitude_report();
   x->dev()->check(agrs_relu_fwd_f32(x->dev()->ctx(), x->rptr(), out->buf->ptr, size_t(x->len())));  // operators.rs:112-116
   return Tensor(out);
 }
@@ -56,6 +59,7 @@ Tensor fwd(const ReLU&, std::vector<Tensor>& xs) {
 Tensor fwd(const Sigmoid&, std::vector<Tensor>& xs) {
   auto x = contig(xs.at(0).data);
   auto out = std::make_shared<Storage>(x->dev(), x->shape);
+  out->expect_magnitude_report();
   x->dev()->check(agrs_sigmoid_fwd_f32(x->dev()->ctx(), x->rptr(), out->buf->ptr, size_t(x->len())));  // operators.rs:195-200
   return Tensor(out);
 }
@@ -132,6 +136,7 @@ std::vector<Tensor> bwd(const ReLU&, const std::vector<Tensor>& xs, const Tensor
   if (x->len() != g->len())
     throw Panic("relu backward: grad has " + std::to_string(g->len()) + " elements, input " + std::to_string(x->len()), AGRS_ERR_SHAPE);
   auto out = std::make_shared<Storage>(g->dev(), g->shape);
+  out->expect_magnitude_report();
   g->dev()->check(agrs_relu_bwd_f32(g->dev()->ctx(), x->rptr(), g->rptr(), out->buf->ptr, size_t(g->len())));
   return {Tensor(out)};
 }
@@ -146,6 +151,7 @@ std::vector<Tensor> bwd(const Sigmoid&, const std::vector<Tensor>& xs, const Ten
     return {mul_inplace(dx, grad)};
   }
   auto out = std::make_shared<Storage>(x->dev(), x->shape);
+  out->expect_magnitude_report();
   x->dev()->check(agrs_sigmoid_bwd_f32(x->dev()->ctx(), x->rptr(), g->rptr(), out->buf->ptr, size_t(x->len())));
   return {Tensor(out)};
 }
@@ -172,6 +178,7 @@ std::vector<Tensor> bwd(const MeanSquaredError&, const std::vector<Tensor>& xs, 
   const float B = float(p.shapei(0));
   if (p.shape() == t.shape() && p.is_contiguous() && t.is_contiguous() && grad.len() == 1) {
     Tensor out = fresh_like(p);
+    out.data->expect_magnitude_report();
     p.dev()->check(agrs_mse_bwd_f32(p.dev()->ctx(), p.data->rptr(), t.data->rptr(), grad.data->rptr(), B, size_t(p.len()), out.data->buf->ptr));
     return {out};
   }

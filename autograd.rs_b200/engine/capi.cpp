@@ -254,6 +254,7 @@ int agrs_eng_tensor_data_ptr(const agrs_tensor* t, void** p) {
   return guarded([&] {
     need(t, "tensor");
     need(p, "out");
+    t->t.data->buf->mx_valid = false;  // the caller may write through the raw pointer
     *p = t->t.data->buf->ptr;
   });
 }

@@ -78,6 +78,7 @@ void DataParallel::fused_sgd_step(float lr) {
     dirty = false;
   }
   dev_->check(agrs_fused_sgd_step(fused_, lr));
+  for (auto& t : params_) t.data->buf->mx_valid = false;  // the kernel rewrote every parameter (its own slice and the peers' broadcasts)
 }
 
 void DataParallel::shard_rows(int64_t rows, int world, int rank, int64_t* begin, int64_t* end) {

@@ -64,7 +64,9 @@ void sgd_step(const std::vector<Tensor>& params, float lr) {
     Bcast k = broadcast_kind(w.shape, g.shape);
     if (k == Bcast::Leading) throw Panic("SGD: gradient " + shape_str(g.shape) + " broadcasts along rows of " + shape_str(w.shape), AGRS_ERR_UNSUPPORTED);
     // tmp = grad * lr; w -= tmp fused in one pass with the same two roundings
-    w.dev()->check(agrs_sgd_step_f32(w.dev()->ctx(), w.wptr(), g.rptr(), lr, size_t(w.len()), size_t(g.len())));
+    float* wp = w.wptr();
+    if (w.len() == g.len()) w.expect_magnitude_report();  // the updated weights are the next step's GEMM operands
+    w.dev()->check(agrs_sgd_step_f32(w.dev()->ctx(), wp, g.rptr(), lr, size_t(w.len()), size_t(g.len())));
   }
 }
 void SGD::step() { sgd_step(parameters_, lr_); }

@@ -54,7 +54,28 @@ Buffer::Buffer(Device* d, int64_t n_elems) : dev(d), keep(d->weak_from_this().lo
 }
 Buffer::Buffer(Device* d, float* external, int64_t n_elems) : dev(d), keep(d->weak_from_this().lock()), ptr(external), n(n_elems), owned(false) {}
 Buffer::~Buffer() {
+  if (mx) agrs_free(dev->ctx(), mx);
   if (ptr && owned) agrs_free(dev->ctx(), ptr);
+}
+uint32_t* Buffer::mx_slot() {
+  if (!mx) {
+    void* p = nullptr;
+    dev->check(agrs_alloc(dev->ctx(), sizeof(uint32_t), &p));
+    mx = static_cast<uint32_t*>(p);
+  }
+  return mx;
+}
+const uint32_t* Buffer::magnitude() {
+  if (!mx_valid) {
+    dev->check(agrs_absmax_f32(dev->ctx(), ptr, size_t(n), mx_slot()));
+    mx_valid = true;
+  }
+  return mx;
+}
+void Storage::expect_magnitude_report() {
+  if (buf->n < (int64_t(1) << 16) || !dev()->reports_magnitudes()) return;
+  dev()->check(agrs_next_output_absmax(dev()->ctx(), buf->mx_slot()));
+  buf->mx_valid = true;
 }
 
 Storage::Storage(Device* d, const Shape& s) : buf(std::make_shared<Buffer>(d, numel(s))), shape(s) {
@@ -68,6 +89,7 @@ float* Storage::wptr() {
     dev()->check(agrs_copy(dev()->ctx(), nb->ptr, buf->ptr, size_t(buf->n) * sizeof(float)));
     buf = nb;
   }
+  buf->mx_valid = false;  // about to be overwritten
   return buf->ptr;
 }
 

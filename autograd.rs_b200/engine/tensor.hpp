@@ -39,6 +39,9 @@ class Device : public std::enable_shared_from_this<Device> {
   void check(int rc) const;  // non-zero status -> Panic(agrs_last_error)
   void sync() const { check(agrs_sync(ctx_)); }
   void seed(uint64_t s) { rng_state_ = s ? s : 0x9E3779B97F4A7C15ull; }
+  // fp16 split mode of the GEMM: would a product of this shape use operand magnitudes / is this output worth reporting on
+  bool gemm_wants_magnitudes(int64_t M, int64_t N, int64_t K) const { return agrs_gemm_wants_absmax(ctx_, M, N, K) != 0; }
+  bool reports_magnitudes() const { return agrs_gemm_wants_absmax(ctx_, 1 << 20, 1 << 20, 1 << 20) != 0; }
   float next_uniform(float lo, float hi);  // xorshift64*: the reference's init is unseeded (init.rs:27,48); only bounds are contractual
   // MatMul::backward flavour (reference defect D3, operators.rs:183-184): literal by default
   bool matmul_backward_literal = true;
@@ -56,6 +59,13 @@ struct Buffer {
   float* ptr = nullptr;
   int64_t n = 0;
   bool owned = true;             // false: a window into memory owned elsewhere (a parameter living in the data-parallel arena)
+  // Magnitude of the contents (bit pattern of the largest finite |x|), one device word, for the split GEMM's fp16 mode
+  // (agrs_gemm_operand_absmax): reported by the kernel that wrote the buffer, or found by one pass the first time a GEMM asks.
+  // Every write access (Storage::wptr) invalidates it.
+  uint32_t* mx = nullptr;
+  bool mx_valid = false;
+  uint32_t* mx_slot();           // allocates the word on first use
+  const uint32_t* magnitude();   // valid magnitude: the producer's report, else agrs_absmax_f32 now
   Buffer(Device* d, int64_t n_elems);
   Buffer(Device* d, float* external, int64_t n_elems);  // non-owning
   ~Buffer();
@@ -82,6 +92,9 @@ struct Storage {
   std::shared_ptr<Storage> deep_copy() const;              // ArrayD::to_owned / CudaData clone (tensor.rs:148,160)
   std::shared_ptr<Storage> contiguous_copy() const;        // standard-layout copy (materialises a transposed view)
   std::vector<float> to_host() const;                      // logical (row-major) order; blocks
+  // Call right before the ONE elementwise launch that fills this (fresh or just-wptr()'d) storage: that launch then also reports
+  // the magnitude of what it writes (agrs_next_output_absmax).  No-op for small tensors and outside the GEMM's fp16 mode.
+  void expect_magnitude_report();
 };
 using StoragePtr = std::shared_ptr<Storage>;
 

@@ -80,8 +80,9 @@ AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);     
  * transB=0: B is [K,N] (ldb>=N); transB=1: B is stored [N,K] (ldb>=K)   -- dX = G W^T (operators.rs:159)
  * so the reference's materialised t_clone() copies (storage.rs:84-88) never exist on the device.
  * bias != NULL fuses `+ b` of Linear::forward / Conv2D::forward (operators.rs:144, :379) into the epilogue.
- * Large aligned shapes run the TMA + tcgen05 split kernel (f32-faithful: x = hi + lo with hi the tf32 part; hi*hi on the tf32
- * tensor pipe, the two correction terms lo*x + x*lo on bf16 operands by default; finite inputs: <= 1e-5 of max|C|; NaN and
+ * Large aligned shapes run the TMA + tcgen05 split kernel (f32-faithful: with announced operand magnitudes x * 2^s = h + l in
+ * fp16 and three fp16 products; otherwise x = hi + lo with hi the tf32 part, hi*hi on the tf32 tensor pipe and the two
+ * correction terms lo*x + x*lo on bf16 operands; finite inputs: <= 1e-5 of max|C|; NaN and
  * zero propagate as in f32; an inf INPUT -- or a finite one above bf16's largest value, 3.39e38, the top 0.4 % of f32's last
  * binade -- yields a non-finite result that is NaN where f32 gives inf; sums folded across K chunks longer than
  * AGRS_TUNE_TC_KCHUNK flush subnormal results to zero);
@@ -91,6 +92,19 @@ AGRS_API int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int
                   const float* A, int64_t lda, const float* B, int64_t ldb,
                   float* C, int64_t ldc, const float* bias);
 enum agrs_gemm_path { AGRS_GEMM_AUTO = 0, AGRS_GEMM_SIMT = 1, AGRS_GEMM_TCGEN05 = 2, AGRS_GEMM_SKINNY = 3 /* HBM-bound kernels for N <= 32 outputs */ };
+/* Operand magnitudes for the fp16 split mode (AGRS_TUNE_TC_CROSS 4): the bit pattern of the largest finite |x| of A and of B,
+ * each ONE device word the caller keeps with its tensor (what CudaData would carry next to `ptr`, storage.rs:5-8).  Applies to the
+ * next agrs_gemm_f32 / agrs_gemm_f32_scatter call on this context only; that GEMM then scales each operand by one exact power
+ * of two and skips its own two magnitude passes.  Any value >= the true maximum (within ~2^10 of it) serves; NULLs (the default)
+ * let the GEMM find per-row / per-column magnitudes itself.  Ignored by every other mode and path. */
+AGRS_API int agrs_gemm_operand_absmax(agrs_ctx* ctx, const uint32_t* a_bits, const uint32_t* b_bits);
+AGRS_API int agrs_gemm_wants_absmax(agrs_ctx* ctx, int64_t M, int64_t N, int64_t K); /* 1 when a GEMM of this shape would use them under the current tuning */
+/* out_bits[0] = bit pattern of max finite |x[i]| (0 for n == 0): the stand-alone pass for tensors no producer reported on */
+AGRS_API int agrs_absmax_f32(agrs_ctx* ctx, const float* x, size_t n, uint32_t* out_bits);
+/* The NEXT elementwise launch on this context (relu / sigmoid forward and backward, mse_bwd, scalar and same-length binary ops,
+ * neg, powi, sgd_step without broadcast) also reports the magnitude of what it writes into out_bits[0] -- the producer touches
+ * every element anyway, so the GEMM that consumes its output needs no pass of its own.  One request serves one call. */
+AGRS_API int agrs_next_output_absmax(agrs_ctx* ctx, uint32_t* out_bits);
 AGRS_API int agrs_set_gemm_path(agrs_ctx* ctx, int path); /* tests/bench: force one path; TCGEN05 on unaligned operands -> AGRS_ERR_UNSUPPORTED */
 AGRS_API int agrs_last_gemm_path(agrs_ctx* ctx);          /* path the most recent agrs_gemm_f32 took */
 /* kernel tuning knobs (tests, benches, profiling); never change results beyond f32 rounding */
@@ -106,7 +120,10 @@ enum agrs_tuning_key {
                                    3 = no tf32 pass: x = bf16 + bf16, three bf16 products (6 MMA slots per k-block instead of 8,
                                    representation error ~4e-6 instead of ~1e-6).  4 = x scaled per row of op(A) / column of op(B) by an
                                    exact power of two, then fp16 + fp16: three fp16 products, representation error ~7e-8, preceded by two
-                                   small absmax kernels per launch.  Default 1; env AGRS_TC_CROSS overrides it at context creation */
+                                   small absmax kernels per launch -- unless the caller announced one magnitude per operand
+                                   (agrs_gemm_operand_absmax), which then serve as the scales.  5 (default) = mode 4 for calls with
+                                   announced magnitudes, mode 1 for calls without: no magnitude pass ever runs.  Env AGRS_TC_CROSS
+                                   overrides the default at context creation */
   AGRS_TUNE_TC_EPI_TMA = 7,     /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
                                    folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
   AGRS_TUNE_TC_REUSE_SCALES = 8 /* cross mode 4, measurement aid: 1 = skip the absmax kernels and reuse the operand magnitudes the previous

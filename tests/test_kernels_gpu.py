@@ -495,3 +495,114 @@ def test_fused_scatter_and_step_single_rank(ctx):
         ctx.check(L.agrs_fused_scatter_f32(f, dg.ptr, 2, 37))  # offsets must be multiples of 4
     L.agrs_fused_destroy(f)
     ctx.call("agrs_peer_free", arena)
+
+
+# ------------------------------------------------------------------ operand magnitudes for the GEMM's fp16 split mode
+def _bits_of_max(a):
+    a = np.asarray(a, np.float32).reshape(-1)
+    fin = np.abs(a[np.isfinite(a)])
+    return int(np.float32(fin.max() if fin.size else 0.0).view(np.uint32))
+
+
+def _read_u32(ctx, buf):
+    return int(ctx.to_host(buf, (1,)).view(np.uint32)[0])
+
+
+@pytest.mark.parametrize("n", [1, 5, 1024, 4099, 1 << 20])
+def test_absmax_pass_and_producer_reports(ctx, n):
+    """agrs_absmax_f32 and the by-product of agrs_next_output_absmax equal the bit pattern of max finite |x| (exact: a maximum
+    has no rounding), ignore inf / NaN, and one request serves exactly one launch."""
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 3).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    if n > 4:
+        x[1], x[3] = np.inf, np.nan
+    dx, dg, dy, slot = ctx.to_device(x), ctx.to_device(g), ctx.empty(n), ctx.empty(1)
+    ctx.call("agrs_absmax_f32", dx.ptr, n, slot.ptr)
+    assert _read_u32(ctx, slot) == _bits_of_max(x)
+    with np.errstate(all="ignore"):
+        cases = [
+            ("agrs_relu_fwd_f32", (dx.ptr, dy.ptr, n), np.where(x > 0, x, 0).astype(np.float32)),
+            ("agrs_relu_bwd_f32", (dx.ptr, dg.ptr, dy.ptr, n), np.where(x <= 0, 0, g).astype(np.float32)),
+            ("agrs_neg_f32", (dy.ptr, dx.ptr, n), -x),
+            ("agrs_scalar_f32", (K.SMUL if hasattr(K, "SMUL") else 0, dy.ptr, dx.ptr, 0.5, n), x * np.float32(0.5)),
+            ("agrs_sgd_step_f32", (dg.ptr, dx.ptr, 0.25, n, n), None),
+        ]
+    for name, args, want in cases:
+        ctx.call("agrs_fill_f32", slot.ptr, 123.0, 1)      # garbage: the library zeroes the word itself
+        ctx.call("agrs_next_output_absmax", slot.ptr)
+        ctx.call(name, *args)
+        got_bits = _read_u32(ctx, slot)
+        out = ctx.to_host(dg if name == "agrs_sgd_step_f32" else dy, (n,))
+        if want is not None:
+            assert np.array_equal(out, want, equal_nan=True), name
+        assert got_bits == _bits_of_max(out), name
+        # consumed: the next launch reports nowhere
+        ctx.call("agrs_fill_f32", slot.ptr, 7.0, 1)
+        ctx.call("agrs_relu_fwd_f32", dx.ptr, dy.ptr, n)
+        assert float(ctx.to_host(slot, (1,))[0]) == 7.0
+
+
+@pytest.mark.parametrize("M,N,Kd,ta,tb", [(512, 512, 512, 0, 0), (1000, 520, 3000, 1, 0), (384, 1000, 520, 0, 1), (2048, 256, 4100, 1, 1)])
+def test_gemm_fp16_mode_with_caller_magnitudes(ctx, M, N, Kd, ta, tb):
+    """cross mode 4 with one magnitude per operand (agrs_gemm_operand_absmax): <= 1e-5 of max|C| against the f64 product, rows of
+    very different size in one operand included; the announcement serves one call (the next one finds its own per-row scales)."""
+    rng = np.random.default_rng(M + N)
+    A = rng.uniform(-1, 1, (Kd, M) if ta else (M, Kd)).astype(np.float32)
+    B = rng.uniform(-1, 1, (N, Kd) if tb else (Kd, N)).astype(np.float32)
+    A[:: 7] *= np.float32(1e-3)          # strips 1000x smaller than the tensor maximum share its scale
+    B *= np.float32(37.5)
+    dA, dB, dC, sa, sb = ctx.to_device(A), ctx.to_device(B), ctx.empty(M * N), ctx.empty(1), ctx.empty(1)
+    ctx.call("agrs_absmax_f32", dA.ptr, A.size, sa.ptr)
+    ctx.call("agrs_absmax_f32", dB.ptr, B.size, sb.ptr)
+    truth = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+    import ctypes as C
+    before = C.c_int64()
+    ctx.call("agrs_get_tuning", K.TUNE_TC_CROSS, C.byref(before))
+    ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, 4)
+    ctx.call("agrs_set_gemm_path", K.GEMM_TCGEN05)
+    try:
+        assert ctx.L.agrs_gemm_wants_absmax(ctx.h, M, N, Kd) == 1
+        for announce in (True, False):
+            if announce:
+                ctx.call("agrs_gemm_operand_absmax", sa.ptr, sb.ptr)
+            ctx.call("agrs_gemm_f32", ta, tb, M, N, Kd, dA.ptr, A.shape[1], dB.ptr, B.shape[1], dC.ptr, N, None)
+            got = ctx.to_host(dC, (M, N))
+            assert np.abs(got - truth).max() / np.abs(truth).max() < 1e-5, announce
+    finally:
+        ctx.call("agrs_set_gemm_path", K.GEMM_AUTO)
+        ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, before.value)
+    assert ctx.L.agrs_gemm_wants_absmax(ctx.h, M, N, Kd) == (1 if before.value in (4, 5) else 0)
+    ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, 1)
+    assert ctx.L.agrs_gemm_wants_absmax(ctx.h, M, N, Kd) == 0
+    ctx.call("agrs_set_tuning", K.TUNE_TC_CROSS, before.value)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("lo_side", ["a", "b"])
+def test_gemm_fp16_mode_exact_with_announced_magnitudes(ctx, ta, tb, lo_side):
+    """The known-answer construction of test_gemm_pair_cross_terms_exact through the DEFAULT tuning (mode 5) with one announced
+    magnitude per operand: the fp16 split must reproduce the f64 product bit for bit (the scales are exact powers of two)."""
+    M, N, Kd = 512, 384, 160
+    rng = np.random.default_rng(5 + 2 * ta + tb)
+    s = rng.choice(np.array([-2.0, -1.0, 1.0, 2.0]), (M, Kd) if lo_side == "a" else (Kd, N))
+    c = rng.integers(0, 4, s.shape)
+    split = (s * (1.0 + c * 2.0 ** -12)).astype(np.float32)
+    ints = rng.integers(-3, 4, (Kd, N) if lo_side == "a" else (M, Kd)).astype(np.float32)
+    opA, opB = (split, ints) if lo_side == "a" else (ints, split)
+    truth = opA.astype(np.float64) @ opB.astype(np.float64)
+    A = np.ascontiguousarray(opA.T) if ta else opA
+    B = np.ascontiguousarray(opB.T) if tb else opB
+    dA, dB, dC, sa, sb = ctx.to_device(A), ctx.to_device(B), ctx.empty(M * N), ctx.empty(1), ctx.empty(1)
+    ctx.call("agrs_absmax_f32", dA.ptr, A.size, sa.ptr)
+    ctx.call("agrs_absmax_f32", dB.ptr, B.size, sb.ptr)
+    if tuning(ctx, K.TUNE_TC_CROSS) not in (4, 5):
+        pytest.skip("the context's default split mode does not use magnitudes")
+    ctx.call("agrs_set_gemm_path", K.GEMM_TCGEN05)
+    try:
+        ctx.call("agrs_gemm_operand_absmax", sa.ptr, sb.ptr)
+        ctx.call("agrs_gemm_f32", ta, tb, M, N, Kd, dA.ptr, A.shape[1], dB.ptr, B.shape[1], dC.ptr, N, None)
+    finally:
+        ctx.call("agrs_set_gemm_path", K.GEMM_AUTO)
+    got = ctx.to_host(dC, (M, N))
+    assert np.array_equal(got.astype(np.float64), truth), float(np.abs(got - truth).max())
