@@ -76,7 +76,11 @@ def lib():
             "agrs_peer_export": [vp, vp, vp],
             "agrs_peer_open": [vp, vp, C.POINTER(vp)],
             "agrs_peer_close": [vp, vp],
-            "agrs_fused_create": [vp, i32, i32, C.POINTER(vp), sz, sz, sz, C.POINTER(vp)],
+            "agrs_fused_create": [vp, i32, i32, C.POINTER(vp), sz, sz, sz, i32, C.POINTER(vp)],
+            "agrs_fused_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+            "agrs_fused_begin_step": [vp, f32],
+            "agrs_fused_bucket_ready": [vp, i32, sz, sz],
+            "agrs_fused_finish_step": [vp],
             "agrs_fused_destroy": [vp],
             "agrs_fused_sgd_step": [vp, f32],
             "agrs_fused_scatter_f32": [vp, vp, sz, sz],
@@ -101,6 +105,9 @@ def lib():
             "agrs_sigmoid_bwd_f32": [vp, vp, vp, vp, sz],
             "agrs_mse_fwd_f32": [vp, vp, vp, sz, vp],
             "agrs_mse_bwd_f32": [vp, vp, vp, vp, f32, sz, vp],
+            "agrs_relu_bwd_colsum_f32": [vp, vp, vp, vp, i64, i64, vp],
+            "agrs_sigmoid_bwd_colsum_f32": [vp, vp, vp, vp, i64, i64, vp],
+            "agrs_mse_bwd_colsum_f32": [vp, vp, vp, vp, f32, i64, i64, vp, vp],
             "agrs_binary_f32": [vp, i32, vp, vp, vp, sz, sz, i32],
             "agrs_scalar_f32": [vp, i32, vp, vp, f32, sz],
             "agrs_neg_f32": [vp, vp, vp, sz],
@@ -129,6 +136,8 @@ def lib():
         L.agrs_graph_info.restype = i32
         L.agrs_fused_flag_floats.argtypes = []
         L.agrs_fused_flag_floats.restype = C.c_size_t
+        L.agrs_fused_max_buckets.argtypes = []
+        L.agrs_fused_max_buckets.restype = i32
         L.agrs_version.argtypes = []
         L.agrs_version.restype = C.c_char_p
         _lib = L

@@ -3,6 +3,7 @@
 // independent accesses in flight per thread, grid = a multiple of the SM count (persistent
 // grid-stride).  Streaming cache hints: nothing here is re-read by the same kernel.
 #include "agrs_internal.h"
+#include "mag.cuh"
 
 namespace {
 
@@ -13,21 +14,6 @@ constexpr int kBlocksPerSM = 8;
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 
-// ---- optional by-product: the largest finite |out[i]| as its bit pattern (agrs_next_output_absmax) ----
-// The split GEMM's fp16 mode scales each operand by a power of two taken from its largest magnitude; a producer that already
-// touches every element reports it for free instead of a separate pass over the tensor.  Non-finite values are left out (the
-// scale must serve the finite ones; inf / NaN stay non-finite whatever the scale).  Unsigned compare == float compare for
-// magnitudes, and a maximum does not depend on the order: deterministic.
-__device__ __forceinline__ uint32_t mag_bits(float v) {
-  const uint32_t b = __float_as_uint(v) & 0x7FFFFFFFu;
-  return b < 0x7F800000u ? b : 0u;
-}
-__device__ __forceinline__ uint32_t mag4(uint32_t m, float4 r) { return max(max(m, mag_bits(r.x)), max(max(mag_bits(r.y), mag_bits(r.z)), mag_bits(r.w))); }
-__device__ __forceinline__ void mag_commit(uint32_t m, uint32_t* slot) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-  if ((threadIdx.x & 31) == 0 && m) atomicMax(slot, m);
-}
 
 // ---- functors (semantics cited from the reference) ----
 struct ReluFwd {  // functional_ndarray.rs:14-22: x > 0 ? x : 0  (-0.0, NaN -> +0.0)
@@ -202,18 +188,10 @@ int grid_for(agrs_ctx* ctx, size_t work_items, int per_thread) {
   return int(blocks);
 }
 
-// the slot of a pending agrs_next_output_absmax request, zeroed on the stream and consumed (one request serves one call)
-int take_mx(agrs_ctx* ctx, uint32_t** slot) {
-  *slot = ctx->next_out_mx;
-  ctx->next_out_mx = nullptr;
-  if (*slot) AGRS_CUDA(ctx, cudaMemsetAsync(*slot, 0, sizeof(uint32_t), ctx->stream));
-  return AGRS_OK;
-}
-
 template <class F>
 int launch_unary(agrs_ctx* ctx, F f, float* out, const float* a, size_t n) {
   uint32_t* mx = nullptr;
-  if (int rc = take_mx(ctx, &mx)) return rc;
+  if (int rc = agrs_take_mx(ctx, &mx)) return rc;
   if (n == 0) return AGRS_OK;
   size_t n4 = (agrs_aligned16(out) && agrs_aligned16(a)) ? n / 4 : 0;
   if (n4) {
@@ -232,7 +210,7 @@ int launch_unary(agrs_ctx* ctx, F f, float* out, const float* a, size_t n) {
 template <class F>
 int launch_binary(agrs_ctx* ctx, F f, float* out, const float* a, const float* b, size_t n) {
   uint32_t* mx = nullptr;
-  if (int rc = take_mx(ctx, &mx)) return rc;
+  if (int rc = agrs_take_mx(ctx, &mx)) return rc;
   if (n == 0) return AGRS_OK;
   size_t n4 = (agrs_aligned16(out) && agrs_aligned16(a) && agrs_aligned16(b)) ? n / 4 : 0;
   if (n4) {

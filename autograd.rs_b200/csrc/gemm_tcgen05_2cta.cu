@@ -358,15 +358,16 @@ __global__ void __launch_bounds__(256) k_absmax_cols(const float* __restrict__ X
 }
 
 // GEMM -> reduce-scatter (data-parallel weight gradients, csrc/fused_dp.cu): with SCATTER the epilogue also pushes every finished
-// 32-column piece of C to the rank that owns it -- element e = off + row*N + col of the flat parameter space belongs to rank
-// e / shard, which keeps one slot per source rank -- with P2P stores over NVLink, tile by tile, while the tensor cores are already
-// on the next tile.
+// 32-column piece of C to the rank that owns it -- element e = off + row*N + col of the flat parameter space lies in granule
+// e >> gshift, which belongs to rank granule % world; every owner keeps one slot per source rank -- with P2P stores over NVLink,
+// tile by tile, while the tensor cores are already on the next tile.
 struct ScatterArgs {
   float* base[16];  // arena of every rank as mapped here
   int world, rank;
   size_t g_off;     // float offset of the gradient region in an arena
-  size_t shard;     // floats per owner (a multiple of 32)
+  size_t shard;     // floats per owner (a multiple of the granule)
   size_t off;       // float offset of C inside the flat parameter space (a multiple of 32)
+  int gshift;       // log2 of the ownership granule in floats (>= 5)
 };
 
 template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
@@ -732,12 +733,14 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             float* dst = Cs + row * lds + col0;
             float* push = nullptr;  // where the finished piece also goes: this rank's slot at the piece's owner
             if (SCATTER && c0 + kb_per_chunk >= w.kb1) {
-              // ownership is interleaved in granules of 32 floats: granule g of the flat parameter space belongs to rank g % world
-              // and is the (g / world)-th granule of that rank's slice -- the eight pieces a thread pushes per tile row go to
-              // eight different ranks, so no rank's NVLink ingress is everybody's target
-              const size_t g = (sc.off + size_t(row) * size_t(N) + size_t(col0)) >> 5;
+              // ownership is interleaved in granules of 2^gshift floats (64 KB by default: a few rows of C): granule g of the flat
+              // parameter space belongs to rank g % world and is the (g / world)-th granule of that rank's slice -- the 32 rows of
+              // an epilogue warp spread over all ranks, so no rank's NVLink ingress is everybody's target
+              const size_t e = sc.off + size_t(row) * size_t(N) + size_t(col0);
+              const size_t g = e >> sc.gshift;
               const size_t owner = g % size_t(sc.world);
-              push = sc.base[owner] + sc.g_off + size_t(sc.rank) * sc.shard + ((g / size_t(sc.world)) << 5);
+              push = sc.base[owner] + sc.g_off + size_t(sc.rank) * sc.shard + ((g / size_t(sc.world)) << sc.gshift) +
+                     (e & ((size_t(1) << sc.gshift) - 1));
             }
             if (vec_s && col0 + 32 <= N) {
               float4 base[8];
@@ -940,7 +943,7 @@ int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t 
 }
 
 // fused_dp.cu
-void agrs_fused_scatter_target(const agrs_fused* f, float* const** bases, int* world, int* rank, size_t* g_off, size_t* shard);
+void agrs_fused_scatter_target(const agrs_fused* f, float* const** bases, int* world, int* rank, size_t* g_off, size_t* shard, int* gshift);
 
 extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                                      const float* B, int64_t ldb, float* C, const float* bias, agrs_fused* f, size_t off) {
@@ -950,7 +953,7 @@ extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int6
   AGRS_REQUIRE(ctx, f, AGRS_ERR_INVALID, "agrs_gemm_f32_scatter: null exchange");
   tc2::ScatterArgs sc{};
   float* const* bases = nullptr;
-  agrs_fused_scatter_target(f, &bases, &sc.world, &sc.rank, &sc.g_off, &sc.shard);
+  agrs_fused_scatter_target(f, &bases, &sc.world, &sc.rank, &sc.g_off, &sc.shard, &sc.gshift);
   for (int p = 0; p < sc.world; ++p) sc.base[p] = bases[p];
   sc.off = off;
   // the pair kernel's vector epilogue must own whole 32-float pieces that never straddle two owners

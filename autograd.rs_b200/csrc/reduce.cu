@@ -3,10 +3,69 @@
 // All reductions are deterministic (fixed summation tree, no float atomics): replicas of a
 // data-parallel job stay bit-identical.
 #include "agrs_internal.h"
+#include "mag.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
+
+// ---- sources of the column-sum kernel: a plain tensor, or an activation / loss backward computed on the fly ----
+// The fused sources write the elementwise result AND feed it to the column sum in the same pass: the gradient that ReLU /
+// Sigmoid / MSE backward hand to the Linear layer below is exactly the tensor whose sum over rows that layer needs for db
+// (operators.rs:161), so the separate pass that re-read it disappears.  Same arithmetic as the functors of elementwise.cu.
+struct SrcPlain {
+  const float* x;
+  static constexpr bool kWrites = false;
+  __device__ float4 at4(int64_t e) const { return __ldcs(reinterpret_cast<const float4*>(x + e)); }
+  __device__ float at1(int64_t e) const { return __ldcs(x + e); }
+};
+struct SrcReluBwd {  // functional_ndarray.rs:23-34: x <= 0 ? 0 : g
+  const float* x;
+  const float* g;
+  float* out;
+  static constexpr bool kWrites = true;
+  __device__ float4 at4(int64_t e) const {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(x + e)), b = __ldcs(reinterpret_cast<const float4*>(g + e));
+    const float4 r = make_float4(a.x <= 0.f ? 0.f : b.x, a.y <= 0.f ? 0.f : b.y, a.z <= 0.f ? 0.f : b.z, a.w <= 0.f ? 0.f : b.w);
+    __stcs(reinterpret_cast<float4*>(out + e), r);
+    return r;
+  }
+  __device__ float at1(int64_t) const { return 0.f; }
+};
+struct SrcSigmoidBwd {  // operators.rs:219-223: ((1 - s) * s) * g, s recomputed from x
+  const float* x;
+  const float* g;
+  float* out;
+  static constexpr bool kWrites = true;
+  __device__ static float f(float x, float g) {
+    const float s = 1.0f / (1.0f + expf(-x));
+    return ((1.0f - s) * s) * g;
+  }
+  __device__ float4 at4(int64_t e) const {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(x + e)), b = __ldcs(reinterpret_cast<const float4*>(g + e));
+    const float4 r = make_float4(f(a.x, b.x), f(a.y, b.y), f(a.z, b.z), f(a.w, b.w));
+    __stcs(reinterpret_cast<float4*>(out + e), r);
+    return r;
+  }
+  __device__ float at1(int64_t) const { return 0.f; }
+};
+struct SrcMseBwd {  // operators.rs:249-253: ((p - t) * 2.0 / B) * grad
+  const float* p;
+  const float* t;
+  const float* up;
+  float batch;
+  float* out;
+  static constexpr bool kWrites = true;
+  __device__ float f(float a, float b, float u) const { return (((a - b) * 2.0f) / batch) * u; }
+  __device__ float4 at4(int64_t e) const {
+    const float u = __ldg(up);
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(p + e)), b = __ldcs(reinterpret_cast<const float4*>(t + e));
+    const float4 r = make_float4(f(a.x, b.x, u), f(a.y, b.y, u), f(a.z, b.z, u), f(a.w, b.w, u));
+    __stcs(reinterpret_cast<float4*>(out + e), r);
+    return r;
+  }
+  __device__ float at1(int64_t) const { return 0.f; }
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -104,10 +163,10 @@ int launch_reduce_all(agrs_ctx* ctx, L ld, size_t n, bool vec_ok, float scale, f
 // Block = 32 x 8 threads: x covers 128 consecutive inner elements as float4 (or 32 scalars),
 // y strides the reduced axis; grid.y splits `len` into chunks whose partials go to a
 // [chunks, outer*inner] workspace folded by k_fold_chunks (fixed order).
-template <int VEC>
-__global__ void __launch_bounds__(256) k_sum_axis_mid(const float* __restrict__ x, int64_t len, int64_t inner, int64_t chunk_len,
+template <int VEC, class S>
+__global__ void __launch_bounds__(256) k_sum_axis_mid(const S src, int64_t len, int64_t inner, int64_t chunk_len,
                                                       float* __restrict__ part /*[chunks][outer*inner]*/, int64_t out_elems,
-                                                      unsigned int* __restrict__ tickets, float* __restrict__ out) {
+                                                      unsigned int* __restrict__ tickets, float* __restrict__ out, uint32_t* mx) {
   __shared__ float sm[8][32 * VEC + 1];
   __shared__ unsigned int s_ticket;
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -118,33 +177,37 @@ __global__ void __launch_bounds__(256) k_sum_axis_mid(const float* __restrict__ 
   float acc[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  uint32_t m = 0;  // magnitude of what a writing source produces (agrs_next_output_absmax), when asked for
   if (col < inner) {
-    const float* base = x + o * len * inner + col;
+    const int64_t base = o * len * inner + col;
     int64_t l = l0 + ty;
     if (VEC == 4) {  // four independent 16-byte loads in flight per thread (rows l, l+8, l+16, l+24)
       for (; l + 24 < l1; l += 32) {
-        float4 v0 = __ldcs(reinterpret_cast<const float4*>(base + l * inner));
-        float4 v1 = __ldcs(reinterpret_cast<const float4*>(base + (l + 8) * inner));
-        float4 v2 = __ldcs(reinterpret_cast<const float4*>(base + (l + 16) * inner));
-        float4 v3 = __ldcs(reinterpret_cast<const float4*>(base + (l + 24) * inner));
+        float4 v0 = src.at4(base + l * inner);
+        float4 v1 = src.at4(base + (l + 8) * inner);
+        float4 v2 = src.at4(base + (l + 16) * inner);
+        float4 v3 = src.at4(base + (l + 24) * inner);
         acc[0] += v0.x; acc[1 % VEC] += v0.y; acc[2 % VEC] += v0.z; acc[3 % VEC] += v0.w;
         acc[0] += v1.x; acc[1 % VEC] += v1.y; acc[2 % VEC] += v1.z; acc[3 % VEC] += v1.w;
         acc[0] += v2.x; acc[1 % VEC] += v2.y; acc[2 % VEC] += v2.z; acc[3 % VEC] += v2.w;
         acc[0] += v3.x; acc[1 % VEC] += v3.y; acc[2 % VEC] += v3.z; acc[3 % VEC] += v3.w;
+        if (S::kWrites && mx) m = mag4(mag4(mag4(mag4(m, v0), v1), v2), v3);
       }
     }
     for (; l < l1; l += 8) {
       if (VEC == 4) {
-        float4 v = __ldcs(reinterpret_cast<const float4*>(base + l * inner));
+        float4 v = src.at4(base + l * inner);
         acc[0] += v.x;
         acc[1 % VEC] += v.y;
         acc[2 % VEC] += v.z;
         acc[3 % VEC] += v.w;
+        if (S::kWrites && mx) m = mag4(m, v);
       } else {
-        acc[0] += __ldcs(base + l * inner);
+        acc[0] += src.at1(base + l * inner);
       }
     }
   }
+  if (S::kWrites && mx) mag_commit(m, mx);  // warp-uniform branch: every lane arrives
 #pragma unroll
   for (int v = 0; v < VEC; ++v) sm[ty][tx * VEC + v] = acc[v];
   __syncthreads();
@@ -264,6 +327,58 @@ __global__ void k_transpose(const float* __restrict__ in, int64_t rows, int64_t 
 
 }  // namespace
 
+// the middle-axis column sum over source S ([outer, len, inner], inner >= 2), one launch, deterministic (see k_sum_axis_mid)
+template <class S>
+static int launch_sum_axis_mid(agrs_ctx* ctx, const S& src, bool vec, int64_t outer, int64_t len, int64_t inner, float* out, uint32_t* mx) {
+  const int64_t out_elems = outer * inner;
+  AGRS_REQUIRE(ctx, outer <= 65535, AGRS_ERR_UNSUPPORTED, "agrs_sum_axis_f32: outer=%lld > 65535 with inner > 1", (long long)outer);
+  int per_block = vec ? 128 : 32;
+  int64_t gx = (inner + per_block - 1) / per_block;
+  // split the reduced axis so the grid fills the machine (>= ~4 blocks per SM), chunks of >= 64 rows
+  int64_t want = (int64_t(ctx->sm_count) * 4 + gx * outer - 1) / (gx * outer);
+  int64_t max_chunks = (len + 63) / 64;
+  int64_t chunks = want < 1 ? 1 : (want > max_chunks ? max_chunks : want);
+  if (chunks > 1024) chunks = 1024;
+  int64_t chunk_len = (len + chunks - 1) / chunks;
+  chunks = (len + chunk_len - 1) / chunk_len;
+  float* part = out;
+  if (chunks > 1) {
+    int rc = agrs_ensure_workspace(ctx, size_t(chunks) * size_t(out_elems) * sizeof(float));
+    if (rc) return rc;
+    part = ctx->workspace;
+  }
+  if (chunks > 1 && size_t(gx * outer) > ctx->tickets_n) {
+    AGRS_NOT_CAPTURING(ctx, "growing the column-sum ticket array (run one ordinary step before capturing)");
+    AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->tickets) AGRS_CUDA(ctx, cudaFree(ctx->tickets));
+    ctx->tickets = nullptr;
+    ctx->tickets_n = 0;
+    size_t n = size_t(gx * outer) < 4096 ? 4096 : size_t(gx * outer);
+    AGRS_CUDA(ctx, cudaMalloc(&ctx->tickets, n * sizeof(unsigned int)));
+    AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, n * sizeof(unsigned int), ctx->stream));
+    ctx->tickets_n = n;
+  }
+  dim3 grid((unsigned)gx, (unsigned)chunks, (unsigned)outer);
+  if (vec)
+    k_sum_axis_mid<4, S><<<grid, 256, 0, ctx->stream>>>(src, len, inner, chunk_len, part, out_elems, ctx->tickets, out, mx);
+  else
+    k_sum_axis_mid<1, S><<<grid, 256, 0, ctx->stream>>>(src, len, inner, chunk_len, part, out_elems, ctx->tickets, out, mx);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+// activation / loss backward fused with the column sum of its result: rows x cols, cols % 4 == 0, 16-byte aligned pointers
+template <class S>
+static int fused_bwd_colsum(agrs_ctx* ctx, const S& src, const char* who, int64_t rows, int64_t cols, const void* p0, const void* p1, const void* p2,
+                            float* colsum) {
+  AGRS_REQUIRE(ctx, rows > 0 && cols > 0 && p0 && p1 && p2 && colsum, AGRS_ERR_INVALID, "%s: null pointer or empty shape", who);
+  AGRS_REQUIRE(ctx, cols % 4 == 0 && agrs_aligned16(p0) && agrs_aligned16(p1) && agrs_aligned16(p2), AGRS_ERR_UNSUPPORTED,
+               "%s: needs cols %% 4 == 0 and 16-byte aligned tensors (use the unfused pair otherwise)", who);
+  uint32_t* mx = nullptr;
+  if (int rc = agrs_take_mx(ctx, &mx)) return rc;
+  return launch_sum_axis_mid(ctx, src, true, 1, rows, cols, colsum, mx);
+}
+
 extern "C" {
 
 int agrs_sum_f32(agrs_ctx* ctx, const float* x, size_t n, float* out1) {
@@ -324,41 +439,23 @@ int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len,
     AGRS_LAUNCHED(ctx);
     return AGRS_OK;
   }
-  AGRS_REQUIRE(ctx, outer <= 65535, AGRS_ERR_UNSUPPORTED, "agrs_sum_axis_f32: outer=%lld > 65535 with inner > 1", (long long)outer);
-  bool vec = (inner % 4 == 0) && agrs_aligned16(x);
-  int per_block = vec ? 128 : 32;
-  int64_t gx = (inner + per_block - 1) / per_block;
-  // split the reduced axis so the grid fills the machine (>= ~4 blocks per SM), chunks of >= 64 rows
-  int64_t want = (int64_t(ctx->sm_count) * 4 + gx * outer - 1) / (gx * outer);
-  int64_t max_chunks = (len + 63) / 64;
-  int64_t chunks = want < 1 ? 1 : (want > max_chunks ? max_chunks : want);
-  if (chunks > 1024) chunks = 1024;
-  int64_t chunk_len = (len + chunks - 1) / chunks;
-  chunks = (len + chunk_len - 1) / chunk_len;
-  float* part = out;
-  if (chunks > 1) {
-    int rc = agrs_ensure_workspace(ctx, size_t(chunks) * size_t(out_elems) * sizeof(float));
-    if (rc) return rc;
-    part = ctx->workspace;
-  }
-  if (chunks > 1 && size_t(gx * outer) > ctx->tickets_n) {
-    AGRS_NOT_CAPTURING(ctx, "growing the column-sum ticket array (run one ordinary step before capturing)");
-    AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->tickets) AGRS_CUDA(ctx, cudaFree(ctx->tickets));
-    ctx->tickets = nullptr;
-    ctx->tickets_n = 0;
-    size_t n = size_t(gx * outer) < 4096 ? 4096 : size_t(gx * outer);
-    AGRS_CUDA(ctx, cudaMalloc(&ctx->tickets, n * sizeof(unsigned int)));
-    AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, n * sizeof(unsigned int), ctx->stream));
-    ctx->tickets_n = n;
-  }
-  dim3 grid((unsigned)gx, (unsigned)chunks, (unsigned)outer);
-  if (vec)
-    k_sum_axis_mid<4><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems, ctx->tickets, out);
-  else
-    k_sum_axis_mid<1><<<grid, 256, 0, ctx->stream>>>(x, len, inner, chunk_len, part, out_elems, ctx->tickets, out);
-  AGRS_LAUNCHED(ctx);
-  return AGRS_OK;
+  const bool vec = (inner % 4 == 0) && agrs_aligned16(x);
+  return launch_sum_axis_mid(ctx, SrcPlain{x}, vec, outer, len, inner, out, nullptr);
+}
+
+int agrs_relu_bwd_colsum_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, int64_t rows, int64_t cols, float* colsum) {
+  AGRS_CHECK_CTX(ctx);
+  return fused_bwd_colsum(ctx, SrcReluBwd{x, g, dx}, "agrs_relu_bwd_colsum_f32", rows, cols, x, g, dx, colsum);
+}
+int agrs_sigmoid_bwd_colsum_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, int64_t rows, int64_t cols, float* colsum) {
+  AGRS_CHECK_CTX(ctx);
+  return fused_bwd_colsum(ctx, SrcSigmoidBwd{x, g, dx}, "agrs_sigmoid_bwd_colsum_f32", rows, cols, x, g, dx, colsum);
+}
+int agrs_mse_bwd_colsum_f32(agrs_ctx* ctx, const float* pred, const float* target, const float* upstream1, float batch, int64_t rows, int64_t cols,
+                            float* out, float* colsum) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, upstream1, AGRS_ERR_INVALID, "agrs_mse_bwd_colsum_f32: null upstream");
+  return fused_bwd_colsum(ctx, SrcMseBwd{pred, target, upstream1, batch, out}, "agrs_mse_bwd_colsum_f32", rows, cols, pred, target, out, colsum);
 }
 
 int agrs_equal_f32(agrs_ctx* ctx, const float* a, const float* b, size_t n, int* host_equal) {

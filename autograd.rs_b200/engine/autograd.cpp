@@ -47,6 +47,29 @@ GradCell* scatter_target(const Tensor& param, int64_t n) {
 
 Tensor fresh_like(const Tensor& x) { return Tensor(std::make_shared<Storage>(x.dev(), x.shape())); }
 
+// f2 fusion: a 2-D gradient [B, O] produced by an activation / loss backward is, in an MLP, what the Linear layer below sums
+// over rows for db -- the producing kernel can leave that sum with the buffer.  Returns the [O] storage to fill, or null.
+StoragePtr wants_colsum(const Storage& like) {
+  if (!like.dev()->fuse_backward_colsum || like.ndim() != 2 || like.transposed) return nullptr;
+  const int64_t rows = like.shape[0], cols = like.shape[1];
+  if (rows < 64 || cols < 32 || cols % 4 != 0) return nullptr;
+  return std::make_shared<Storage>(like.dev(), Shape{cols});
+}
+void leave_colsum(Storage& out, const StoragePtr& cs) {
+  out.buf->colsum = cs;
+  out.buf->colsum_cols = out.shape[1];
+}
+// db = grad.sum_axis(0) (operators.rs:161): taken from the producer when it left one, else one pass over grad
+Tensor rows_sum(const Tensor& grad) {
+  Buffer& b = *grad.data->buf;
+  if (b.colsum && grad.ndim() == 2 && !grad.data->transposed && grad.shapei(1) == b.colsum_cols) {
+    Tensor db(b.colsum);
+    b.colsum.reset();
+    return db;
+  }
+  return grad.sum_axis(0);
+}
+
 // ---------------------------------------------------------------- per-operator forward
 Tensor fwd(const ReLU&, std::vector<Tensor>& xs) {
   auto x = contig(xs.at(0).data);
@@ -137,6 +160,11 @@ std::vector<Tensor> bwd(const ReLU&, const std::vector<Tensor>& xs, const Tensor
     throw Panic("relu backward: grad has " + std::to_string(g->len()) + " elements, input " + std::to_string(x->len()), AGRS_ERR_SHAPE);
   auto out = std::make_shared<Storage>(g->dev(), g->shape);
   out->expect_magnitude_report();
+  if (StoragePtr cs = wants_colsum(*out)) {
+    g->dev()->check(agrs_relu_bwd_colsum_f32(g->dev()->ctx(), x->rptr(), g->rptr(), out->buf->ptr, out->shape[0], out->shape[1], cs->buf->ptr));
+    leave_colsum(*out, cs);
+    return {Tensor(out)};
+  }
   g->dev()->check(agrs_relu_bwd_f32(g->dev()->ctx(), x->rptr(), g->rptr(), out->buf->ptr, size_t(g->len())));
   return {Tensor(out)};
 }
@@ -152,6 +180,11 @@ std::vector<Tensor> bwd(const Sigmoid&, const std::vector<Tensor>& xs, const Ten
   }
   auto out = std::make_shared<Storage>(x->dev(), x->shape);
   out->expect_magnitude_report();
+  if (StoragePtr cs = wants_colsum(*out)) {
+    x->dev()->check(agrs_sigmoid_bwd_colsum_f32(x->dev()->ctx(), x->rptr(), g->rptr(), out->buf->ptr, out->shape[0], out->shape[1], cs->buf->ptr));
+    leave_colsum(*out, cs);
+    return {Tensor(out)};
+  }
   x->dev()->check(agrs_sigmoid_bwd_f32(x->dev()->ctx(), x->rptr(), g->rptr(), out->buf->ptr, size_t(x->len())));
   return {Tensor(out)};
 }
@@ -160,7 +193,7 @@ std::vector<Tensor> bwd(const Linear&, const std::vector<Tensor>& xs, const Tens
   const Tensor &x = xs.at(0), &w = xs.at(1);
   Tensor dx = gemm(grad, false, w, true);   // g.dot(&w.t_clone())   operators.rs:159
   Tensor dw = gemm(x, true, grad, false, nullptr, scatter_target(w, x.shapei(1) * grad.shapei(1)));   // x.t_clone().dot(g)    operators.rs:160
-  Tensor db = grad.sum_axis(0);             // 1-D [O]               operators.rs:161
+  Tensor db = rows_sum(grad);               // 1-D [O]               operators.rs:161 (left by the producer of grad when it could)
   return {dx, dw, db};
 }
 
@@ -179,6 +212,12 @@ std::vector<Tensor> bwd(const MeanSquaredError&, const std::vector<Tensor>& xs, 
   if (p.shape() == t.shape() && p.is_contiguous() && t.is_contiguous() && grad.len() == 1) {
     Tensor out = fresh_like(p);
     out.data->expect_magnitude_report();
+    if (StoragePtr cs = wants_colsum(*out.data)) {
+      p.dev()->check(agrs_mse_bwd_colsum_f32(p.dev()->ctx(), p.data->rptr(), t.data->rptr(), grad.data->rptr(), B, p.shapei(0), p.shapei(1),
+                                             out.data->buf->ptr, cs->buf->ptr));
+      leave_colsum(*out.data, cs);
+      return {out};
+    }
     p.dev()->check(agrs_mse_bwd_f32(p.dev()->ctx(), p.data->rptr(), t.data->rptr(), grad.data->rptr(), B, size_t(p.len()), out.data->buf->ptr));
     return {out};
   }

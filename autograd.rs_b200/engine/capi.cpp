@@ -119,6 +119,12 @@ int agrs_eng_device_seed(agrs_device* d, uint64_t seed) {
     d->dev.seed(seed);
   });
 }
+int agrs_eng_device_set_fusions(agrs_device* d, int backward_colsum) {
+  return guarded([&] {
+    need(d, "device");
+    d->dev.fuse_backward_colsum = backward_colsum != 0;
+  });
+}
 int agrs_eng_device_set_matmul_backward_literal(agrs_device* d, int literal) {
   return guarded([&] {
     need(d, "device");
@@ -533,6 +539,24 @@ int agrs_eng_dp_fused_connect(agrs_dp* dp, const void* handles) {
     need(dp, "dp");
     need(handles, "handles");
     dp->dp.fused_connect(handles);
+  });
+}
+int agrs_eng_dp_fused_disable(agrs_dp* dp) {
+  return guarded([&] {
+    need(dp, "dp");
+    dp->dp.fused_disable();
+  });
+}
+int agrs_eng_dp_fused_begin(agrs_dp* dp, float lr) {
+  return guarded([&] {
+    need(dp, "dp");
+    dp->dp.fused_begin(lr);
+  });
+}
+int agrs_eng_dp_fused_finish(agrs_dp* dp) {
+  return guarded([&] {
+    need(dp, "dp");
+    dp->dp.fused_finish();
   });
 }
 int agrs_eng_dp_fused_sgd_step(agrs_dp* dp, float lr) {

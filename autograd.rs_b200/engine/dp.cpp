@@ -31,14 +31,27 @@ DataParallel::~DataParallel() {
 void DataParallel::fused_prepare(void* handle64) {
   if (arena_) throw Panic("DataParallel::fused_prepare called twice");
   if (params_.empty()) throw Panic("DataParallel::fused_prepare: register the parameters first");
+  // Buckets: a large parameter (a weight matrix) opens one, the small ones that follow (its bias) join it -- the gradients of
+  // one layer become ready together during backward.  Every bucket is a granule*world aligned range of the flat parameter space.
+  granule_log2_ = 14;  // 64 KB granules
+  const int64_t G = int64_t(1) << granule_log2_, GW = G * world_;
+  const int max_buckets = agrs_fused_max_buckets();
   int64_t off = 0;
   for (auto& t : params_) {
     if (t.data->transposed) throw Panic("DataParallel(fused): transposed parameter view", AGRS_ERR_UNSUPPORTED);
-    slots_[t.grad.get()] = Slot{off, t.len()};
+    const bool opens = buckets_.empty() || (t.len() >= (int64_t(1) << 16) && int(buckets_.size()) < max_buckets);
+    if (opens) {
+      off = (off + GW - 1) / GW * GW;
+      buckets_.push_back(Bucket{off, 0, 0, 0});
+    }
+    Bucket& bk = buckets_.back();
+    slots_[t.grad.get()] = Slot{off, t.len(), int(buckets_.size()) - 1};
+    bk.cells += 1;
     off += (t.len() + 63) / 64 * 64;  // 256-byte aligned slots: TMA-mappable, float4-friendly
+    bk.n = off - bk.off;
   }
-  const int64_t q = 4 * int64_t(world_) * 64;
-  region_ = size_t((off + q - 1) / q * q);
+  for (auto& bk : buckets_) bk.n = (bk.n + GW - 1) / GW * GW;
+  region_ = size_t((off + GW - 1) / GW * GW);
   w_off_ = agrs_fused_flag_floats();
   g_off_ = w_off_ + region_;
   void* a = nullptr;
@@ -66,12 +79,45 @@ void DataParallel::fused_connect(const void* handles) {
     }
     dev_->check(agrs_peer_open(dev_->ctx(), static_cast<const char*>(handles) + size_t(p) * AGRS_PEER_HANDLE_BYTES, &peer_maps_[size_t(p)]));
   }
-  dev_->check(agrs_fused_create(dev_->ctx(), world_, rank_, peer_maps_.data(), w_off_, g_off_, region_, &fused_));
+  dev_->check(agrs_fused_create(dev_->ctx(), world_, rank_, peer_maps_.data(), w_off_, g_off_, region_, granule_log2_, &fused_));
   for (auto& c : cells_) c->scatter = fused_;  // from now on the dW GEMMs push their tiles to the owners themselves
+}
+
+void DataParallel::fused_disable() {
+  for (auto& c : cells_) {
+    c->scatter = nullptr;
+    c->scattered = false;
+  }
+  if (fused_) agrs_fused_destroy(fused_);
+  fused_ = nullptr;
+  armed_ = false;
+}
+
+void DataParallel::fused_begin(float lr) {
+  if (!fused_) throw Panic("DataParallel::fused_begin before fused_connect");
+  if (armed_) throw Panic("DataParallel::fused_begin: the previous step was not finished");
+  for (auto& kv : dirty_)
+    if (kv.second) throw Panic("DataParallel::fused_begin: a parameter already holds a gradient of this step (call it before backward)");
+  for (auto& bk : buckets_) bk.ready = 0;
+  dev_->check(agrs_fused_begin_step(fused_, lr));
+  armed_ = true;
+}
+
+void DataParallel::fused_finish() {
+  if (!armed_) throw Panic("DataParallel::fused_finish without fused_begin");
+  for (auto& c : cells_) {
+    bool& dirty = dirty_[c.get()];
+    if (!dirty) throw Panic("called `Option::unwrap()` on a `None` value (DataParallel fused step: a parameter received no gradient)");
+    dirty = false;
+  }
+  dev_->check(agrs_fused_finish_step(fused_));
+  armed_ = false;
+  for (auto& t : params_) t.data->buf->mx_valid = false;  // every parameter was rewritten (own granules by the kernel, the rest by the peers' copies)
 }
 
 void DataParallel::fused_sgd_step(float lr) {
   if (!fused_) throw Panic("DataParallel::fused_sgd_step before fused_connect");
+  if (armed_) throw Panic("DataParallel::fused_sgd_step inside fused_begin / fused_finish");
   for (auto& c : cells_) {
     bool& dirty = dirty_[c.get()];
     if (!dirty) throw Panic("called `Option::unwrap()` on a `None` value (DataParallel fused step: a parameter received no gradient)");
@@ -112,15 +158,21 @@ void DataParallel::on_accumulated(GradCell& cell) {
   if (it == dirty_.end()) return;
   // Averaging is linear and an averaged gradient is identical on every rank, so mean_r(avg + local_r) = avg + mean_r(local_r):
   // reducing after every accumulation (overlap) or once before the optimiser step gives the same result.
-  it->second = true;
+  if (!fused_) it->second = true;
   if (fused_) {  // the gradient joins the arena; the exchange itself is the fused step's job
     const Slot& sl = slots_[&cell];
     const Storage& g = *cell.get();
     if (g.transposed || g.len() != sl.n) throw Panic("DataParallel(fused): gradient does not match its parameter", AGRS_ERR_SHAPE);
+    if (armed_ && it->second) throw Panic("DataParallel(fused, overlapped): a parameter received a second gradient in one step; use fused_sgd_step for that", AGRS_ERR_UNSUPPORTED);
+    it->second = true;
     if (cell.scattered)  // the GEMM that produced it already pushed it, tile by tile
       cell.scattered = false;
-    else                 // bias sums, conv filters, second accumulations: push it now
+    else                 // bias sums, conv filters, split-K results, second accumulations: push it now
       dev_->check(agrs_fused_scatter_f32(fused_, g.rptr(), size_t(sl.off), size_t(sl.n)));
+    if (armed_) {        // the last gradient of a bucket starts that bucket's exchange, under the rest of backward
+      Bucket& bk = buckets_[size_t(sl.bucket)];
+      if (++bk.ready == bk.cells) dev_->check(agrs_fused_bucket_ready(fused_, sl.bucket, size_t(bk.off), size_t(bk.n)));
+    }
     return;
   }
   if (!overlap_ || world_ == 1) return;

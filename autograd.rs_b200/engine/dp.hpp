@@ -34,10 +34,19 @@ class DataParallel : public GradHook {
   // fused_connect  maps the arenas of all ranks (handles gathered by the launcher, world x 64 bytes, rank order);
   // during backward every parameter gradient is pushed into this rank's slot at the ranks that own it: by the epilogue of the
   //                dW GEMM itself (Linear::backward asks for agrs_gemm_f32_scatter) or by on_accumulated (scatter kernel);
-  // fused_sgd_step one kernel: barrier, local sum of the slots, w -= lr * mean(g) on the owned slice, all-gather of the new
-  //                weights (P2P stores), barrier.  p.grad() keeps this rank's LOCAL gradient: the mean is never materialised.
+  // then EITHER, per step,
+  //   fused_begin(lr) before backward: from now on, the moment backward has accumulated (and pushed) every gradient of a BUCKET
+  //                (one layer's W and b, contiguous in the arena) the exchange of that bucket starts on a communication stream --
+  //                local sum of the slots, w -= lr * mean(g) on the owned granules, all-gather by the copy engines -- while the
+  //                backward of the earlier layers keeps the compute stream busy (agrs_fused_bucket_ready);
+  //   fused_finish() after backward: the compute stream waits for what is still in flight (the first layer's exchange);
+  // OR fused_sgd_step(lr) after backward: one kernel (barrier, slot sum, SGD, all-gather with P2P stores, barrier).
+  // p.grad() keeps this rank's LOCAL gradient either way: the mean is never materialised.
   void fused_prepare(void* handle64);
   void fused_connect(const void* handles);
+  void fused_disable();  // a peer could not connect: back to the NCCL exchange (parameters stay in the arena, nothing is pushed)
+  void fused_begin(float lr);
+  void fused_finish();
   void fused_sgd_step(float lr);
   bool fused() const { return fused_ != nullptr; }
 
@@ -52,7 +61,11 @@ class DataParallel : public GradHook {
   bool overlap_ = false;
   std::vector<std::shared_ptr<GradCell>> cells_;
   // fused mode
-  struct Slot { int64_t off = 0, n = 0; };
+  struct Slot { int64_t off = 0, n = 0; int bucket = 0; };
+  struct Bucket { int64_t off = 0, n = 0; int cells = 0, ready = 0; };
+  std::vector<Bucket> buckets_;
+  bool armed_ = false;       // between fused_begin and fused_finish
+  int granule_log2_ = 14;
   std::vector<Tensor> params_;                    // registration order (one per cell)
   std::unordered_map<GradCell*, Slot> slots_;     // float offset of the parameter inside the weight / gradient regions
   float* arena_ = nullptr;

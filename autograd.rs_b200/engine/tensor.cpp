@@ -90,6 +90,7 @@ float* Storage::wptr() {
     buf = nb;
   }
   buf->mx_valid = false;  // about to be overwritten
+  buf->colsum.reset();
   return buf->ptr;
 }
 

@@ -45,6 +45,8 @@ class Device : public std::enable_shared_from_this<Device> {
   float next_uniform(float lo, float hi);  // xorshift64*: the reference's init is unseeded (init.rs:27,48); only bounds are contractual
   // MatMul::backward flavour (reference defect D3, operators.rs:183-184): literal by default
   bool matmul_backward_literal = true;
+  // Fusions across the Operator boundary; same results bit for bit, so on by default; switchable for A/B tests
+  bool fuse_backward_colsum = true;
 
  private:
   agrs_ctx* ctx_ = nullptr;
@@ -66,6 +68,10 @@ struct Buffer {
   bool mx_valid = false;
   uint32_t* mx_slot();           // allocates the word on first use
   const uint32_t* magnitude();   // valid magnitude: the producer's report, else agrs_absmax_f32 now
+  // Sum over rows of the [rows, cols] contents, left here by the backward kernel that wrote the buffer (agrs_*_bwd_colsum_f32)
+  // for the Linear layer below, whose db it is.  Single use: Linear::backward takes it; any write access drops it.
+  std::shared_ptr<struct Storage> colsum;
+  int64_t colsum_cols = 0;
   Buffer(Device* d, int64_t n_elems);
   Buffer(Device* d, float* external, int64_t n_elems);  // non-owning
   ~Buffer();

@@ -58,6 +58,7 @@ def lib():
         "agrs_eng_device_sync": [vp],
         "agrs_eng_device_seed": [vp, C.c_uint64],
         "agrs_eng_device_set_matmul_backward_literal": [vp, i32],
+        "agrs_eng_device_set_fusions": [vp, i32],
         "agrs_eng_tensor_from_host": [vp, vp, pi64, i32, pvp],
         "agrs_eng_tensor_full": [vp, pi64, i32, f32, pvp],
         "agrs_eng_tensor_uniform": [vp, pi64, i32, f32, f32, pvp],
@@ -111,6 +112,9 @@ def lib():
         "agrs_eng_dp_fused_prepare": [vp, vp],
         "agrs_eng_dp_fused_connect": [vp, vp],
         "agrs_eng_dp_fused_sgd_step": [vp, f32],
+        "agrs_eng_dp_fused_begin": [vp, f32],
+        "agrs_eng_dp_fused_finish": [vp],
+        "agrs_eng_dp_fused_disable": [vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -167,6 +171,10 @@ class Device:
     def prefetch_join(self):
         """the compute stream waits for every Tensor.prefetch_from_numpy issued so far"""
         _check(lib().agrs_eng_device_prefetch_join(self._h))
+
+    def set_fusions(self, backward_colsum=True):
+        """operator-boundary fusions (on by default; bit-identical either way): db left by the backward kernel that produced the gradient"""
+        _check(lib().agrs_eng_device_set_fusions(self._h, int(bool(backward_colsum))))
 
     def set_matmul_backward_literal(self, literal):
         _check(lib().agrs_eng_device_set_matmul_backward_literal(self._h, int(bool(literal))))
@@ -774,6 +782,7 @@ class DataParallel:
         assert len(handles) == self.world
         if any(len(h) != 64 for h in handles):
             self.fused_error = err or "a peer could not export its arena"
+            lib().agrs_eng_dp_fused_disable(self._h)
             return False
         try:
             _check(lib().agrs_eng_dp_fused_connect(self._h, b"".join(handles)))
@@ -782,10 +791,20 @@ class DataParallel:
             err, ok = e, b"\x00"
         votes = all_gather(ok)
         if any(v != b"\x01" for v in votes):
+            # this rank may have connected: undo it, or its dW GEMMs would keep pushing tiles to peers that never sum them
             self.fused_error = err or "a peer could not map the arenas"
+            lib().agrs_eng_dp_fused_disable(self._h)
             return False
         self.fused = True
         return True
+
+    def fused_begin(self, lr):
+        """before backward: every layer's reduce-scatter + SGD + all-gather then starts the moment backward has produced that
+        layer's gradients and overlaps the backward of the earlier layers (call fused_finish after backward)"""
+        _check(lib().agrs_eng_dp_fused_begin(self._h, float(lr)))
+
+    def fused_finish(self):
+        _check(lib().agrs_eng_dp_fused_finish(self._h))
 
     def fused_sgd_step(self, lr):
         """reduce-scatter(grad) + w -= lr * mean(grad) + all-gather(w) in one kernel; replaces sync_grads() and SGD.step()"""

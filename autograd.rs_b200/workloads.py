@@ -73,7 +73,8 @@ class Trainer:
     """One training iteration exactly as the reference's examples spell it (fit_sine.rs:64-93):
     forward -> MSE -> backward -> [average gradients over ranks] -> SGD step -> zero_grad."""
 
-    def __init__(self, model, lr, dp=None):
+    def __init__(self, model, lr, dp=None, fused_overlap=True):
+        self.fused_overlap = fused_overlap   # fused exchange: per layer under backward (default) or one kernel after it
         self.model = model
         self.params = model.parameters()
         self.optim = F.nn.SGD(self.params, lr)
@@ -83,10 +84,18 @@ class Trainer:
     def step(self, x, t):
         pred = self.model.forward([x.clone()])
         loss = self.loss_layer.forward([pred, t.clone()])
+        if self.dp is not None and self.dp.fused and self.fused_overlap:
+            # exchange over NVLink peer memory, layer by layer under the backward pass: the dW GEMM's epilogue pushes the gradient
+            # tiles to their owners, and as soon as a layer's gradients exist its slot sum + SGD + all-gather run on side streams.
+            # Only the registered parameters exist in this model, so this replaces sync_grads() and optim.step().
+            self.dp.fused_begin(self.optim.lr)
+            loss.backward()
+            self.dp.fused_finish()
+            self.model.zero_grad()
+            return loss
         loss.backward()
         if self.dp is not None and self.dp.fused:
-            # one kernel over NVLink peer memory: reduce-scatter of the gradients + SGD on the owned slice + all-gather of the
-            # weights.  Only the registered parameters exist in this model, so it replaces sync_grads() and optim.step().
+            # the same exchange as ONE kernel after backward (cross-rank barrier, slot sum, SGD, all-gather, barrier)
             self.dp.fused_sgd_step(self.optim.lr)
         else:
             if self.dp is not None:

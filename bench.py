@@ -296,7 +296,7 @@ def run_reference_arm(args, cfg):
 
 
 def workload_config(args, cfg, world):
-    return workload_config_for(args.config, cfg, world, getattr(args, "fused", False), getattr(args, "no_overlap", False))
+    return workload_config_for(args.config, cfg, world, getattr(args, "fused", False), getattr(args, "no_overlap", False), getattr(args, "fused_mono", False))
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -381,10 +381,10 @@ def dp_parity(job):
         oparams = [q.data for l in olayers for q in l.parameters()]
     out = {"workload": f"{layers} x Linear({width},{width}) + sigmoid, global batch {rows} in {world} shards, {steps} steps, lr {lr}",
            "tolerance": 1e-4, "paths": {}}
-    for name, fused in (("nccl", False), ("fused", True)):
+    for name, fused, overlap in (("nccl", False, True), ("fused", True, True), ("fused_one_kernel", True, False)):
         model = W.build_mlp(dev, ws, bs, "sigmoid")
         dp, fused_on = job.data_parallel(model.parameters(), fused)
-        tr = W.Trainer(model, lr, dp=dp)
+        tr = W.Trainer(model, lr, dp=dp, fused_overlap=overlap)
         X, T = F.Tensor.from_numpy(dev, x[b:e]), F.Tensor.from_numpy(dev, t[b:e])
         T.requires_grad = False
         losses = []
@@ -521,7 +521,7 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
     model = W.build_mlp(dev, ws, bs, cfg["act"])
     del ws, bs
     dp, fused_on = job.data_parallel(model.parameters(), args.fused, overlap=not args.no_overlap)
-    tr = W.Trainer(model, cfg["lr"], dp=dp)
+    tr = W.Trainer(model, cfg["lr"], dp=dp, fused_overlap=not args.fused_mono)
 
     x, t = W.mlp_batch(cfg["rows"], cfg["width"], cfg["width"], seed=1, rank=rank)  # this rank's shard of the global batch
     hx, ht = dev.pinned_empty(x.shape), dev.pinned_empty(t.shape)
@@ -563,7 +563,7 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
            "algorithmic_tflops_per_gpu": flops_per_sample(cfg) * cfg["rows"] * steps / (ms * 1e-3) / 1e12,
            "final_loss": final_loss, "pool_used_high_bytes": pool_high, "gpu_launches": launches,
            "roofline": gemm_roofline(dev, g_n, g_ms, g_fl, ms_local), "simt_gemm": {"launches": s_n, "ms": s_ms},
-           "fused": fused_on, "config": workload_config_for(name, cfg, world, fused_on, args.no_overlap)}
+           "fused": fused_on, "config": workload_config_for(name, cfg, world, fused_on, args.no_overlap, args.fused_mono)}
 
     # ---- end to end: host buffers in, loss out, every step ----
     # Every step's X and T come from pinned host memory (268 MB) and its loss goes back to the host.  The copy of step i+1
@@ -609,12 +609,13 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
     return res
 
 
-def workload_config_for(name, cfg, world, fused, no_overlap):
+def workload_config_for(name, cfg, world, fused, no_overlap, fused_mono=False):
     return {"workload": f"{name}: {cfg['layers']} x Linear({cfg['width']},{cfg['width']}) + {cfg['act']} between, MSELoss, SGD; "
                         f"{cfg['rows']} rows per GPU ({ {'mlp4096': 'BASELINE.json configs[1]', 'mlp8192': 'BASELINE.json configs[4], per-GPU shard'}.get(name, 'test-size') })",
             "rows_per_gpu": cfg["rows"], "global_batch": cfg["rows"] * world, "width": cfg["width"], "layers": cfg["layers"],
             "activation": cfg["act"], "lr": cfg["lr"], "parallelism": f"dp{world}",
-            "gradient_exchange": ("none" if world == 1 else ("fused over NVLink peer memory: reduce-scatter pushed from the dW GEMM epilogue / scatter kernel, then one slot-sum + SGD + all-gather kernel" if fused
+            "gradient_exchange": ("none" if world == 1 else (("fused over NVLink peer memory: reduce-scatter pushed from the dW GEMM epilogue / scatter kernel, then one slot-sum + SGD + all-gather kernel after backward" if fused_mono else
+                                                               "fused over NVLink peer memory, per layer under the backward pass: reduce-scatter pushed from the dW GEMM epilogue / scatter kernel, flag round, slot-sum + SGD kernel on a side stream, all-gather by the copy engines") if fused
                                                               else "NCCL all-reduce(avg) per parameter" + ("" if no_overlap else ", overlapped with backward"))),
             "l2": "working set (activations + weights, > 2 GB) is larger than the 126 MB L2; no flush needed"}
 
@@ -713,6 +714,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce gradients after backward instead of during it")
     ap.add_argument("--fused", action="store_true", help="N > 1: one fused reduce-scatter + SGD + all-gather kernel over NVLink peer memory "
                                                          "instead of NCCL all-reduce + SGD (the default)")
+    ap.add_argument("--fused-mono", action="store_true", help="N > 1, fused exchange: ONE kernel after backward instead of per-layer exchanges under backward")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all-reduce per parameter + SGD kernel (the baseline the fused kernel replaces)")
     args = ap.parse_args()
     claim_stdout()

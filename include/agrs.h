@@ -166,6 +166,16 @@ AGRS_API int agrs_mse_fwd_f32(agrs_ctx* ctx, const float* pred, const float* tar
 AGRS_API int agrs_mse_bwd_f32(agrs_ctx* ctx, const float* pred, const float* target, const float* upstream1,
                      float batch, size_t n, float* out);
 
+/* Fusions across the Operator boundary: the gradient that ReLU / Sigmoid / MSE backward hands to the Linear layer
+ * below is the tensor whose sum over rows that layer needs for db (operators.rs:161).  These compute the elementwise result
+ * [rows, cols] AND colsum[c] = sum_r result[r, c] in ONE pass -- the same values, bit for bit, as the unfused pair
+ * (agrs_*_bwd_f32 then agrs_sum_axis_f32(outer 1, len rows, inner cols)): same functors, same summation tree.
+ * Need cols % 4 == 0 and 16-byte aligned tensors (AGRS_ERR_UNSUPPORTED otherwise); honour agrs_next_output_absmax. */
+AGRS_API int agrs_relu_bwd_colsum_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, int64_t rows, int64_t cols, float* colsum);
+AGRS_API int agrs_sigmoid_bwd_colsum_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, int64_t rows, int64_t cols, float* colsum);
+AGRS_API int agrs_mse_bwd_colsum_f32(agrs_ctx* ctx, const float* pred, const float* target, const float* upstream1, float batch,
+                                     int64_t rows, int64_t cols, float* out, float* colsum);
+
 /* ---- tensor arithmetic (src/tensor/storage_arithmetic.rs, src/tensor/utils.rs:16-75) ----
  * out[i] = a[i] (op) b[j],  j = i            when nb == n
  *                           j = i % nb       when bmode == AGRS_BCAST_TRAILING  ([O] or [1,O] onto [B,O]; [1,1] onto anything)
@@ -222,11 +232,17 @@ AGRS_API int agrs_comm_join(agrs_comm* comm);
  * Each rank keeps parameters and parameter gradients in an ARENA: one agrs_peer_alloc block laid out identically on every
  * rank ([flag words | ... weight region at w_off ... | ... gradient region at g_off ...], offsets in floats).  The arenas are
  * exported (agrs_peer_export -> 64-byte handle, exchanged by the launcher) and mapped by every peer (agrs_peer_open).
- * The gradient region of an arena holds one slot per source rank for the slice of the parameter space this rank owns.  During
- * backward every rank pushes its gradients into its slot at the owners (agrs_gemm_f32_scatter from the dW GEMM's epilogue,
- * agrs_fused_scatter_f32 otherwise); agrs_fused_sgd_step then runs ONE kernel per training step: cross-rank barrier, local
- * sum of the slots, w -= lr * mean(g) on the owned slice, all-gather of the updated weights with P2P stores, cross-rank barrier.
- * It replaces all-reduce + agrs_sgd_step_f32 (optim.rs:25-34).  Every rank must call it the same number of times. */
+ * The flat parameter space is dealt out in granules of 2^granule_log2 floats (granule g belongs to rank g % world); the gradient
+ * region of an arena holds one slot per source rank for the slice this rank owns.  During backward every rank pushes its
+ * gradients into its slot at the owners (agrs_gemm_f32_scatter from the dW GEMM's epilogue, agrs_fused_scatter_f32 otherwise).
+ * The step is then finished, replacing all-reduce + agrs_sgd_step_f32 (optim.rs:25-34), in one of two ways:
+ *  - per bucket, overlapped with the rest of backward: agrs_fused_begin_step(lr) before backward; agrs_fused_bucket_ready(b, off, n)
+ *    as soon as every gradient of the contiguous range [off, off+n) (one layer's W and b) has been pushed -- a flag round, then
+ *    on a communication stream the local sum of the slots + w -= lr * mean(g) on the owned granules, then the all-gather of the
+ *    new weights by the copy engines (one strided peer copy per peer); agrs_fused_finish_step() after backward makes the compute
+ *    stream wait for everything that is still in flight;
+ *  - agrs_fused_sgd_step(lr): ONE kernel after backward (cross-rank barrier, slot sum, SGD, all-gather with P2P stores, barrier).
+ * Every rank must make the same calls in the same order. */
 #define AGRS_PEER_HANDLE_BYTES 64
 typedef struct agrs_fused agrs_fused;
 AGRS_API int agrs_peer_alloc(agrs_ctx* ctx, size_t nbytes, void** out);          /* zeroed; plain cudaMalloc (IPC-exportable) */
@@ -235,9 +251,18 @@ AGRS_API int agrs_peer_export(agrs_ctx* ctx, void* ptr, void* handle64);
 AGRS_API int agrs_peer_open(agrs_ctx* ctx, const void* handle64, void** out);    /* maps a PEER's arena into this process */
 AGRS_API int agrs_peer_close(agrs_ctx* ctx, void* ptr);
 AGRS_API size_t agrs_fused_flag_floats(void);                                    /* floats reserved at the start of an arena */
-/* arenas[p]: rank p's arena as mapped here (arenas[rank] = the local block); total: floats per region, multiple of 4*world */
+AGRS_API int agrs_fused_max_buckets(void);
+/* arenas[p]: rank p's arena as mapped here (arenas[rank] = the local block); total: floats per region, a multiple of
+ * 2^granule_log2 * world; granule_log2 in 5 .. 24 (14 = 64 KB granules: whole rows for the copy engines, a few rows of a weight
+ * gradient per granule so that a GEMM tile's pushes still spread over all ranks) */
 AGRS_API int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, size_t w_off, size_t g_off, size_t total,
-                               agrs_fused** out);
+                               int granule_log2, agrs_fused** out);
+/* how this exchange synchronises and moves data: stream memory operations in use, copy streams, all-gather by kernel stores */
+AGRS_API int agrs_fused_info(agrs_fused* f, int* memops, int* copy_streams, int* allgather_kernel);
+AGRS_API int agrs_fused_begin_step(agrs_fused* f, float lr);
+/* bucket < agrs_fused_max_buckets(); off and n multiples of 2^granule_log2 * world */
+AGRS_API int agrs_fused_bucket_ready(agrs_fused* f, int bucket, size_t off, size_t n);
+AGRS_API int agrs_fused_finish_step(agrs_fused* f);
 AGRS_API int agrs_fused_destroy(agrs_fused* f);
 /* the scatter half of the reduce-scatter: push `n` gradient values that belong at float offset `off` of the (flat) parameter
  * space into this rank's slot at their owners.  src is device memory, 16-byte aligned; off a multiple of 4. */

@@ -41,6 +41,10 @@ AGRS_API int agrs_eng_device_sync(agrs_device* dev);
 AGRS_API int agrs_eng_device_seed(agrs_device* dev, uint64_t seed); /* the reference's init is unseeded (init.rs:27,48) */
 /* MatMul::backward flavour: 1 = literal reference (no transposes, defect D3, operators.rs:183-184; default), 0 = mathematically correct */
 AGRS_API int agrs_eng_device_set_matmul_backward_literal(agrs_device* dev, int literal);
+/* Fusions across the Operator boundary, on by default, bit-identical to the unfused path:
+ * backward_colsum: ReLU / Sigmoid / MSE backward of a [B, O] tensor also leaves the sum over rows of its result with the buffer,
+ * which Linear::backward of the layer below takes as db (operators.rs:161) instead of re-reading the gradient. */
+AGRS_API int agrs_eng_device_set_fusions(agrs_device* dev, int backward_colsum);
 
 /* ---- Tensor constructors (tensor.rs:37-92, init.rs:19-49) ---- */
 AGRS_API int agrs_eng_tensor_from_host(agrs_device* dev, const float* host, const int64_t* shape, int ndim, agrs_tensor** out);
@@ -131,17 +135,23 @@ AGRS_API int agrs_eng_dp_register(agrs_dp* dp, agrs_tensor* const* params, int n
 /* all-reduce whatever has not been reduced yet, make the compute stream wait for the communication stream, and turn
  * the sums into means.  Call between backward() and sgd_step(). */
 AGRS_API int agrs_eng_dp_sync_grads(agrs_dp* dp);
-/* Fused optimiser step over NVLink peer memory (agrs_fused_*, agrs.h): ONE kernel does reduce-scatter of the gradients,
- * w -= lr * mean(g) and all-gather of the new weights; it replaces agrs_eng_dp_sync_grads + agrs_eng_sgd_step for the
- * registered parameters.  Set-up, once, after agrs_eng_dp_register:
+/* Fused optimiser step over NVLink peer memory (agrs_fused_*, agrs.h): reduce-scatter of the gradients (pushed by the dW GEMM's
+ * epilogue), w -= lr * mean(g) on the owned slice and all-gather of the new weights; it replaces agrs_eng_dp_sync_grads +
+ * agrs_eng_sgd_step for the registered parameters.  Set-up, once, after agrs_eng_dp_register:
  *   agrs_eng_dp_fused_prepare(dp, handle)   moves the parameters into an exportable arena (their storages are re-pointed: every
  *                                           clone follows) and returns its 64-byte IPC handle;
  *   the launcher gathers the handles of all ranks (world x 64 bytes, rank order);
  *   agrs_eng_dp_fused_connect(dp, handles)  maps the peers' arenas.
- * Then, every iteration: backward(); agrs_eng_dp_fused_sgd_step(dp, lr); zero_grad().  The tensors' grad() keep the LOCAL
- * gradient of this rank (the mean only exists inside the kernel). */
+ * Then, every iteration, either  agrs_eng_dp_fused_begin(dp, lr); backward(); agrs_eng_dp_fused_finish(dp); zero_grad()  -- each
+ * layer's exchange and update start during backward as soon as its gradients exist and overlap the backward of the earlier
+ * layers (every parameter must receive exactly one gradient per step) -- or  backward(); agrs_eng_dp_fused_sgd_step(dp, lr);
+ * zero_grad()  (one kernel after backward).  The tensors' grad() keep the LOCAL gradient of this rank (the mean only exists
+ * inside the kernels).  agrs_eng_dp_fused_disable returns to the NCCL exchange when a peer could not connect. */
 AGRS_API int agrs_eng_dp_fused_prepare(agrs_dp* dp, void* handle64_out);
 AGRS_API int agrs_eng_dp_fused_connect(agrs_dp* dp, const void* handles);
+AGRS_API int agrs_eng_dp_fused_disable(agrs_dp* dp);
+AGRS_API int agrs_eng_dp_fused_begin(agrs_dp* dp, float lr);
+AGRS_API int agrs_eng_dp_fused_finish(agrs_dp* dp);
 AGRS_API int agrs_eng_dp_fused_sgd_step(agrs_dp* dp, float lr);
 /* mean over ranks of a 1-element tensor (the loss value), in place */
 AGRS_API int agrs_eng_dp_mean_scalar(agrs_dp* dp, agrs_tensor* t);

@@ -89,7 +89,7 @@ def test_two_rank_data_parallel_tracks_single_device(tmp_path):
 
 
 # ---- the fused exchange's ownership map (csrc/fused_dp.cu, gemm_tcgen05_2cta.cu), restated in NumPy -----------------------
-GRANULE = 32  # floats
+GRANULE = 32  # floats (agrs_fused_create's granule_log2 = 5; the engine uses 2^14 = 64 KB granules: same maps, see the last test)
 
 
 def _owner_and_index(e, world):
@@ -152,3 +152,26 @@ def test_fused_exchange_emulated_equals_mean_gradient_sgd(world):
     want = w0 - (acc * np.float32(1.0 / world)) * lr
     for r in range(world):
         assert np.array_equal(W[r], W[0]) and np.array_equal(W[r], want)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_bucket_copy_geometry_matches_ownership(world):
+    """The all-gather of the bucket protocol is ONE strided (2-D) peer copy per peer: rows of G floats, pitch G * world, starting
+    at the rank's first granule of the bucket.  With the engine's 64 KB granules that copy must cover exactly the elements the
+    ownership map gives the rank inside a granule*world aligned bucket -- nothing else, nothing twice."""
+    G = 1 << 14
+    off, n = 3 * G * world, 5 * G * world              # a bucket: [off, off + n)
+    e = np.arange(off, off + n)
+    owner = (e // G) % world
+    for r in range(world):
+        rows = (n // G) // world
+        first = off + r * G
+        copied = (first + np.arange(rows)[:, None] * (G * world) + np.arange(G)[None, :]).reshape(-1)
+        assert np.array_equal(np.sort(copied), e[owner == r])
+        # and k_bucket_sgd's (row, j) -> (flat element, slice index) pair lands on the same elements, slice indices contiguous per row
+        g0 = off // G
+        flat = ((g0 + np.arange(rows) * world + r) * G)[:, None] + np.arange(G)[None, :]
+        idx = ((g0 // world + np.arange(rows)) * G)[:, None] + np.arange(G)[None, :]
+        assert np.array_equal(flat.reshape(-1), copied)
+        gg = flat // G
+        assert np.array_equal(((gg // world) * G + flat % G), idx)      # == the scatter side's index for the same element

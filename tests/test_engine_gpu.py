@@ -548,8 +548,9 @@ def test_data_parallel_two_gpus_tracks_oracle():
     assert r.returncode == 0 and "DP PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("overlap", [True, False])
 @pytest.mark.parametrize("width,rows", [(192, 320), (256, 512)])
-def test_fused_optimizer_world1_matches_plain_sgd(dev, width, rows):
+def test_fused_optimizer_world1_matches_plain_sgd(dev, width, rows, overlap):
     """The fused peer-memory step with a single rank: parameters move into the arena (address changes, values and every
     clone follow), gradients reach the exchange slots (192 wide: scatter kernel after the GEMM; 256 wide: pushed by the
     epilogue of the tcgen05 pair GEMM itself), one kernel per step does the slot sum + SGD + broadcast, and the losses are those
@@ -567,11 +568,16 @@ def test_fused_optimizer_world1_matches_plain_sgd(dev, width, rows):
     assert after == sorted(after)  # one arena, registration order
     for p, w0 in zip(params, [a for pair in zip(ws, bs) for a in pair]):
         assert np.array_equal(p.data(), w0)
-    tr = W.Trainer(model, 1e-4, dp=dp)
+    tr = W.Trainer(model, 1e-4, dp=dp, fused_overlap=overlap)   # per bucket under backward / one kernel after backward
     X, Tt = T(dev, x), T(dev, t)
     Tt.requires_grad = False
     n0 = dev.launches()
     got = [tr.step(X, Tt).item() for _ in range(4)]
+    # against the oracle, not only against the device's own plain path (north star tolerance)
+    owant, olayers = O.mlp_train(x, t, ws, bs, "sigmoid", 1e-4, 4, np.float32)
+    assert max(abs(a - c) / abs(c) for a, c in zip(got, owant)) < TOL
+    for p, q in zip(model.parameters(), [q for l in olayers for q in l.parameters()]):
+        assert O.rel_err(p.data(), q.data) < TOL
     # 192 wide: the same kernels in the same order as the plain path -> the same bits.  256 wide: the scattering GEMM never
     # splits K while the plain dW GEMM may (a different, equally valid summation order) -> equal to f32 rounding.
     same = (lambda a, b: np.array_equal(a, b)) if width == 192 else (lambda a, b: np.allclose(a, b, rtol=2e-5, atol=1e-7))
@@ -599,3 +605,26 @@ def test_data_parallel_world1_is_identity(dev):
     got = [tr.step(X, Tt).item() for _ in range(3)]
     dp.close()
     assert got == want
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid"])
+def test_backward_colsum_fusion_changes_no_bit(dev, act):
+    """f2: with the fusion on (default) db comes from the backward kernel that produced the gradient; off, from a separate pass.
+    Losses and every parameter after 3 steps are identical bit for bit, and both track the oracle."""
+    ws, bs = W.mlp_init(3, 256, seed=81)
+    x, t = W.mlp_batch(512, 256, 256, seed=82)
+    runs = []
+    for fused in (True, False):
+        dev.set_fusions(backward_colsum=fused)
+        try:
+            n0 = dev.launches()
+            losses, params, _ = run_device_mlp(dev, x, t, ws, bs, act, 1e-4, 3)
+            runs.append((losses, params, dev.launches() - n0))
+        finally:
+            dev.set_fusions(backward_colsum=True)
+    assert runs[0][0] == runs[1][0]
+    for p, q in zip(runs[0][1], runs[1][1]):
+        assert np.array_equal(p, q)
+    assert runs[0][2] < runs[1][2]   # three column-sum launches per step fewer
+    want, layers = O.mlp_train(x, t, ws, bs, act, 1e-4, 3, np.float32)
+    assert max(abs(a - c) / abs(c) for a, c in zip(runs[0][0], want)) < TOL

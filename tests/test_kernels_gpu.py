@@ -474,7 +474,7 @@ def test_fused_scatter_and_step_single_rank(ctx):
     ctx.call("agrs_peer_alloc", (g_off + total) * 4, C.byref(arena))
     arenas = (C.c_void_p * 1)(arena.value)
     f = C.c_void_p()
-    ctx.call("agrs_fused_create", 1, 0, arenas, w_off, g_off, total, C.byref(f))
+    ctx.call("agrs_fused_create", 1, 0, arenas, w_off, g_off, total, 5, C.byref(f))   # 32-float granules
     rng = np.random.default_rng(5)
     w = rng.standard_normal(total).astype(np.float32)
     g = rng.standard_normal(37).astype(np.float32)
@@ -493,6 +493,24 @@ def test_fused_scatter_and_step_single_rank(ctx):
     assert np.array_equal(got, w - want_slot * np.float32(0.25))
     with pytest.raises(K.AgrsError):
         ctx.check(L.agrs_fused_scatter_f32(f, dg.ptr, 2, 37))  # offsets must be multiples of 4
+    # the bucket protocol on the same exchange: two buckets signalled in backward order, each updates only its own range
+    w1 = got.copy()
+    g2 = rng.standard_normal(total).astype(np.float32)
+    dg2 = ctx.to_device(g2)
+    assert L.agrs_fused_begin_step(f, C.c_float(0.5)) == 0
+    assert L.agrs_fused_scatter_f32(f, dg2.ptr, 0, total) == 0
+    assert L.agrs_fused_bucket_ready(f, 1, 32 * 4, 32 * 5) == 0    # [128, 288)
+    assert L.agrs_fused_bucket_ready(f, 0, 0, 32 * 4) == 0        # [0, 128)
+    with pytest.raises(K.AgrsError):
+        ctx.check(L.agrs_fused_bucket_ready(f, 0, 0, 32 * 4))     # a bucket is signalled once per step
+    assert L.agrs_fused_finish_step(f) == 0
+    ctx.call("agrs_download", got.ctypes.data, arena.value + 4 * w_off, got.nbytes)
+    assert np.array_equal(got, w1 - g2 * np.float32(0.5))
+    with pytest.raises(K.AgrsError):
+        ctx.check(L.agrs_fused_finish_step(f))                    # no open step
+    memops, streams, agk = C.c_int(), C.c_int(), C.c_int()
+    assert L.agrs_fused_info(f, C.byref(memops), C.byref(streams), C.byref(agk)) == 0
+    print("fused exchange: stream memory operations", memops.value, "copy streams", streams.value, "all-gather by kernel", agk.value)
     L.agrs_fused_destroy(f)
     ctx.call("agrs_peer_free", arena)
 
@@ -606,3 +624,39 @@ def test_gemm_fp16_mode_exact_with_announced_magnitudes(ctx, ta, tb, lo_side):
         ctx.call("agrs_set_gemm_path", K.GEMM_AUTO)
     got = ctx.to_host(dC, (M, N))
     assert np.array_equal(got.astype(np.float64), truth), float(np.abs(got - truth).max())
+
+
+# ------------------------------------------------------------------ f2: backward + column sum in one pass
+@pytest.mark.parametrize("rows,cols", [(64, 32), (1000, 520), (8192, 4096), (4097, 36)])
+def test_backward_colsum_fusions_bit_identical(ctx, rows, cols):
+    """agrs_{relu,sigmoid,mse}_bwd_colsum_f32 == the unfused pair (elementwise backward, then agrs_sum_axis_f32 over rows), bit for
+    bit, for the result and for the column sums; the magnitude by-product works through the fused kernels too."""
+    rng = np.random.default_rng(rows + cols)
+    n = rows * cols
+    x = rng.standard_normal(n).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    up = np.array([0.75], np.float32)
+    dx, dg, dup = ctx.to_device(x), ctx.to_device(g), ctx.to_device(up)
+    o1, o2, c1, c2, slot = ctx.empty(n), ctx.empty(n), ctx.empty(cols), ctx.empty(cols), ctx.empty(1)
+    cases = [
+        ("relu", lambda o: ctx.call("agrs_relu_bwd_f32", dx.ptr, dg.ptr, o.ptr, n), lambda o, c: ctx.call("agrs_relu_bwd_colsum_f32", dx.ptr, dg.ptr, o.ptr, rows, cols, c.ptr)),
+        ("sigmoid", lambda o: ctx.call("agrs_sigmoid_bwd_f32", dx.ptr, dg.ptr, o.ptr, n), lambda o, c: ctx.call("agrs_sigmoid_bwd_colsum_f32", dx.ptr, dg.ptr, o.ptr, rows, cols, c.ptr)),
+        ("mse", lambda o: ctx.call("agrs_mse_bwd_f32", dx.ptr, dg.ptr, dup.ptr, float(rows), n, o.ptr),
+         lambda o, c: ctx.call("agrs_mse_bwd_colsum_f32", dx.ptr, dg.ptr, dup.ptr, float(rows), rows, cols, o.ptr, c.ptr)),
+    ]
+    for name, plain, fused in cases:
+        plain(o1)
+        ctx.call("agrs_sum_axis_f32", o1.ptr, 1, rows, cols, c1.ptr)
+        ctx.call("agrs_next_output_absmax", slot.ptr)
+        fused(o2, c2)
+        a, b = ctx.to_host(o1, (n,)), ctx.to_host(o2, (n,))
+        assert np.array_equal(a, b), name
+        assert np.array_equal(ctx.to_host(c1, (cols,)), ctx.to_host(c2, (cols,))), name
+        assert _read_u32(ctx, slot) == _bits_of_max(a), name
+
+
+def test_backward_colsum_refuses_unaligned(ctx):
+    d = ctx.empty(64 * 6)
+    with pytest.raises(K.AgrsError) as e:
+        ctx.call("agrs_relu_bwd_colsum_f32", d.ptr, d.ptr, d.ptr, 64, 6, d.ptr)   # cols % 4 != 0
+    assert e.value.code == 4

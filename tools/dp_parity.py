@@ -27,14 +27,14 @@ def main():
         dist.all_gather_object(out, h)
         return out
 
-    for overlap, fused in ((True, False), (False, False), (True, True)):
+    for overlap, fused, fo in ((True, False, True), (False, False, True), (True, True, True), (True, True, False)):
         ids = [F.comm_unique_id() if rank == 0 else None]   # an NCCL id is good for ONE communicator
         dist.broadcast_object_list(ids, src=0)
         model = W.build_mlp(dev, ws, bs, "sigmoid")
         dp = F.DataParallel(dev, world, rank, ids[0], model.parameters(), overlap=overlap)
         if fused:
             assert dp.enable_fused(all_gather_bytes), dp.fused_error   # parameters move into the peer-mapped arena; one fused kernel per step
-        tr = W.Trainer(model, lr, dp=dp)
+        tr = W.Trainer(model, lr, dp=dp, fused_overlap=fo)
         X, T = F.Tensor.from_numpy(dev, x[b:e]), F.Tensor.from_numpy(dev, t[b:e])
         T.requires_grad = False
         losses = []
@@ -54,7 +54,7 @@ def main():
             want, olayers = O.mlp_train(x, t, ws, bs, "sigmoid", lr, steps, np.float32)
             el = max(abs(a - c) / abs(c) for a, c in zip(losses, want))
             ew = max(O.rel_err(p, q.data) for p, q in zip(params, [q for l in olayers for q in l.parameters()]))
-            print(f"world={world} overlap={overlap} fused={fused}: losses {losses} oracle {want}; max rel err loss {el:.2e} weights {ew:.2e}")
+            print(f"world={world} overlap={overlap} fused={fused} per_layer={fo}: losses {losses} oracle {want}; max rel err loss {el:.2e} weights {ew:.2e}")
             assert el < 1e-4 and ew < 1e-4
         dp.close()
         dist.barrier()

@@ -15,6 +15,8 @@ from autograd_rs_b200 import _capi  # noqa: E402
 
 
 REUSE_SCALES = False
+AUTO = False
+ANNOUNCE = False  # announce one magnitude per operand before every call (what the host engine does): the default mode then runs fp16 x3
 
 
 def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias=False, splitk=0):
@@ -24,11 +26,23 @@ def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_2CTA, pair)
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_KCHUNK, kchunk)
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_SPLITK, splitk)
-    ctx.call("agrs_set_gemm_path", _capi.GEMM_TCGEN05)
+    ctx.call("agrs_set_gemm_path", _capi.GEMM_AUTO if AUTO else _capi.GEMM_TCGEN05)
     dA, dB, dC = ctx.to_device(A), ctx.to_device(B), ctx.empty(M * N)
     dbias = ctx.to_device(bv) if bias else None
     args = (int(ta), int(tb), M, N, K, dA.ptr, A.shape[1], dB.ptr, B.shape[1], dC.ptr, N, dbias.ptr if bias else None)
-    ctx.call("agrs_gemm_f32", *args)
+    if ANNOUNCE:
+        sa, sb = ctx.empty(1), ctx.empty(1)
+        ctx.call("agrs_absmax_f32", dA.ptr, A.size, sa.ptr)
+        ctx.call("agrs_absmax_f32", dB.ptr, B.size, sb.ptr)
+        plain = ctx.call
+
+        def call(name, *a):  # the magnitudes belong to the tensors (computed once); every GEMM call is told about them
+            if name == "agrs_gemm_f32":
+                plain("agrs_gemm_operand_absmax", sa.ptr, sb.ptr)
+            plain(name, *a)
+    else:
+        call = ctx.call
+    call("agrs_gemm_f32", *args)
     got = ctx.to_host(dC, (M, N))
     rows = np.unique(np.concatenate([np.arange(min(M, 4)), np.arange(max(M - 4, 0), M), rng.integers(0, M, check_rows)]))
     opA = (A.T if ta else A)[rows].astype(np.float64)
@@ -38,14 +52,14 @@ def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias
     err = float(np.abs(got[rows] - truth).max() / scale)
     f32 = ((A.T if ta else A)[rows] @ (B.T if tb else B)).astype(np.float64) + (bv if bias else 0.0)
     err32 = float(np.abs(f32 - truth).max() / scale)
-    res = {"M": M, "N": N, "K": K, "ta": int(ta), "tb": int(tb), "pair": pair, "kchunk": kchunk, "splitk": splitk, "bias": bias, "rel_err_vs_f64": err,
+    res = {"M": M, "N": N, "K": K, "ta": int(ta), "tb": int(tb), "pair": pair, "announced_magnitudes": ANNOUNCE, "kchunk": kchunk, "splitk": splitk, "bias": bias, "rel_err_vs_f64": err,
            "numpy_f32_rel_err_vs_f64": err32, "finite": bool(np.isfinite(got).all())}
     if iters:
         for _ in range(3):
-            ctx.call("agrs_gemm_f32", *args)
+            call("agrs_gemm_f32", *args)
         ctx.call("agrs_timer_begin")
         for _ in range(iters):
-            ctx.call("agrs_gemm_f32", *args)
+            call("agrs_gemm_f32", *args)
         import ctypes as C
         ms = C.c_float()
         ctx.call("agrs_timer_end", C.byref(ms))
@@ -72,14 +86,18 @@ def main():
     ap.add_argument("--linear", action="store_true", help="also the Linear fwd/dX/dW shapes of C2 (8192x4096x4096) and C5 (8192x8192x8192)")
     ap.add_argument("--linear-c2", action="store_true", help="only the three Linear shapes of C2")
     ap.add_argument("--reuse-scales", action="store_true", help="cross mode 4: also time the kernel without its absmax passes")
+    ap.add_argument("--announce", action="store_true", help="announce one magnitude per operand before every call, as the host engine does")
+    ap.add_argument("--auto", action="store_true", help="let AUTO path selection choose the kernel instead of forcing the tcgen05 path")
     ap.add_argument("--odd", action="store_true", help="ragged shapes (partial tiles in M, N and K)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kchunk", type=int, default=1024)
     ap.add_argument("--splitk", default="0", help="comma list of forced K splits for the pair kernel (0 = automatic)")
     ap.add_argument("--majors", default="00,01,10", help="ta tb pairs for the square sizes: 00 = X.W, 01 = G.W^T, 10 = X^T.G, 11")
     a = ap.parse_args()
-    global REUSE_SCALES
+    global REUSE_SCALES, ANNOUNCE, AUTO
     REUSE_SCALES = a.reuse_scales
+    ANNOUNCE = a.announce
+    AUTO = a.auto
     pairs = [0, 1] if a.pair == "both" else [int(a.pair)]
     ctx = _capi.Ctx(0)
     rng = np.random.default_rng(0)
