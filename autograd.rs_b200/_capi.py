@@ -76,7 +76,9 @@ def lib():
             "agrs_peer_export": [vp, vp, vp],
             "agrs_peer_open": [vp, vp, C.POINTER(vp)],
             "agrs_peer_close": [vp, vp],
-            "agrs_fused_create": [vp, i32, i32, C.POINTER(vp), sz, sz, sz, i32, C.POINTER(vp)],
+            "agrs_fused_create": [vp, i32, i32, C.POINTER(vp), sz, sz, sz, sz, i32, C.POINTER(vp)],
+            "agrs_fused_weights_offset": [vp, C.POINTER(sz)],
+            "agrs_fused_exposed_ms": [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
             "agrs_fused_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
             "agrs_fused_begin_step": [vp, f32],
             "agrs_fused_bucket_ready": [vp, i32, sz, sz],

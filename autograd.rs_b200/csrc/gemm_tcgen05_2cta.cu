@@ -943,6 +943,7 @@ int agrs_gemm_tc_2cta(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t 
 }
 
 // fused_dp.cu
+extern "C" int agrs_fused_scatter_by_copy(agrs_fused* f);
 void agrs_fused_scatter_target(const agrs_fused* f, float* const** bases, int* world, int* rank, size_t* g_off, size_t* shard, int* gshift);
 
 extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
@@ -964,7 +965,8 @@ extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int6
   // partials are added: that shape keeps the split-K GEMM and pushes the result with the scatter kernel instead.
   const int64_t tiles = ((M + 2 * tc::BM - 1) / (2 * tc::BM)) * ((N + tc2::BN - 1) / tc2::BN);
   const bool wants_split = tc2::choose_splits(tiles, ctx->sm_count / 2, (K + tc::BK - 1) / tc::BK, ctx->tc_splitk) > 1;
-  if (fused_ok && !wants_split) {
+  // when the exchange moves gradients with the copy engines (bucket protocol, default) the GEMM keeps its staged TMA epilogue
+  if (fused_ok && !wants_split && !agrs_fused_scatter_by_copy(f)) {
     ctx->last_gemm_path = AGRS_GEMM_TCGEN05;
     agrs_ctx::ProfRec rec;  // timed like every other GEMM launch (bench.py's roofline counts all of them)
     if (int prc = agrs_prof_begin(ctx, AGRS_GEMM_TCGEN05, 2.0 * double(M) * double(N) * double(K), &rec)) return prc;

@@ -191,8 +191,25 @@ std::vector<Tensor> bwd(const Sigmoid&, const std::vector<Tensor>& xs, const Ten
 
 std::vector<Tensor> bwd(const Linear&, const std::vector<Tensor>& xs, const Tensor& grad) {
   const Tensor &x = xs.at(0), &w = xs.at(1);
+  GradCell* wcell = x.ndim() == 2 && grad.ndim() == 2 ? scatter_target(w, x.shapei(1) * grad.shapei(1)) : nullptr;
+  if (wcell) {
+    // Data-parallel training with the fused exchange: the three results are independent, so the parameter gradients come FIRST
+    // and leave for their owners at once; this layer's exchange (and, weights being double-buffered, its update) then runs
+    // under the dX GEMM below -- for the first layer that is what hides it, nothing follows dX in the backward walk.
+    Tensor dw = gemm(x, true, grad, false, nullptr, wcell);   // x.t_clone().dot(g)    operators.rs:160
+    Tensor db = rows_sum(grad);                               // 1-D [O]               operators.rs:161
+    if (xs.size() > 2) {
+      GradCell* bcell = scatter_target(xs[2], db.len());
+      if (bcell && db.is_contiguous()) {
+        db.dev()->check(agrs_fused_scatter_f32(bcell->scatter, db.data->rptr(), bcell->scatter_off, size_t(db.len())));
+        bcell->scattered = true;
+      }
+    }
+    Tensor dx = gemm(grad, false, w, true);                   // g.dot(&w.t_clone())   operators.rs:159
+    return {dx, dw, db};
+  }
   Tensor dx = gemm(grad, false, w, true);   // g.dot(&w.t_clone())   operators.rs:159
-  Tensor dw = gemm(x, true, grad, false, nullptr, scatter_target(w, x.shapei(1) * grad.shapei(1)));   // x.t_clone().dot(g)    operators.rs:160
+  Tensor dw = gemm(x, true, grad, false);   // x.t_clone().dot(g)    operators.rs:160
   Tensor db = rows_sum(grad);               // 1-D [O]               operators.rs:161 (left by the producer of grad when it could)
   return {dx, dw, db};
 }

@@ -559,6 +559,13 @@ int agrs_eng_dp_fused_finish(agrs_dp* dp) {
     dp->dp.fused_finish();
   });
 }
+int agrs_eng_dp_fused_exposed_ms(agrs_dp* dp, double* total_ms, uint64_t* steps) {
+  return guarded([&] {
+    need(dp, "dp");
+    need(total_ms, "out");
+    *total_ms = dp->dp.fused_exposed_ms(steps);
+  });
+}
 int agrs_eng_dp_fused_sgd_step(agrs_dp* dp, float lr) {
   return guarded([&] {
     need(dp, "dp");

@@ -53,7 +53,8 @@ void DataParallel::fused_prepare(void* handle64) {
   for (auto& bk : buckets_) bk.n = (bk.n + GW - 1) / GW * GW;
   region_ = size_t((off + GW - 1) / GW * GW);
   w_off_ = agrs_fused_flag_floats();
-  g_off_ = w_off_ + region_;
+  w_alt_ = w_off_ + region_;   // second weight region: the exchange writes the new weights where the running step does not read
+  g_off_ = w_alt_ + region_;
   void* a = nullptr;
   dev_->check(agrs_peer_alloc(dev_->ctx(), (g_off_ + region_) * sizeof(float), &a));
   arena_ = static_cast<float*>(a);
@@ -61,6 +62,7 @@ void DataParallel::fused_prepare(void* handle64) {
     const Slot& sl = slots_[t.grad.get()];
     float* dst = arena_ + w_off_ + sl.off;
     dev_->check(agrs_copy(dev_->ctx(), dst, t.data->rptr(), size_t(sl.n) * sizeof(float)));
+    dev_->check(agrs_copy(dev_->ctx(), arena_ + w_alt_ + sl.off, t.data->rptr(), size_t(sl.n) * sizeof(float)));
     t.data->buf = std::make_shared<Buffer>(dev_, dst, sl.n);  // the shared storage cell now points into the arena
     t.grad->scatter_off = size_t(sl.off);
   }
@@ -79,7 +81,7 @@ void DataParallel::fused_connect(const void* handles) {
     }
     dev_->check(agrs_peer_open(dev_->ctx(), static_cast<const char*>(handles) + size_t(p) * AGRS_PEER_HANDLE_BYTES, &peer_maps_[size_t(p)]));
   }
-  dev_->check(agrs_fused_create(dev_->ctx(), world_, rank_, peer_maps_.data(), w_off_, g_off_, region_, granule_log2_, &fused_));
+  dev_->check(agrs_fused_create(dev_->ctx(), world_, rank_, peer_maps_.data(), w_off_, w_alt_, g_off_, region_, granule_log2_, &fused_));
   for (auto& c : cells_) c->scatter = fused_;  // from now on the dW GEMMs push their tiles to the owners themselves
 }
 
@@ -112,7 +114,24 @@ void DataParallel::fused_finish() {
   }
   dev_->check(agrs_fused_finish_step(fused_));
   armed_ = false;
-  for (auto& t : params_) t.data->buf->mx_valid = false;  // every parameter was rewritten (own granules by the kernel, the rest by the peers' copies)
+  repoint_parameters();  // the new weights live in the other region: fresh buffers (no magnitude yet) for every parameter storage
+}
+
+double DataParallel::fused_exposed_ms(uint64_t* steps) {
+  double ms = 0.0;
+  if (fused_) dev_->check(agrs_fused_exposed_ms(fused_, &ms, steps));
+  return ms;
+}
+
+void DataParallel::repoint_parameters() {
+  size_t w_now = 0;
+  dev_->check(agrs_fused_weights_offset(fused_, &w_now));
+  for (auto& t : params_) {
+    const Slot& sl = slots_[t.grad.get()];
+    float* p = arena_ + w_now + sl.off;
+    if (t.data->buf->ptr != p) t.data->buf = std::make_shared<Buffer>(dev_, p, sl.n);
+    else t.data->buf->mx_valid = false;
+  }
 }
 
 void DataParallel::fused_sgd_step(float lr) {

@@ -49,6 +49,7 @@ class DataParallel : public GradHook {
   void fused_finish();
   void fused_sgd_step(float lr);
   bool fused() const { return fused_ != nullptr; }
+  double fused_exposed_ms(uint64_t* steps);  // profiling: time the compute stream waited for the exchange in fused_finish
 
   // rows [begin, end) of a global batch owned by `rank` (equal shards; the remainder goes to the first ranks)
   static void shard_rows(int64_t rows, int world, int rank, int64_t* begin, int64_t* end);
@@ -70,7 +71,8 @@ class DataParallel : public GradHook {
   std::unordered_map<GradCell*, Slot> slots_;     // float offset of the parameter inside the weight / gradient regions
   float* arena_ = nullptr;
   std::vector<void*> peer_maps_;                  // arenas of all ranks as mapped here ([rank] = arena_)
-  size_t w_off_ = 0, g_off_ = 0, region_ = 0;
+  size_t w_off_ = 0, w_alt_ = 0, g_off_ = 0, region_ = 0;  // two weight regions (double-buffered by the bucket protocol), gradient slots
+  void repoint_parameters();   // after a swap of the weight regions: every parameter storage follows
   agrs_fused* fused_ = nullptr;
   std::unordered_map<GradCell*, bool> dirty_;  // holds local contributions that have not been averaged yet
 };

@@ -113,6 +113,7 @@ def lib():
         "agrs_eng_dp_fused_connect": [vp, vp],
         "agrs_eng_dp_fused_sgd_step": [vp, f32],
         "agrs_eng_dp_fused_begin": [vp, f32],
+        "agrs_eng_dp_fused_exposed_ms": [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)],
         "agrs_eng_dp_fused_finish": [vp],
         "agrs_eng_dp_fused_disable": [vp],
     }
@@ -805,6 +806,12 @@ class DataParallel:
 
     def fused_finish(self):
         _check(lib().agrs_eng_dp_fused_finish(self._h))
+
+    def fused_exposed_ms(self):
+        """(total ms, steps): time the compute stream spent waiting for the exchange while Device.profile_enable was on"""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().agrs_eng_dp_fused_exposed_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def fused_sgd_step(self, lr):
         """reduce-scatter(grad) + w -= lr * mean(grad) + all-gather(w) in one kernel; replaces sync_grads() and SGD.step()"""

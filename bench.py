@@ -555,6 +555,7 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
     dev.profile_enable(False)
     g_n, g_ms, g_fl = dev.profile_gemm(_capi.GEMM_TCGEN05)
     s_n, s_ms, s_fl = dev.profile_gemm(_capi.GEMM_SIMT)
+    exposed = dp.fused_exposed_ms() if (dp is not None and fused_on and not args.fused_mono) else None
     ms_local = ms
     ms = job.max_over_ranks(ms)
     final_loss = loss.item()
@@ -563,7 +564,9 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
            "algorithmic_tflops_per_gpu": flops_per_sample(cfg) * cfg["rows"] * steps / (ms * 1e-3) / 1e12,
            "final_loss": final_loss, "pool_used_high_bytes": pool_high, "gpu_launches": launches,
            "roofline": gemm_roofline(dev, g_n, g_ms, g_fl, ms_local), "simt_gemm": {"launches": s_n, "ms": s_ms},
-           "fused": fused_on, "config": workload_config_for(name, cfg, world, fused_on, args.no_overlap, args.fused_mono)}
+           "fused": fused_on,
+           "exchange_exposed_ms_per_step": (job.max_over_ranks(exposed[0] / max(exposed[1], 1)) if exposed else None),
+           "config": workload_config_for(name, cfg, world, fused_on, args.no_overlap, args.fused_mono)}
 
     # ---- end to end: host buffers in, loss out, every step ----
     # Every step's X and T come from pinned host memory (268 MB) and its loss goes back to the host.  The copy of step i+1
@@ -662,6 +665,7 @@ def run_b200_arm(args, cfg):
         "config": head["config"], "algorithmic_tflops_per_gpu": head["algorithmic_tflops_per_gpu"],
         "final_loss": head["final_loss"], "pool_used_high_bytes": head["pool_used_high_bytes"], "clocks": clocks, "e2e": head.get("e2e"),
         "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "simt_gemm": head["simt_gemm"],
+        "exchange_exposed_ms_per_step": head["exchange_exposed_ms_per_step"],
     }
     if also:
         line["also"] = also

@@ -254,9 +254,17 @@ AGRS_API size_t agrs_fused_flag_floats(void);                                   
 AGRS_API int agrs_fused_max_buckets(void);
 /* arenas[p]: rank p's arena as mapped here (arenas[rank] = the local block); total: floats per region, a multiple of
  * 2^granule_log2 * world; granule_log2 in 5 .. 24 (14 = 64 KB granules: whole rows for the copy engines, a few rows of a weight
- * gradient per granule so that a GEMM tile's pushes still spread over all ranks) */
-AGRS_API int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, size_t w_off, size_t g_off, size_t total,
+ * gradient per granule so that a GEMM tile's pushes still spread over all ranks); w_alt: see agrs_fused_weights_offset (0 = none) */
+AGRS_API int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, size_t w_off, size_t w_alt, size_t g_off, size_t total,
                                int granule_log2, agrs_fused** out);
+/* w_alt != 0: a second weight region of the same size (initialised with the same values).  The bucket protocol then reads the
+ * current region and writes the new weights into the other one; agrs_fused_finish_step swaps them and the caller re-points its
+ * parameter tensors (agrs_fused_weights_offset).  Nothing the exchange writes is read by the running step, so a layer's exchange
+ * may start before that layer's dX GEMM has read W. */
+AGRS_API int agrs_fused_weights_offset(agrs_fused* f, size_t* w_off_now);
+/* while agrs_profile_enable is on, agrs_fused_finish_step brackets its waits with CUDA events: the time the compute stream spent
+ * waiting for the exchange, i.e. the part backward did not hide.  Synchronises, returns the sum since the last call and resets. */
+AGRS_API int agrs_fused_exposed_ms(agrs_fused* f, double* total_ms, uint64_t* steps);
 /* how this exchange synchronises and moves data: stream memory operations in use, copy streams, all-gather by kernel stores */
 AGRS_API int agrs_fused_info(agrs_fused* f, int* memops, int* copy_streams, int* allgather_kernel);
 AGRS_API int agrs_fused_begin_step(agrs_fused* f, float lr);

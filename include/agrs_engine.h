@@ -153,6 +153,8 @@ AGRS_API int agrs_eng_dp_fused_disable(agrs_dp* dp);
 AGRS_API int agrs_eng_dp_fused_begin(agrs_dp* dp, float lr);
 AGRS_API int agrs_eng_dp_fused_finish(agrs_dp* dp);
 AGRS_API int agrs_eng_dp_fused_sgd_step(agrs_dp* dp, float lr);
+/* profiling (agrs_profile_enable on): how long the compute stream waited inside agrs_eng_dp_fused_finish since the last call */
+AGRS_API int agrs_eng_dp_fused_exposed_ms(agrs_dp* dp, double* total_ms, uint64_t* steps);
 /* mean over ranks of a 1-element tensor (the loss value), in place */
 AGRS_API int agrs_eng_dp_mean_scalar(agrs_dp* dp, agrs_tensor* t);
 

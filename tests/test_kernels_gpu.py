@@ -474,7 +474,7 @@ def test_fused_scatter_and_step_single_rank(ctx):
     ctx.call("agrs_peer_alloc", (g_off + total) * 4, C.byref(arena))
     arenas = (C.c_void_p * 1)(arena.value)
     f = C.c_void_p()
-    ctx.call("agrs_fused_create", 1, 0, arenas, w_off, g_off, total, 5, C.byref(f))   # 32-float granules
+    ctx.call("agrs_fused_create", 1, 0, arenas, w_off, 0, g_off, total, 5, C.byref(f))   # 32-float granules, single weight region
     rng = np.random.default_rng(5)
     w = rng.standard_normal(total).astype(np.float32)
     g = rng.standard_normal(37).astype(np.float32)
