@@ -499,6 +499,18 @@ int agrs_eng_im2col_backward(const agrs_tensor* col, int64_t h_out, int64_t w_ou
 int agrs_eng_sgd_step(agrs_tensor* const* params, int n, float lr) {
   return guarded([&] { nn::sgd_step(gather(params, n), lr); });
 }
+int agrs_eng_save_parameters(agrs_tensor* const* params, int n, const char* path) {
+  return guarded([&] {
+    need(path, "path");
+    nn::save_parameters(gather(params, n), path);
+  });
+}
+int agrs_eng_load_parameters(agrs_tensor* const* params, int n, const char* path) {
+  return guarded([&] {
+    need(path, "path");
+    nn::load_parameters(gather(params, n), path);
+  });
+}
 int agrs_eng_zero_grad(agrs_tensor* const* params, int n) {
   return guarded([&] { nn::zero_grad(gather(params, n)); });
 }

@@ -1,6 +1,8 @@
 #include "nn.hpp"
 
 #include <cmath>
+#include <cstdio>
+#include <cstring>
 
 namespace agrs {
 std::pair<int64_t, int64_t> calculate_fan_in_and_fan_out(const Shape& s);  // tensor.cpp (init.rs:30-45)
@@ -70,6 +72,69 @@ void sgd_step(const std::vector<Tensor>& params, float lr) {
   }
 }
 void SGD::step() { sgd_step(parameters_, lr_); }
+
+namespace {
+struct File {
+  FILE* f;
+  File(const std::string& path, const char* mode) : f(fopen(path.c_str(), mode)) {
+    if (!f) throw Panic("cannot open " + path);
+  }
+  ~File() { fclose(f); }
+  void put(const void* p, size_t n) {
+    if (n && fwrite(p, 1, n, f) != n) throw Panic("short write while saving parameters");
+  }
+  void get(void* p, size_t n) {
+    if (n && fread(p, 1, n, f) != n) throw Panic("parameter file is truncated");
+  }
+};
+const char kMagic[8] = {'A', 'G', 'R', 'S', 'W', 'T', 'S', '1'};
+}  // namespace
+
+void save_parameters(const std::vector<Tensor>& params, const std::string& path) {
+  File out(path, "wb");
+  out.put(kMagic, 8);
+  const uint32_t count = uint32_t(params.size());
+  out.put(&count, 4);
+  for (auto& p : params) {
+    const uint32_t nd = uint32_t(p.ndim());
+    out.put(&nd, 4);
+    for (auto d : p.shape()) {
+      const uint64_t v = uint64_t(d);
+      out.put(&v, 8);
+    }
+    const std::vector<float> h = p.to_vec();  // logical order, whatever the storage's major
+    out.put(h.data(), h.size() * sizeof(float));
+  }
+}
+
+void load_parameters(const std::vector<Tensor>& params, const std::string& path) {
+  File in(path, "rb");
+  char magic[8];
+  in.get(magic, 8);
+  if (memcmp(magic, kMagic, 8) != 0) throw Panic(path + " is not an AGRSWTS1 parameter file");
+  uint32_t count = 0;
+  in.get(&count, 4);
+  if (count != params.size())
+    throw Panic("parameter file holds " + std::to_string(count) + " tensors, the model has " + std::to_string(params.size()), AGRS_ERR_SHAPE);
+  for (auto& p : params) {
+    uint32_t nd = 0;
+    in.get(&nd, 4);
+    Shape s(nd);
+    for (auto& d : s) {
+      uint64_t v = 0;
+      in.get(&v, 8);
+      d = int64_t(v);
+    }
+    if (s != p.shape()) throw Panic("parameter file has shape " + shape_str(s) + " where the model has " + shape_str(p.shape()), AGRS_ERR_SHAPE);
+    if (p.data->transposed) throw Panic("load_parameters into a transposed view is not supported", AGRS_ERR_UNSUPPORTED);
+    std::vector<float> h(size_t(p.len()));
+    in.get(h.data(), h.size() * sizeof(float));
+    if (!h.empty()) {
+      p.dev()->check(agrs_upload(p.dev()->ctx(), p.data->wptr(), h.data(), h.size() * sizeof(float)));
+      p.dev()->sync();  // `h` is pageable and dies here
+    }
+  }
+}
 
 }  // namespace nn
 }  // namespace agrs

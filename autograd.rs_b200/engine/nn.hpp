@@ -93,5 +93,12 @@ class SGD : public Optimizer {
 };
 void sgd_step(const std::vector<Tensor>& params, float lr);
 
+// Model serialisation (the reference lists it as a TODO: README.md:71).  One self-describing little-endian file:
+//   "AGRSWTS1" | u32 count | per tensor { u32 ndim | u64 dim[ndim] | f32 data[prod(dim)] in logical (row-major) order }
+// save reads the parameters back (blocks); load writes INTO the existing parameter storages (every clone follows, parameters
+// living in a data-parallel arena stay there) and panics on a count / shape mismatch.
+void save_parameters(const std::vector<Tensor>& params, const std::string& path);
+void load_parameters(const std::vector<Tensor>& params, const std::string& path);
+
 }  // namespace nn
 }  // namespace agrs

@@ -59,6 +59,8 @@ def lib():
         "agrs_eng_device_seed": [vp, C.c_uint64],
         "agrs_eng_device_set_matmul_backward_literal": [vp, i32],
         "agrs_eng_device_set_fusions": [vp, i32],
+        "agrs_eng_save_parameters": [pvp, i32, C.c_char_p],
+        "agrs_eng_load_parameters": [pvp, i32, C.c_char_p],
         "agrs_eng_tensor_from_host": [vp, vp, pi64, i32, pvp],
         "agrs_eng_tensor_full": [vp, pi64, i32, f32, pvp],
         "agrs_eng_tensor_uniform": [vp, pi64, i32, f32, f32, pvp],
@@ -698,6 +700,16 @@ class nn:
         def zero_grad(self):
             ps = self.parameters()
             _check(lib().agrs_eng_zero_grad(_handles(ps), len(ps)))
+
+        def save(self, path):
+            """model serialisation (README.md:71 lists it as a TODO of the reference): every parameter, in parameters() order"""
+            ps = self.parameters()
+            _check(lib().agrs_eng_save_parameters(_handles(ps), len(ps), os.fsencode(path)))
+
+        def load(self, path):
+            """write a saved file into this model's parameter storages (shapes must match)"""
+            ps = self.parameters()
+            _check(lib().agrs_eng_load_parameters(_handles(ps), len(ps), os.fsencode(path)))
 
     class Sequential(NN):
         """Convenience for the benchmark configurations: layers applied in order."""

@@ -121,6 +121,11 @@ AGRS_API int agrs_eng_im2col_backward(const agrs_tensor* col, int64_t h_out, int
 /* ---- nn (optim.rs:25-34, model.rs:14-21) ---- */
 AGRS_API int agrs_eng_sgd_step(agrs_tensor* const* params, int n, float lr);
 AGRS_API int agrs_eng_zero_grad(agrs_tensor* const* params, int n); /* only parameters whose grad is Some */
+/* Model serialisation (a TODO of the reference, README.md:71): "AGRSWTS1" | u32 count | per tensor { u32 ndim | u64 dims | f32 data },
+ * little-endian, logical row-major order.  load writes into the existing parameter storages (clones follow; arena-resident
+ * parameters stay in the arena) and fails with AGRS_ERR_SHAPE on a count / shape mismatch. */
+AGRS_API int agrs_eng_save_parameters(agrs_tensor* const* params, int n, const char* path);
+AGRS_API int agrs_eng_load_parameters(agrs_tensor* const* params, int n, const char* path);
 
 /* ---- data parallel training (new: the reference has no multi-device concept; BASELINE north star) ----
  * One process per GPU.  Every rank holds identical parameters and a shard of the minibatch rows; after backward the

@@ -121,9 +121,11 @@ impl CudaData {
 /// (tensor.rs:148, :160).
 impl Clone for CudaData {
     fn clone(&self) -> CudaData {
-        let out = CudaData::alloc(&self.ctx, &self.shape);
+        // (no struct-update syntax here: moving fields out of a value whose type implements Drop is error E0509)
+        let mut out = CudaData::alloc(&self.ctx, &self.shape);
         self.ctx.check(unsafe { sys::agrs_copy(self.ctx.raw(), out.ptr as *mut c_void, self.ptr as *const c_void, self.len() * 4) });
-        CudaData { transposed: self.transposed, ..out }
+        out.transposed = self.transposed;
+        out
     }
 }
 

@@ -628,3 +628,70 @@ def test_backward_colsum_fusion_changes_no_bit(dev, act):
     assert runs[0][2] < runs[1][2]   # three column-sum launches per step fewer
     want, layers = O.mlp_train(x, t, ws, bs, act, 1e-4, 3, np.float32)
     assert max(abs(a - c) / abs(c) for a, c in zip(runs[0][0], want)) < TOL
+
+
+# ====================================================================== examples and model serialisation
+@pytest.mark.parametrize("script,args,needle", [("fit_sine.py", ["--epochs", "300"], "Result: y ="), ("fit_sine.py", ["--epochs", "300", "--graph"], "Result: y ="),
+                                                ("example.py", [], "identical = True")])
+def test_example_ports_run(script, args, needle):
+    """the reference's two examples (examples/fit_sine.rs, examples/example.rs), ported to the front end, run to completion"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "autograd.rs_b200", "examples", script)] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and needle in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    if script == "fit_sine.py":
+        losses = [float(l.split("loss [")[1].split("]")[0]) for l in r.stdout.splitlines() if "loss [" in l]
+        assert len(losses) == 3 and losses[-1] < losses[0]
+
+
+def test_example_rs_hand_written_step_tracks_oracle(dev):
+    """examples/example.rs:43-74 with injected weights: forward, MSE, backward, `w -= grad * lr` by tensor arithmetic on the
+    parameter handles (in place on the shared storage), zero_grad -- two epochs over two batches of 8, against the oracle."""
+    ws, bs = W.mlp_init(2, 128, seed=91, in_features=784, out_features=10)
+    rng = np.random.default_rng(92)
+    xt, yt = rng.uniform(0, 1, (16, 784)).astype(np.float32), rng.uniform(0, 1, (16, 10)).astype(np.float32)
+    model = W.build_mlp(dev, ws, bs, "sigmoid")
+    ol = [O.OLinearLayer(w.copy(), b.copy()) for w, b in zip(ws, bs)]
+    oparams = [q for l in ol for q in l.parameters()]
+    lr = 0.1
+    for epoch in range(2):
+        for i in (0, 8):
+            x, y = T(dev, xt[i:i + 8]), T(dev, yt[i:i + 8])
+            y.requires_grad = False
+            loss = F.nn.MeanSquaredError().forward([model.forward([x]), y.clone()])
+            loss.backward()
+            for p in model.parameters():
+                g = p.grad() * lr
+                p -= g
+            model.zero_grad()
+            ox, oy = O.OTensor(xt[i:i + 8]), O.OTensor(yt[i:i + 8], requires_grad=False)
+            oloss = O.OpMSE().forward([ol[1].forward(O.OpSigmoid().forward([ol[0].forward(ox)])), oy])
+            oloss.backward()
+            O.sgd(oparams, lr)
+            O.model_zero_grad(oparams)
+            assert abs(loss.item() - float(oloss.data[0, 0])) / abs(float(oloss.data[0, 0])) < TOL
+    for p, q in zip(model.parameters(), oparams):
+        assert O.rel_err(p.data(), q.data) < TOL
+
+
+def test_save_and_load_parameters(dev, tmp_path):
+    """AGRSWTS1 round trip: bit-exact values, written into the existing storages (clones follow), shape mismatches refused"""
+    ws, bs = W.mlp_init(2, 96, seed=93)
+    model = W.build_mlp(dev, ws, bs, "relu")
+    path = str(tmp_path / "m.agrs")
+    model.save(path)
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"AGRSWTS1" and int.from_bytes(raw[8:12], "little") == 4
+    assert len(raw) == 12 + sum(4 + 8 * a.ndim + a.nbytes for pair in zip(ws, bs) for a in pair)
+    other = W.build_mlp(dev, [np.zeros_like(w) for w in ws], [np.zeros_like(b) for b in bs], "relu")
+    clones = [p.clone() for p in other.parameters()]
+    before = [p.data_ptr() for p in other.parameters()]
+    other.load(path)
+    for p, c, a in zip(other.parameters(), clones, [a for pair in zip(ws, bs) for a in pair]):
+        assert np.array_equal(p.data(), a) and np.array_equal(c.data(), a)
+    assert [p.data_ptr() for p in other.parameters()] == before
+    wrong = W.build_mlp(dev, [np.zeros((96, 64), np.float32)], [np.zeros((1, 64), np.float32)], None)
+    with pytest.raises(F.Panic):
+        wrong.load(path)
