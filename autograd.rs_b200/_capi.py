@@ -123,6 +123,8 @@ def lib():
             "agrs_im2col_f32": [vp, vp, i64, i64, i64, i64, i64, i64, i64, vp],
             "agrs_col2im_f32": [vp, vp, i64, i64, i64, i64, i64, i64, vp],
             "agrs_broadcast_filter_f32": [vp, vp, i64, i64, i64, vp],
+            "agrs_conv2d_fwd_f32": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp],
+            "agrs_conv2d_bwd_f32": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -140,6 +142,8 @@ def lib():
         L.agrs_fused_flag_floats.restype = C.c_size_t
         L.agrs_fused_max_buckets.argtypes = []
         L.agrs_fused_max_buckets.restype = i32
+        L.agrs_conv2d_implicit_ok.argtypes = [i64] * 8
+        L.agrs_conv2d_implicit_ok.restype = i32
         L.agrs_version.argtypes = []
         L.agrs_version.restype = C.c_char_p
         _lib = L

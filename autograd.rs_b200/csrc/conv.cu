@@ -262,6 +262,137 @@ unsigned grid1d(agrs_ctx* ctx, int64_t total) {
   return unsigned(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Implicit-GEMM Conv2D for single-channel inputs (the LeNet layer of BASELINE configs[2]): the col matrix of
+// operators.rs:350-390 -- 18x the image for k = 5 -- is never materialised.  With C_in = 1 the lowered GEMMs are
+//   forward   out[b, p, o] = sum_t col[b, p, t] * filt[t, o] + bias[o]          K = k*k (25), N = C_out (6)
+//   dxcol     g[b, p, :] . filt[t, :]  followed by the overlap-add of col2im      (functional_ndarray.rs:107-138)
+//   dw        sum_{b, p} col[b, p, t] * g[b, p, o],   db = sum_{b, p} g[b, p, o]  (operators.rs:405, :445)
+// and col[b, p, t] is im[b, 0, y*s - pad + i, x*s - pad + j]: every kernel below reads it straight from the image of one sample
+// staged (zero-padded) in shared memory.  HBM traffic: image + output forward; image + gradient + dx backward.
+// One CTA walks samples b = blockIdx.x, blockIdx.x + gridDim.x, ..; all sums run in a fixed order (deterministic).
+constexpr int kConvCo = 8;  // C_out handled per thread (register accumulators)
+
+template <int CO>
+__global__ void __launch_bounds__(256) k_conv1_fwd(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ bias,
+                                                   int B, int H, int W, int k, int co, int s, int pad, int Ho, int Wo, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, kk = k * k, P = Ho * Wo;
+  float* img = sm;               // [Hp][Wp], zero border
+  float* fl = sm + Hp * Wp;      // [kk][co]
+  for (int e = threadIdx.x; e < kk * co; e += blockDim.x) fl[e] = __ldg(filt + e);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < Hp * Wp; e += blockDim.x) {
+      const int h = e / Wp - pad, w = e % Wp - pad;
+      img[e] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldcs(im + (int64_t(b) * H + h) * W + w) : 0.f;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      const int y = p / Wo, x = p % Wo;
+      float acc[CO];
+#pragma unroll
+      for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+      const float* base = img + (y * s) * Wp + x * s;
+      for (int i = 0; i < k; ++i)
+        for (int j = 0; j < k; ++j) {  // t = i*k + j ascending: the GEMM's order over K
+          const float v = base[i * Wp + j];
+          const float* f = fl + (i * k + j) * co;
+#pragma unroll
+          for (int o = 0; o < CO; ++o)
+            if (o < co) acc[o] = fmaf(v, f[o], acc[o]);
+        }
+      float* dst = out + (int64_t(b) * P + p) * co;  // NHWC (operators.rs:383)
+#pragma unroll
+      for (int o = 0; o < CO; ++o)
+        if (o < co) dst[o] = acc[o] + __ldg(bias + o);
+    }
+  }
+}
+
+// backward of the same layer: dx (padded size, per sample), and this CTA's partial sums of dw [kk][co] and db [co]; the last CTA
+// to finish folds the partials in CTA order.
+template <int CO>
+__global__ void __launch_bounds__(256) k_conv1_bwd(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ g,
+                                                   int B, int H, int W, int k, int co, int s, int pad, int Ho, int Wo, float* __restrict__ dx,
+                                                   float* __restrict__ dw, float* __restrict__ db, float* __restrict__ part,
+                                                   unsigned int* __restrict__ ticket) {
+  extern __shared__ float sm[];
+  __shared__ unsigned int s_ticket;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, kk = k * k, P = Ho * Wo;
+  const int hx = (Ho - 1) * s + k, wx = (Wo - 1) * s + k;  // dx keeps the padded size (TODO at operators.rs:427)
+  float* img = sm;                  // [Hp][Wp]
+  float* gt = img + Hp * Wp;        // [P][co]
+  float* fl = gt + P * co;          // [kk][co]
+  for (int e = threadIdx.x; e < kk * co; e += blockDim.x) fl[e] = __ldg(filt + e);
+  // thread t < kk*co owns dw[t / co][t % co]; threads kk*co .. kk*co + co - 1 own db
+  const int nacc = kk * co + co;
+  float acc = 0.f;
+  const int my_t = threadIdx.x < kk * co ? threadIdx.x / co : -1, my_o = threadIdx.x < kk * co ? threadIdx.x % co : threadIdx.x - kk * co;
+  const int my_i = my_t >= 0 ? my_t / k : 0, my_j = my_t >= 0 ? my_t % k : 0;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < Hp * Wp; e += blockDim.x) {
+      const int h = e / Wp - pad, w = e % Wp - pad;
+      img[e] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldcs(im + (int64_t(b) * H + h) * W + w) : 0.f;
+    }
+    const float* gb = g + int64_t(b) * P * co;
+    for (int e = threadIdx.x; e < P * co; e += blockDim.x) gt[e] = __ldcs(gb + e);
+    __syncthreads();
+    // dw / db: one accumulator per thread, positions in ascending order
+    if (int(threadIdx.x) < nacc) {
+      if (my_t >= 0) {
+        for (int y = 0; y < Ho; ++y) {
+          const float* row = img + (y * s + my_i) * Wp + my_j;
+          const float* gr = gt + y * Wo * co + my_o;
+          for (int x = 0; x < Wo; ++x) acc = fmaf(row[x * s], gr[x * co], acc);
+        }
+      } else {
+        for (int p = 0; p < P; ++p) acc += gt[p * co + my_o];
+      }
+    }
+    // dx[b, 0, u, v] = sum over positions (y, x) ascending and taps with y*s + i == u, x*s + j == v of g[y, x, :] . filt[i*k + j, :]
+    for (int e = threadIdx.x; e < hx * wx; e += blockDim.x) {
+      const int u = e / wx, v = e % wx;
+      float a = 0.f;
+      for (int i = k - 1; i >= 0; --i) {  // i descending = y ascending
+        const int uy = u - i;
+        if (uy < 0 || uy % s) continue;
+        const int y = uy / s;
+        if (y >= Ho) continue;
+        for (int j = k - 1; j >= 0; --j) {
+          const int vx = v - j;
+          if (vx < 0 || vx % s) continue;
+          const int x = vx / s;
+          if (x >= Wo) continue;
+          const float* gp = gt + (y * Wo + x) * co;
+          const float* f = fl + (i * k + j) * co;
+          float t = 0.f;
+#pragma unroll
+          for (int o = 0; o < CO; ++o)
+            if (o < co) t = fmaf(gp[o], f[o], t);  // dxcol[p, t]: the GEMM g . filt^T over C_out
+          a += t;                                  // the overlap-add of col2im
+        }
+      }
+      __stcs(dx + int64_t(b) * hx * wx + e, a);
+    }
+  }
+  if (int(threadIdx.x) < nacc) part[int64_t(blockIdx.x) * nacc + threadIdx.x] = acc;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  if (int(threadIdx.x) < nacc) {
+    float t = 0.f;
+    for (unsigned c = 0; c < gridDim.x; ++c) t += __ldcg(part + int64_t(c) * nacc + threadIdx.x);
+    if (my_t >= 0) dw[threadIdx.x] = t;  // [k][k][co] == [kk][co]
+    else           db[my_o] = t;
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
 }  // namespace
 
 extern "C" {
@@ -350,6 +481,64 @@ int agrs_broadcast_filter_f32(agrs_ctx* ctx, const float* filt, int64_t kk, int6
   if (total == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, filt && out, AGRS_ERR_INVALID, "agrs_broadcast_filter_f32: null pointer");
   k_broadcast_filter<<<unsigned((total + 255) / 256), 256, 0, ctx->stream>>>(filt, per, total, out);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+
+// shapes the implicit-GEMM kernels take (anything else goes through im2col + GEMM)
+static bool conv1_shape_ok(int64_t B, int64_t H, int64_t W, int64_t k, int64_t co, int64_t stride, int64_t pad, size_t* smem_fwd, size_t* smem_bwd) {
+  if (B < 1 || k < 1 || k > 11 || co < 1 || co > kConvCo || stride < 1 || pad < 0 || H + 2 * pad < k || W + 2 * pad < k) return false;
+  const int64_t Ho = (H - k + 2 * pad) / stride + 1, Wo = (W - k + 2 * pad) / stride + 1;
+  if (k * k * co + co > 256) return false;  // one dw / db accumulator per thread
+  const size_t img = size_t(H + 2 * pad) * size_t(W + 2 * pad), fl = size_t(k * k * co);
+  *smem_fwd = (img + fl) * sizeof(float);
+  *smem_bwd = (img + size_t(Ho * Wo * co) + fl) * sizeof(float);
+  return *smem_bwd <= 160 * 1024 && B < (int64_t(1) << 31) && H < 32768 && W < 32768;
+}
+
+int agrs_conv2d_implicit_ok(int64_t B, int64_t C, int64_t H, int64_t W, int64_t k, int64_t c_out, int64_t stride, int64_t pad) {
+  size_t a, b;
+  return C == 1 && conv1_shape_ok(B, H, W, k, c_out, stride, pad, &a, &b) ? 1 : 0;
+}
+
+int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W, int64_t k,
+                        int64_t c_out, int64_t stride, int64_t pad, float* out) {
+  AGRS_CHECK_CTX(ctx);
+  size_t smem = 0, smem_b = 0;
+  AGRS_REQUIRE(ctx, conv1_shape_ok(B, H, W, k, c_out, stride, pad, &smem, &smem_b), AGRS_ERR_UNSUPPORTED,
+               "agrs_conv2d_fwd_f32: shape outside the implicit-GEMM kernels (single input channel, C_out <= %d, k*k*C_out + C_out <= 256): use im2col + GEMM", kConvCo);
+  AGRS_REQUIRE(ctx, im && filt && bias && out, AGRS_ERR_INVALID, "agrs_conv2d_fwd_f32: null pointer");
+  const int Ho = int((H - k + 2 * pad) / stride + 1), Wo = int((W - k + 2 * pad) / stride + 1);
+  const int64_t cap = int64_t(ctx->sm_count) * 4;
+  AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd<kConvCo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  k_conv1_fwd<kConvCo><<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo, out);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* grad, int64_t B, int64_t H, int64_t W, int64_t k,
+                        int64_t c_out, int64_t stride, int64_t pad, float* dx, float* dw, float* db) {
+  AGRS_CHECK_CTX(ctx);
+  size_t smem_f = 0, smem = 0;
+  AGRS_REQUIRE(ctx, conv1_shape_ok(B, H, W, k, c_out, stride, pad, &smem_f, &smem), AGRS_ERR_UNSUPPORTED,
+               "agrs_conv2d_bwd_f32: shape outside the implicit-GEMM kernels: use the im2col path");
+  AGRS_REQUIRE(ctx, im && filt && grad && dx && dw && db, AGRS_ERR_INVALID, "agrs_conv2d_bwd_f32: null pointer");
+  const int Ho = int((H - k + 2 * pad) / stride + 1), Wo = int((W - k + 2 * pad) / stride + 1);
+  const int64_t cap = int64_t(ctx->sm_count) * 2;
+  const int64_t grid = B < cap ? B : cap;
+  const size_t nacc = size_t(k * k * c_out + c_out);
+  int rc = agrs_ensure_workspace(ctx, size_t(grid) * nacc * sizeof(float));
+  if (rc) return rc;
+  if (ctx->tickets_n < 1) {
+    AGRS_NOT_CAPTURING(ctx, "allocating the ticket array (run one ordinary step before capturing)");
+    AGRS_CUDA(ctx, cudaMalloc(&ctx->tickets, 4096 * sizeof(unsigned int)));
+    AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, 4096 * sizeof(unsigned int), ctx->stream));
+    ctx->tickets_n = 4096;
+  }
+  AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd<kConvCo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  k_conv1_bwd<kConvCo><<<unsigned(grid), 256, smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo,
+                                                                  dx, dw, db, ctx->workspace, ctx->tickets);
   AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }

@@ -137,8 +137,24 @@ Tensor kernel_matrix(const Conv2D& op, const Tensor& filters) {
   return Tensor(km);
 }
 
+// the shapes the implicit-GEMM Conv2D kernels take (agrs_conv2d_*_f32)
+bool conv_implicit_ok(const Conv2D& op, const Tensor& im, const Tensor& filters, const Tensor& bias) {
+  return im.dev()->conv_implicit && im.ndim() == 4 && im.is_contiguous() && filters.is_contiguous() && bias.is_contiguous() &&
+         op.in_channels == 1 && im.shapei(1) == 1 && filters.len() == op.k_size * op.k_size * op.out_channels && bias.len() == op.out_channels &&
+         agrs_conv2d_implicit_ok(im.shapei(0), 1, im.shapei(2), im.shapei(3), op.k_size, op.out_channels, op.stride, op.pad) != 0;
+}
+
 Tensor fwd(const Conv2D& op, std::vector<Tensor>& xs) {
   const Tensor &im = xs.at(0), &filters = xs.at(1), &bias = xs.at(2);
+  if (conv_implicit_ok(op, im, filters, bias)) {
+    // one input channel: col[b, p, i*k+j] is read from the image inside the kernel; nothing is cached for backward (the node keeps
+    // its three inputs; the literal path below pushes col as a 4th variable, operators.rs:386-388)
+    auto [h_out, w_out] = op.get_output_shape(im.shapei(2), im.shapei(3));
+    auto out = std::make_shared<Storage>(im.dev(), Shape{im.shapei(0), h_out, w_out, op.out_channels});  // NHWC (operators.rs:383)
+    im.dev()->check(agrs_conv2d_fwd_f32(im.dev()->ctx(), im.data->rptr(), filters.data->rptr(), bias.data->rptr(), im.shapei(0), im.shapei(2),
+                                        im.shapei(3), op.k_size, op.out_channels, op.stride, op.pad, out->buf->ptr));
+    return Tensor(out);
+  }
   Tensor col = Conv2D::im2col(im, op.k_size, op.stride, op.pad);  // [B, P, C*k*k]
   Tensor kernel = kernel_matrix(op, filters);
   const int64_t kkc = op.k_size * op.k_size * op.in_channels;
@@ -260,6 +276,19 @@ std::vector<Tensor> bwd(const Conv2D& op, const std::vector<Tensor>& xs, const T
   if (grad.ndim() != 4) throw Panic("index out of bounds: Conv2D backward expects a BxH_outxW_outxC_out gradient", AGRS_ERR_SHAPE);
   Tensor g = grad.clone();
   g.reshape({g.shapei(0) * g.shapei(1) * g.shapei(2), g.shapei(3)});  // mutates the shared storage shape, as operators.rs:402-403
+  if (xs.size() == 3 && conv_implicit_ok(op, im, filters, xs.at(2)) && g.is_contiguous() &&
+      g.shapei(1) == op.out_channels) {
+    // forward cached no col: db, dw and dx straight from the image and the gradient, one kernel (per-sample overlap-add: D1)
+    auto [ho, wo] = op.get_output_shape(im.shapei(2), im.shapei(3));
+    if (g.shapei(0) != im.shapei(0) * ho * wo) throw Panic("Conv2D backward: gradient does not match the output shape", AGRS_ERR_SHAPE);
+    auto dx = std::make_shared<Storage>(im.dev(), Shape{im.shapei(0), 1, (ho - 1) * op.stride + op.k_size, (wo - 1) * op.stride + op.k_size});
+    auto dw = std::make_shared<Storage>(im.dev(), Shape{op.k_size, op.k_size, op.out_channels});
+    auto db = std::make_shared<Storage>(im.dev(), Shape{op.out_channels});
+    im.dev()->check(agrs_conv2d_bwd_f32(im.dev()->ctx(), im.data->rptr(), filters.data->rptr(), g.data->rptr(), im.shapei(0), im.shapei(2), im.shapei(3),
+                                        op.k_size, op.out_channels, op.stride, op.pad, dx->buf->ptr, dw->buf->ptr, db->buf->ptr));
+    return {Tensor(dx), Tensor(dw), Tensor(db)};
+  }
+  if (xs.size() < 4) throw Panic("index out of bounds: the len is 3 but the index is 3 (Conv2D backward without the cached col)");
   Tensor db = g.sum_axis(0);                                         // :405
   Tensor kernels = kernel_matrix(op, filters);                       // :408-419
   Tensor dxcol = gemm(g, false, kernels, true);                      // g.dot(kernels.t())  :422

@@ -125,6 +125,12 @@ int agrs_eng_device_set_fusions(agrs_device* d, int backward_colsum) {
     d->dev.fuse_backward_colsum = backward_colsum != 0;
   });
 }
+int agrs_eng_device_set_conv_implicit(agrs_device* d, int on) {
+  return guarded([&] {
+    need(d, "device");
+    d->dev.conv_implicit = on != 0;
+  });
+}
 int agrs_eng_device_set_matmul_backward_literal(agrs_device* d, int literal) {
   return guarded([&] {
     need(d, "device");

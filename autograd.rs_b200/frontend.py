@@ -59,6 +59,7 @@ def lib():
         "agrs_eng_device_seed": [vp, C.c_uint64],
         "agrs_eng_device_set_matmul_backward_literal": [vp, i32],
         "agrs_eng_device_set_fusions": [vp, i32],
+        "agrs_eng_device_set_conv_implicit": [vp, i32],
         "agrs_eng_save_parameters": [pvp, i32, C.c_char_p],
         "agrs_eng_load_parameters": [pvp, i32, C.c_char_p],
         "agrs_eng_tensor_from_host": [vp, vp, pi64, i32, pvp],
@@ -178,6 +179,10 @@ class Device:
     def set_fusions(self, backward_colsum=True):
         """operator-boundary fusions (on by default; bit-identical either way): db left by the backward kernel that produced the gradient"""
         _check(lib().agrs_eng_device_set_fusions(self._h, int(bool(backward_colsum))))
+
+    def set_conv_implicit(self, on=True):
+        """Conv2D with one input channel: implicit-GEMM kernels without a col matrix (default) or the literal im2col lowering"""
+        _check(lib().agrs_eng_device_set_conv_implicit(self._h, int(bool(on))))
 
     def set_matmul_backward_literal(self, literal):
         _check(lib().agrs_eng_device_set_matmul_backward_literal(self._h, int(bool(literal))))

@@ -210,6 +210,17 @@ AGRS_API int agrs_im2col_f32(agrs_ctx* ctx, const float* im, int64_t B, int64_t 
 /* overlap-add inverse; col is [B, Ho*Wo, C*k*k]; im_out is [B, C, (Ho-1)s+k, (Wo-1)s+k] (padded size, as the reference) */
 AGRS_API int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t C, int64_t Ho, int64_t Wo,
                     int64_t k, int64_t stride, float* im_out);
+/* Implicit-GEMM Conv2D for single-channel images: same results as im2col + GEMM (+ col2im, + the two reductions)
+ * of operators.rs:350-449 without ever materialising col -- every kernel reads col[b, p, i*k+j] = im[b, 0, y*s-pad+i, x*s-pad+j]
+ * from the sample staged in shared memory.  im [B,1,H,W]; filt [k,k,Co]; out / grad [B,Ho,Wo,Co] (NHWC);
+ * dx [B,1,(Ho-1)s+k,(Wo-1)s+k] (padded size, as the reference); dw [k,k,Co]; db [Co].  agrs_conv2d_implicit_ok tells whether a
+ * shape is taken (C == 1, Co <= 8, k*k*Co + Co <= 256, one sample's image + gradient within 160 KB); otherwise the calls return
+ * AGRS_ERR_UNSUPPORTED and the caller lowers with agrs_im2col_f32 + agrs_gemm_f32. */
+AGRS_API int agrs_conv2d_implicit_ok(int64_t B, int64_t C, int64_t H, int64_t W, int64_t k, int64_t c_out, int64_t stride, int64_t pad);
+AGRS_API int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W,
+                                 int64_t k, int64_t c_out, int64_t stride, int64_t pad, float* out);
+AGRS_API int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* grad, int64_t B, int64_t H, int64_t W,
+                                 int64_t k, int64_t c_out, int64_t stride, int64_t pad, float* dx, float* dw, float* db);
 /* out[c*kk + r, o] = filt[r, o] for every c: the [k,k,Co] -> [Ci,k,k,Co] broadcast (storage.rs:114-120) */
 AGRS_API int agrs_broadcast_filter_f32(agrs_ctx* ctx, const float* filt, int64_t kk, int64_t c_out, int64_t c_in, float* out);
 

@@ -45,6 +45,9 @@ AGRS_API int agrs_eng_device_set_matmul_backward_literal(agrs_device* dev, int l
  * backward_colsum: ReLU / Sigmoid / MSE backward of a [B, O] tensor also leaves the sum over rows of its result with the buffer,
  * which Linear::backward of the layer below takes as db (operators.rs:161) instead of re-reading the gradient. */
 AGRS_API int agrs_eng_device_set_fusions(agrs_device* dev, int backward_colsum);
+/* Conv2D with one input channel (on by default): implicit-GEMM kernels that never materialise col; the node then keeps its three
+ * inputs only.  0 = always the literal lowering of operators.rs:350-449 (im2col + GEMM, col cached as the 4th variable). */
+AGRS_API int agrs_eng_device_set_conv_implicit(agrs_device* dev, int on);
 
 /* ---- Tensor constructors (tensor.rs:37-92, init.rs:19-49) ---- */
 AGRS_API int agrs_eng_tensor_from_host(agrs_device* dev, const float* host, const int64_t* shape, int ndim, agrs_tensor** out);

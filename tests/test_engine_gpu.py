@@ -304,7 +304,16 @@ def test_mse_and_mean_ops(dev):
                                               (5, 3, 10, 9, 6, 3, 1, 1),  # B > 1: the per-sample generalisation of col2im (D1)
                                               (64, 1, 28, 28, 6, 5, 1, 0)])  # the LeNet geometry
 def test_conv2d_values_match_literal_oracle(dev, B, C, H, Wd, co, k, s, p):
-    """Conv2D forward AND backward values against the oracle's literal restatement of operators.rs:350-449, quirks included"""
+    """Conv2D forward AND backward values against the oracle's literal restatement of operators.rs:350-449, quirks included
+    (the literal lowering: im2col + GEMM with the col matrix cached in the node)"""
+    dev.set_conv_implicit(False)
+    try:
+        _conv2d_literal_case(dev, B, C, H, Wd, co, k, s, p)
+    finally:
+        dev.set_conv_implicit(True)
+
+
+def _conv2d_literal_case(dev, B, C, H, Wd, co, k, s, p):
     rng = np.random.default_rng(B + C + H + k + p)
     im = rng.standard_normal((B, C, H, Wd)).astype(np.float32)
     filt = rng.standard_normal((k, k, co)).astype(np.float32)
@@ -695,3 +704,59 @@ def test_save_and_load_parameters(dev, tmp_path):
     wrong = W.build_mlp(dev, [np.zeros((96, 64), np.float32)], [np.zeros((1, 64), np.float32)], None)
     with pytest.raises(F.Panic):
         wrong.load(path)
+
+
+@pytest.mark.parametrize("B,H,Wd,co,k,s,p", [(64, 28, 28, 6, 5, 1, 0), (3, 9, 11, 8, 3, 1, 1), (5, 12, 10, 4, 3, 2, 1), (1, 7, 7, 5, 2, 2, 0), (300, 28, 28, 6, 5, 1, 0)])
+def test_conv2d_implicit_gemm_matches_oracle_and_literal_path(dev, B, H, Wd, co, k, s, p):
+    """f3: Conv2D with one input channel through the implicit-GEMM kernels (no col matrix): forward and all three gradients against
+    the oracle's literal restatement, and against the device's own im2col + GEMM path; the node keeps three variables."""
+    rng = np.random.default_rng(B + H + k + p + co)
+    im = rng.standard_normal((B, 1, H, Wd)).astype(np.float32)
+    filt = rng.standard_normal((k, k, co)).astype(np.float32)
+    bias = rng.standard_normal((co,)).astype(np.float32)
+    want_out, col2d = O.conv2d_fwd(im, filt, bias, 1, k, s, p)
+    g = rng.standard_normal(want_out.shape).astype(np.float32)
+    wdx, wdw, wdb = O.conv2d_bwd(im, filt, col2d, g, 1, k, s, p, literal=False)
+    res = {}
+    for implicit in (True, False):
+        dev.set_conv_implicit(implicit)
+        try:
+            conv = F.Conv2D(1, co, k, s, p)
+            X, Fl, Bi = T(dev, im), T(dev, filt), T(dev, bias)
+            out = conv.forward([X.clone(), Fl.clone(), Bi.clone()])
+            assert out.graph_info() == ("Conv2D", 3 if implicit else 4, 0)
+            xs = [X, Fl, Bi] + ([] if implicit else [T(dev, col2d)])
+            dx, dw, db = conv.backward(xs, T(dev, g))
+            res[implicit] = (out.data(), dx.data(), dw.data(), db.data())
+        finally:
+            dev.set_conv_implicit(True)
+    o, dx, dw, db = res[True]
+    assert o.shape == want_out.shape and dx.shape == wdx.shape and dw.shape == (k, k, co) and db.shape == (co,)
+    assert O.rel_err(o, want_out) < 1e-5 and O.rel_err(dx, wdx) < 1e-5 and O.rel_err(dw, wdw) < 2e-5 and O.rel_err(db, wdb) < 2e-5
+    for a, b in zip(res[True], res[False]):
+        assert O.rel_err(a, b) < 2e-5
+
+
+def test_lenet_implicit_and_literal_conv_train_alike(dev):
+    """C3 in miniature through both Conv2D paths: losses of 3 steps agree to 1e-5 and both track the oracle"""
+    rng = np.random.default_rng(33)
+    B = 48
+    im = rng.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32)
+    t = rng.uniform(0, 1, (B, 10)).astype(np.float32)
+    filt = rng.uniform(-0.3, 0.3, (5, 5, 6)).astype(np.float32)
+    cb = rng.uniform(-0.1, 0.1, (6,)).astype(np.float32)
+    w = rng.uniform(-0.05, 0.05, (3456, 10)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (1, 10)).astype(np.float32)
+    runs = []
+    for implicit in (True, False):
+        dev.set_conv_implicit(implicit)
+        try:
+            tr = W.Trainer(W.build_lenet(dev, filt, cb, w, b), 1e-3)
+            X, Tt = T(dev, im), T(dev, t)
+            Tt.requires_grad = False
+            n0 = dev.launches()
+            runs.append(([tr.step(X, Tt).item() for _ in range(3)], dev.launches() - n0))
+        finally:
+            dev.set_conv_implicit(True)
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
+    assert runs[0][1] < runs[1][1]  # fewer kernels per step
