@@ -66,6 +66,16 @@ struct agrs_ctx {
 
 int agrs_fail(agrs_ctx* ctx, int code, const char* fmt, ...);
 
+// NVTX range around a C-ABI entry point (tracing).  nvtx3 is header-only and binds to a profiler's injection
+// library at run time: without a tool attached a range costs one predictable branch.
+#include <nvtx3/nvToolsExt.h>
+struct AgrsRange {
+  explicit AgrsRange(const char* name) { nvtxRangePushA(name); }
+  ~AgrsRange() { nvtxRangePop(); }
+  AgrsRange(const AgrsRange&) = delete;
+};
+#define AGRS_RANGE(name) AgrsRange agrs_range_(name)
+
 #define AGRS_CHECK_CTX(ctx)                 \
   do {                                      \
     if (!(ctx)) return AGRS_ERR_INVALID;    \

@@ -92,6 +92,7 @@ int agrs_comm_unique_id(void* out_id128) {
 
 int agrs_comm_create(agrs_ctx* ctx, int world, int rank, const void* id128, agrs_comm** out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_comm_create");
   AGRS_REQUIRE(ctx, out && id128 && world >= 1 && rank >= 0 && rank < world, AGRS_ERR_INVALID, "agrs_comm_create: bad arguments");
   *out = nullptr;
   NcclApi* api = nccl();
@@ -142,6 +143,7 @@ int agrs_comm_allreduce_f32(agrs_comm* c, float* buf, size_t n, int average) {
   if (!c) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = c->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_comm_allreduce_f32");
   if (n == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, buf, AGRS_ERR_INVALID, "agrs_comm_allreduce_f32: null pointer");
   // the collective starts once everything enqueued so far on the compute stream (the kernel that produced buf) is done
@@ -155,6 +157,7 @@ int agrs_comm_join(agrs_comm* c) {
   if (!c) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = c->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_comm_join");
   AGRS_CUDA(ctx, cudaEventRecord(c->done, c->stream));
   AGRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, c->done, 0));
   return AGRS_OK;

@@ -272,124 +272,202 @@ unsigned grid1d(agrs_ctx* ctx, int64_t total) {
 // and col[b, p, t] is im[b, 0, y*s - pad + i, x*s - pad + j]: every kernel below reads it straight from the image of one sample
 // staged (zero-padded) in shared memory.  HBM traffic: image + output forward; image + gradient + dx backward.
 // One CTA walks samples b = blockIdx.x, blockIdx.x + gridDim.x, ..; all sums run in a fixed order (deterministic).
-constexpr int kConvCo = 8;  // C_out handled per thread (register accumulators)
+constexpr int kConvCo = 8;  // C_out handled per thread (register accumulators); channel vectors are padded to 8 in shared memory
 
-template <int CO>
+// 8 floats (one position's C_out values, or one tap's filter row) from shared memory: two 16-byte loads
+struct F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ld8(const float* p) { return {*reinterpret_cast<const float4*>(p), *reinterpret_cast<const float4*>(p + 4)}; }
+__device__ __forceinline__ float dot8(const F8& a, const F8& b) {  // sum over C_out in channel order (padding channels are zero)
+  float t = a.lo.x * b.lo.x;
+  t = fmaf(a.lo.y, b.lo.y, t); t = fmaf(a.lo.z, b.lo.z, t); t = fmaf(a.lo.w, b.lo.w, t);
+  t = fmaf(a.hi.x, b.hi.x, t); t = fmaf(a.hi.y, b.hi.y, t); t = fmaf(a.hi.z, b.hi.z, t); t = fmaf(a.hi.w, b.hi.w, t);
+  return t;
+}
+
+// forward: thread per output position, the CTA's results staged in shared memory and written as one coalesced stream
 __global__ void __launch_bounds__(256) k_conv1_fwd(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ bias,
                                                    int B, int H, int W, int k, int co, int s, int pad, int Ho, int Wo, float* __restrict__ out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, kk = k * k, P = Ho * Wo;
-  float* img = sm;               // [Hp][Wp], zero border
-  float* fl = sm + Hp * Wp;      // [kk][co]
-  for (int e = threadIdx.x; e < kk * co; e += blockDim.x) fl[e] = __ldg(filt + e);
+  float* fl = sm;                          // [kk][8], zero padded
+  float* bs = fl + kk * 8;                 // [8]
+  float* img = bs + 8;                     // [Hp][Wp], zero border
+  float* stage = img + ((Hp * Wp + 3) & ~3);  // [P][co]: the sample's output exactly as it lies in global memory
+  for (int e = threadIdx.x; e < kk * 8 + 8; e += blockDim.x) {
+    const int t = e >> 3, o = e & 7;
+    fl[e] = o < co ? (t < kk ? __ldg(filt + t * co + o) : __ldg(bias + o)) : 0.f;
+  }
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    for (int e = threadIdx.x; e < Hp * Wp; e += blockDim.x) {
-      const int h = e / Wp - pad, w = e % Wp - pad;
-      img[e] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldcs(im + (int64_t(b) * H + h) * W + w) : 0.f;
+    const float* src = im + int64_t(b) * H * W;
+    if (pad == 0) {
+      for (int e = threadIdx.x; e < H * W; e += blockDim.x) img[e] = __ldcs(src + e);
+    } else {
+      for (int e = threadIdx.x; e < Hp * Wp; e += blockDim.x) {
+        const int h = e / Wp - pad, w = e % Wp - pad;
+        img[e] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldcs(src + h * W + w) : 0.f;
+      }
     }
     __syncthreads();
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
-      const int y = p / Wo, x = p % Wo;
-      float acc[CO];
+      const int y = p / Wo, x = p - y * Wo;
+      float acc[8];
 #pragma unroll
-      for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+      for (int o = 0; o < 8; ++o) acc[o] = 0.f;
       const float* base = img + (y * s) * Wp + x * s;
       for (int i = 0; i < k; ++i)
         for (int j = 0; j < k; ++j) {  // t = i*k + j ascending: the GEMM's order over K
           const float v = base[i * Wp + j];
-          const float* f = fl + (i * k + j) * co;
-#pragma unroll
-          for (int o = 0; o < CO; ++o)
-            if (o < co) acc[o] = fmaf(v, f[o], acc[o]);
+          const F8 f = ld8(fl + (i * k + j) * 8);  // the same address for the whole warp: a broadcast
+          acc[0] = fmaf(v, f.lo.x, acc[0]); acc[1] = fmaf(v, f.lo.y, acc[1]); acc[2] = fmaf(v, f.lo.z, acc[2]); acc[3] = fmaf(v, f.lo.w, acc[3]);
+          acc[4] = fmaf(v, f.hi.x, acc[4]); acc[5] = fmaf(v, f.hi.y, acc[5]); acc[6] = fmaf(v, f.hi.z, acc[6]); acc[7] = fmaf(v, f.hi.w, acc[7]);
         }
-      float* dst = out + (int64_t(b) * P + p) * co;  // NHWC (operators.rs:383)
 #pragma unroll
-      for (int o = 0; o < CO; ++o)
-        if (o < co) dst[o] = acc[o] + __ldg(bias + o);
+      for (int o = 0; o < 8; ++o)
+        if (o < co) stage[p * co + o] = acc[o] + bs[o];
+    }
+    __syncthreads();
+    float* dst = out + int64_t(b) * P * co;  // NHWC (operators.rs:383): [P][co] contiguous per sample
+    const int n = P * co;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+      for (int e = threadIdx.x; e < n / 4; e += blockDim.x) __stcs(reinterpret_cast<float4*>(dst) + e, reinterpret_cast<const float4*>(stage)[e]);
+    } else {
+      for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = stage[e];
     }
   }
 }
 
 // backward of the same layer: dx (padded size, per sample), and this CTA's partial sums of dw [kk][co] and db [co]; the last CTA
-// to finish folds the partials in CTA order.
-template <int CO>
+// to finish folds the partials in CTA order.  dw / db: thread = (tap, half of the channels, slice of the positions), accumulators
+// live in registers across all the samples of the CTA; dx: thread per pixel, channel vectors of 8 from shared memory.  The
+// gradient tile is staged with a zero border of k-1 positions, so for stride 1 the dx loops carry no bounds checks (profiling the
+// first version showed 7 integer / branch instructions per FFMA: profiles/r2_conv_implicit.md).  KT = compile-time k (0: run-time).
+template <bool S1, int KT>
 __global__ void __launch_bounds__(256) k_conv1_bwd(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ g,
-                                                   int B, int H, int W, int k, int co, int s, int pad, int Ho, int Wo, float* __restrict__ dx,
+                                                   int B, int H, int W, int k_rt, int co, int s, int pad, int Ho, int Wo, float* __restrict__ dx,
                                                    float* __restrict__ dw, float* __restrict__ db, float* __restrict__ part,
                                                    unsigned int* __restrict__ ticket) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   __shared__ unsigned int s_ticket;
+  const int k = KT ? KT : k_rt;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, kk = k * k, P = Ho * Wo;
   const int hx = (Ho - 1) * s + k, wx = (Wo - 1) * s + k;  // dx keeps the padded size (TODO at operators.rs:427)
-  float* img = sm;                  // [Hp][Wp]
-  float* gt = img + Hp * Wp;        // [P][co]
-  float* fl = gt + P * co;          // [kk][co]
-  for (int e = threadIdx.x; e < kk * co; e += blockDim.x) fl[e] = __ldg(filt + e);
-  // thread t < kk*co owns dw[t / co][t % co]; threads kk*co .. kk*co + co - 1 own db
-  const int nacc = kk * co + co;
-  float acc = 0.f;
-  const int my_t = threadIdx.x < kk * co ? threadIdx.x / co : -1, my_o = threadIdx.x < kk * co ? threadIdx.x % co : threadIdx.x - kk * co;
-  const int my_i = my_t >= 0 ? my_t / k : 0, my_j = my_t >= 0 ? my_t % k : 0;
+  const int bd = k - 1, Wg = Wo + 2 * bd, Hg = Ho + 2 * bd;  // gradient tile with its zero border
+  float* fl = sm;                           // [kk][8]
+  float* gt = fl + kk * 8;                  // [Hg][Wg][8]
+  float* img = gt + Hg * Wg * 8;            // [Hp][Wp]
+  float* red = img + ((Hp * Wp + 3) & ~3);  // [slices][kk + 1][8]: the CTA's dw / db partials, folded over the position slices at the end
+  for (int e = threadIdx.x; e < kk * 8; e += blockDim.x) fl[e] = (e & 7) < co ? __ldg(filt + (e >> 3) * co + (e & 7)) : 0.f;
+  for (int e = threadIdx.x; e < Hg * Wg * 8; e += blockDim.x) gt[e] = 0.f;  // the border (and the padding channels) stay zero
+  // dw / db work split: unit u = threadIdx.x covers tap (or the db row) r = u % (kk + 1), channel half h = (u / (kk + 1)) & 1, and
+  // position slice sl = u / (2 * (kk + 1)); slices = blockDim.x / (2 * (kk + 1)) >= 1 (k*k*Co + Co <= 256 is checked by the host)
+  const int rows = kk + 1, slices = int(blockDim.x) / (2 * rows);
+  const int u = threadIdx.x, r = u % rows, hf = (u / rows) & 1, sl = u / (2 * rows);
+  const bool worker = sl < slices;
+  const int ti = r < kk ? r / k : 0, tj = r < kk ? r % k : 0;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
-    for (int e = threadIdx.x; e < Hp * Wp; e += blockDim.x) {
-      const int h = e / Wp - pad, w = e % Wp - pad;
-      img[e] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldcs(im + (int64_t(b) * H + h) * W + w) : 0.f;
+    const float* src = im + int64_t(b) * H * W;
+    if (pad == 0) {
+      for (int e = threadIdx.x; e < H * W; e += blockDim.x) img[e] = __ldcs(src + e);
+    } else {
+      for (int e = threadIdx.x; e < Hp * Wp; e += blockDim.x) {
+        const int h = e / Wp - pad, w = e % Wp - pad;
+        img[e] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldcs(src + h * W + w) : 0.f;
+      }
     }
     const float* gb = g + int64_t(b) * P * co;
-    for (int e = threadIdx.x; e < P * co; e += blockDim.x) gt[e] = __ldcs(gb + e);
+    {
+      int p = int(threadIdx.x) / co, o = int(threadIdx.x) - p * co;   // element e = p*co + o of the sample's gradient, no division per element
+      int y = p / Wo, x = p - y * Wo;
+      const int dp = int(blockDim.x) / co, d_o = int(blockDim.x) - dp * co;
+      for (int e = threadIdx.x; e < P * co; e += blockDim.x) {
+        gt[((y + bd) * Wg + x + bd) * 8 + o] = __ldcs(gb + e);
+        o += d_o; x += dp;
+        if (o >= co) { o -= co; ++x; }
+        while (x >= Wo) { x -= Wo; ++y; }
+      }
+    }
     __syncthreads();
-    // dw / db: one accumulator per thread, positions in ascending order
-    if (int(threadIdx.x) < nacc) {
-      if (my_t >= 0) {
-        for (int y = 0; y < Ho; ++y) {
-          const float* row = img + (y * s + my_i) * Wp + my_j;
-          const float* gr = gt + y * Wo * co + my_o;
-          for (int x = 0; x < Wo; ++x) acc = fmaf(row[x * s], gr[x * co], acc);
-        }
-      } else {
-        for (int p = 0; p < P; ++p) acc += gt[p * co + my_o];
+    if (worker) {  // positions p = sl, sl + slices, ..: ascending inside the slice
+      int y = sl / Wo, x = sl - y * Wo;  // (y, x) of position p, advanced without a division per position
+      const float* tap = img + ti * Wp + tj;
+      const float* gp = gt + (bd * Wg + bd) * 8 + hf * 4;
+      for (int p = sl; p < P; p += slices) {
+        const float v = r < kk ? tap[y * s * Wp + x * s] : 1.0f;  // the db row sums g itself
+        const float4 gv = *reinterpret_cast<const float4*>(gp + (y * Wg + x) * 8);
+        a0 = fmaf(v, gv.x, a0); a1 = fmaf(v, gv.y, a1); a2 = fmaf(v, gv.z, a2); a3 = fmaf(v, gv.w, a3);
+        x += slices;
+        while (x >= Wo) { x -= Wo; ++y; }
       }
     }
     // dx[b, 0, u, v] = sum over positions (y, x) ascending and taps with y*s + i == u, x*s + j == v of g[y, x, :] . filt[i*k + j, :]
+    int uu = int(threadIdx.x) / wx, vv = int(threadIdx.x) - uu * wx;
     for (int e = threadIdx.x; e < hx * wx; e += blockDim.x) {
-      const int u = e / wx, v = e % wx;
       float a = 0.f;
-      for (int i = k - 1; i >= 0; --i) {  // i descending = y ascending
-        const int uy = u - i;
-        if (uy < 0 || uy % s) continue;
-        const int y = uy / s;
-        if (y >= Ho) continue;
-        for (int j = k - 1; j >= 0; --j) {
-          const int vx = v - j;
-          if (vx < 0 || vx % s) continue;
-          const int x = vx / s;
-          if (x >= Wo) continue;
-          const float* gp = gt + (y * Wo + x) * co;
-          const float* f = fl + (i * k + j) * co;
-          float t = 0.f;
+      if (S1) {
+        // stride 1: y = u - i, x = v - j; in the bordered tile every (i, j) is in range, the border contributes exact zeros
+        const float* gq = gt + (uu * Wg + vv) * 8;  // tile position (u - i + bd, v - j + bd) for i = j = bd
 #pragma unroll
-          for (int o = 0; o < CO; ++o)
-            if (o < co) t = fmaf(gp[o], f[o], t);  // dxcol[p, t]: the GEMM g . filt^T over C_out
-          a += t;                                  // the overlap-add of col2im
+        for (int i = k - 1; i >= 0; --i) {          // i descending = y ascending
+#pragma unroll
+          for (int j = k - 1; j >= 0; --j)
+            a += dot8(ld8(gq + ((bd - i) * Wg + (bd - j)) * 8), ld8(fl + (i * k + j) * 8));  // dxcol[p, t], then col2im's overlap-add
+        }
+      } else {
+        for (int i = k - 1; i >= 0; --i) {
+          int y = uu - i;
+          if (y < 0 || y % s) continue;
+          y /= s;
+          if (y >= Ho) continue;
+          for (int j = k - 1; j >= 0; --j) {
+            int x = vv - j;
+            if (x < 0 || x % s) continue;
+            x /= s;
+            if (x >= Wo) continue;
+            a += dot8(ld8(gt + ((y + bd) * Wg + x + bd) * 8), ld8(fl + (i * k + j) * 8));
+          }
         }
       }
       __stcs(dx + int64_t(b) * hx * wx + e, a);
+      vv += blockDim.x;
+      while (vv >= wx) { vv -= wx; ++uu; }
     }
   }
-  if (int(threadIdx.x) < nacc) part[int64_t(blockIdx.x) * nacc + threadIdx.x] = acc;
+  // fold the position slices (slice order), then hand this CTA's kk*co + co sums to the cross-CTA fold
+  __syncthreads();
+  if (worker) *reinterpret_cast<float4*>(red + (sl * rows + r) * 8 + hf * 4) = make_float4(a0, a1, a2, a3);
+  __syncthreads();
+  const int nacc = kk * co + co;
+  if (int(threadIdx.x) < nacc) {
+    const int rr = threadIdx.x / co, o = threadIdx.x % co;  // rows 0 .. kk-1: dw, row kk: db
+    float t = 0.f;
+    for (int q = 0; q < slices; ++q) t += red[(q * rows + rr) * 8 + o];
+    part[int64_t(blockIdx.x) * nacc + threadIdx.x] = t;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
   __threadfence();
+  // Cross-CTA fold by the last CTA: thread o adds the partials of output o in CTA order; the loads go out in independent
+  // batches of 8 (a one-at-a-time chain of L2 round trips costs tens of microseconds for ~600 CTAs), the adds stay in order.
   if (int(threadIdx.x) < nacc) {
+    const float* src = part + threadIdx.x;
     float t = 0.f;
-    for (unsigned c = 0; c < gridDim.x; ++c) t += __ldcg(part + int64_t(c) * nacc + threadIdx.x);
-    if (my_t >= 0) dw[threadIdx.x] = t;  // [k][k][co] == [kk][co]
-    else           db[my_o] = t;
+    unsigned c = 0;
+    for (; c + 8 <= gridDim.x; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + int64_t(c + q) * nacc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += v[q];
+    }
+    for (; c < gridDim.x; ++c) t += __ldcg(src + int64_t(c) * nacc);
+    if (int(threadIdx.x) < kk * co) dw[threadIdx.x] = t;  // [k][k][co] == [kk][co]
+    else                            db[threadIdx.x - kk * co] = t;
   }
   if (threadIdx.x == 0) *ticket = 0;
 }
@@ -400,6 +478,7 @@ extern "C" {
 int agrs_im2col_f32(agrs_ctx* ctx, const float* im, int64_t B, int64_t C, int64_t H, int64_t W, int64_t k, int64_t stride,
                     int64_t pad, float* col) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_im2col_f32");
   AGRS_REQUIRE(ctx, B >= 0 && C >= 0 && H >= 0 && W >= 0 && k > 0 && stride > 0 && pad >= 0, AGRS_ERR_INVALID, "agrs_im2col_f32: bad geometry");
   AGRS_REQUIRE(ctx, H + 2 * pad >= k && W + 2 * pad >= k, AGRS_ERR_SHAPE, "agrs_im2col_f32: kernel %lld larger than padded image %lldx%lld",
                (long long)k, (long long)(H + 2 * pad), (long long)(W + 2 * pad));
@@ -433,6 +512,7 @@ int agrs_im2col_f32(agrs_ctx* ctx, const float* im, int64_t B, int64_t C, int64_
 int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t C, int64_t Ho, int64_t Wo, int64_t k, int64_t stride,
                     float* im_out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_col2im_f32");
   AGRS_REQUIRE(ctx, B >= 0 && C >= 0 && Ho > 0 && Wo > 0 && k > 0 && stride > 0, AGRS_ERR_INVALID, "agrs_col2im_f32: bad geometry");
   int64_t Hi = (Ho - 1) * stride + k, Wi = (Wo - 1) * stride + k;
   int64_t total = B * C * Hi * Wi;
@@ -476,6 +556,7 @@ int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t C, int64
 
 int agrs_broadcast_filter_f32(agrs_ctx* ctx, const float* filt, int64_t kk, int64_t c_out, int64_t c_in, float* out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_broadcast_filter_f32");
   AGRS_REQUIRE(ctx, kk >= 0 && c_out >= 0 && c_in >= 0, AGRS_ERR_INVALID, "agrs_broadcast_filter_f32: negative extent");
   int64_t per = kk * c_out, total = per * c_in;
   if (total == 0) return AGRS_OK;
@@ -491,10 +572,13 @@ static bool conv1_shape_ok(int64_t B, int64_t H, int64_t W, int64_t k, int64_t c
   if (B < 1 || k < 1 || k > 11 || co < 1 || co > kConvCo || stride < 1 || pad < 0 || H + 2 * pad < k || W + 2 * pad < k) return false;
   const int64_t Ho = (H - k + 2 * pad) / stride + 1, Wo = (W - k + 2 * pad) / stride + 1;
   if (k * k * co + co > 256) return false;  // one dw / db accumulator per thread
-  const size_t img = size_t(H + 2 * pad) * size_t(W + 2 * pad), fl = size_t(k * k * co);
-  *smem_fwd = (img + fl) * sizeof(float);
-  *smem_bwd = (img + size_t(Ho * Wo * co) + fl) * sizeof(float);
-  return *smem_bwd <= 160 * 1024 && B < (int64_t(1) << 31) && H < 32768 && W < 32768;
+  if (2 * (k * k + 1) > 256) return false;   // at least one position slice of (tap, channel half) threads
+  const size_t img = (size_t(H + 2 * pad) * size_t(W + 2 * pad) + 3) & ~size_t(3), fl = size_t(k * k * 8), P = size_t(Ho * Wo);
+  const size_t slices = 256 / (2 * size_t(k * k + 1));
+  *smem_fwd = (fl + 8 + img + P * size_t(co)) * sizeof(float);
+  const size_t gtile = size_t(Ho + 2 * (k - 1)) * size_t(Wo + 2 * (k - 1)) * 8;  // gradient tile with its zero border
+  *smem_bwd = (fl + gtile + img + slices * size_t(k * k + 1) * 8) * sizeof(float);
+  return *smem_bwd <= 160 * 1024 && *smem_fwd <= 160 * 1024 && B < (int64_t(1) << 31) && H < 32768 && W < 32768;
 }
 
 int agrs_conv2d_implicit_ok(int64_t B, int64_t C, int64_t H, int64_t W, int64_t k, int64_t c_out, int64_t stride, int64_t pad) {
@@ -505,14 +589,19 @@ int agrs_conv2d_implicit_ok(int64_t B, int64_t C, int64_t H, int64_t W, int64_t 
 int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W, int64_t k,
                         int64_t c_out, int64_t stride, int64_t pad, float* out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_conv2d_fwd_f32");
   size_t smem = 0, smem_b = 0;
   AGRS_REQUIRE(ctx, conv1_shape_ok(B, H, W, k, c_out, stride, pad, &smem, &smem_b), AGRS_ERR_UNSUPPORTED,
                "agrs_conv2d_fwd_f32: shape outside the implicit-GEMM kernels (single input channel, C_out <= %d, k*k*C_out + C_out <= 256): use im2col + GEMM", kConvCo);
   AGRS_REQUIRE(ctx, im && filt && bias && out, AGRS_ERR_INVALID, "agrs_conv2d_fwd_f32: null pointer");
   const int Ho = int((H - k + 2 * pad) / stride + 1), Wo = int((W - k + 2 * pad) / stride + 1);
   const int64_t cap = int64_t(ctx->sm_count) * 4;
-  AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd<kConvCo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  k_conv1_fwd<kConvCo><<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo, out);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  k_conv1_fwd<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo, out);
   AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }
@@ -520,12 +609,13 @@ int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
 int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* grad, int64_t B, int64_t H, int64_t W, int64_t k,
                         int64_t c_out, int64_t stride, int64_t pad, float* dx, float* dw, float* db) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_conv2d_bwd_f32");
   size_t smem_f = 0, smem = 0;
   AGRS_REQUIRE(ctx, conv1_shape_ok(B, H, W, k, c_out, stride, pad, &smem_f, &smem), AGRS_ERR_UNSUPPORTED,
                "agrs_conv2d_bwd_f32: shape outside the implicit-GEMM kernels: use the im2col path");
   AGRS_REQUIRE(ctx, im && filt && grad && dx && dw && db, AGRS_ERR_INVALID, "agrs_conv2d_bwd_f32: null pointer");
   const int Ho = int((H - k + 2 * pad) / stride + 1), Wo = int((W - k + 2 * pad) / stride + 1);
-  const int64_t cap = int64_t(ctx->sm_count) * 2;
+  const int64_t cap = int64_t(ctx->sm_count) * 4;
   const int64_t grid = B < cap ? B : cap;
   const size_t nacc = size_t(k * k * c_out + c_out);
   int rc = agrs_ensure_workspace(ctx, size_t(grid) * nacc * sizeof(float));
@@ -536,9 +626,21 @@ int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
     AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, 4096 * sizeof(unsigned int), ctx->stream));
     ctx->tickets_n = 4096;
   }
-  AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd<kConvCo>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  k_conv1_bwd<kConvCo><<<unsigned(grid), 256, smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo,
-                                                                  dx, dw, db, ctx->workspace, ctx->tickets);
+#define AGRS_CONV_BWD(S1_, KT_)                                                                                                            \
+  do {                                                                                                                                   \
+    static bool attr_set = false;                                                                                                        \
+    if (!attr_set) {                                                                                                                     \
+      AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd<S1_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));               \
+      attr_set = true;                                                                                                                   \
+    }                                                                                                                                    \
+    k_conv1_bwd<S1_, KT_><<<unsigned(grid), 256, smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(k), int(c_out), int(stride), \
+                                                                      int(pad), Ho, Wo, dx, dw, db, ctx->workspace, ctx->tickets);        \
+  } while (0)
+  if (stride != 1) AGRS_CONV_BWD(false, 0);
+  else if (k == 5) AGRS_CONV_BWD(true, 5);
+  else if (k == 3) AGRS_CONV_BWD(true, 3);
+  else             AGRS_CONV_BWD(true, 0);
+#undef AGRS_CONV_BWD
   AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }

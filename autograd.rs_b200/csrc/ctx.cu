@@ -94,6 +94,7 @@ const char* agrs_last_error(agrs_ctx* ctx) { return ctx ? ctx->err.c_str() : "nu
 
 int agrs_sync(agrs_ctx* ctx) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sync");
   AGRS_NOT_CAPTURING(ctx, "agrs_sync");
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AGRS_OK;
@@ -108,6 +109,7 @@ struct agrs_graph {
 
 int agrs_capture_begin(agrs_ctx* ctx) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_capture_begin");
   AGRS_NOT_CAPTURING(ctx, "agrs_capture_begin");
   AGRS_REQUIRE(ctx, !ctx->profiling, AGRS_ERR_UNSUPPORTED, "agrs_capture_begin: disable agrs_profile_enable first");
   AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -165,6 +167,7 @@ int agrs_capture_end(agrs_ctx* ctx, agrs_graph** out) {
 
 int agrs_graph_launch(agrs_ctx* ctx, agrs_graph* graph, int times) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_graph_launch");
   AGRS_NOT_CAPTURING(ctx, "agrs_graph_launch");
   AGRS_REQUIRE(ctx, graph && graph->exec && times >= 0, AGRS_ERR_INVALID, "agrs_graph_launch: bad arguments");
   for (int i = 0; i < times; ++i) AGRS_CUDA(ctx, cudaGraphLaunch(graph->exec, ctx->stream));
@@ -190,6 +193,7 @@ int agrs_graph_info(agrs_graph* graph, uint64_t* kernel_nodes, uint64_t* total_n
 
 int agrs_timer_begin(agrs_ctx* ctx) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_timer_begin");
   AGRS_NOT_CAPTURING(ctx, "agrs_timer_begin");
   if (!ctx->timer_a) {
     AGRS_CUDA(ctx, cudaEventCreate(&ctx->timer_a));
@@ -201,6 +205,7 @@ int agrs_timer_begin(agrs_ctx* ctx) {
 
 int agrs_timer_end(agrs_ctx* ctx, float* ms) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_timer_end");
   AGRS_NOT_CAPTURING(ctx, "agrs_timer_end");
   AGRS_REQUIRE(ctx, ms && ctx->timer_a, AGRS_ERR_INVALID, "agrs_timer_end without agrs_timer_begin");
   AGRS_CUDA(ctx, cudaEventRecord(ctx->timer_b, ctx->stream));
@@ -215,6 +220,7 @@ uint64_t agrs_launch_count(agrs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int agrs_device_info(agrs_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_device_info");
   if (sm_count) *sm_count = ctx->sm_count;
   if (cc_major) *cc_major = ctx->cc_major;
   if (cc_minor) *cc_minor = ctx->cc_minor;
@@ -230,6 +236,7 @@ int agrs_device_info(agrs_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor,
 
 int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_alloc");
   AGRS_REQUIRE(ctx, out != nullptr, AGRS_ERR_INVALID, "agrs_alloc: null out");
   if (nbytes == 0) nbytes = 4;  // empty tensors still get a distinct address
   AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -240,6 +247,7 @@ int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
 
 int agrs_pool_reserve(agrs_ctx* ctx, size_t nbytes) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_pool_reserve");
   AGRS_NOT_CAPTURING(ctx, "agrs_pool_reserve");
   if (nbytes == 0) return AGRS_OK;
   void* p = nullptr;
@@ -252,6 +260,7 @@ int agrs_pool_reserve(agrs_ctx* ctx, size_t nbytes) {
 
 int agrs_pool_stats(agrs_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes, size_t* reserved_high, size_t* used_high) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_pool_stats");
   uint64_t v = 0;
   if (reserved_bytes) { AGRS_CUDA(ctx, cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &v)); *reserved_bytes = size_t(v); }
   if (used_bytes) { AGRS_CUDA(ctx, cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrUsedMemCurrent, &v)); *used_bytes = size_t(v); }
@@ -262,6 +271,7 @@ int agrs_pool_stats(agrs_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes, s
 
 int agrs_free(agrs_ctx* ctx, void* ptr) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_free");
   if (!ptr) return AGRS_OK;
   if (ctx->capturing) {
     auto it = ctx->capture_allocs.find(ptr);
@@ -277,6 +287,7 @@ int agrs_free(agrs_ctx* ctx, void* ptr) {
 
 int agrs_host_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_host_alloc");
   AGRS_REQUIRE(ctx, out != nullptr, AGRS_ERR_INVALID, "agrs_host_alloc: null out");
   AGRS_CUDA(ctx, cudaMallocHost(out, nbytes ? nbytes : 4));
   return AGRS_OK;
@@ -284,12 +295,14 @@ int agrs_host_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
 
 int agrs_host_free(agrs_ctx* ctx, void* ptr) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_host_free");
   if (ptr) AGRS_CUDA(ctx, cudaFreeHost(ptr));
   return AGRS_OK;
 }
 
 int agrs_upload(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_upload");
   if (nbytes == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_upload: null pointer");
   // pageable sources are staged by the runtime before the call returns; pinned ones stay async
@@ -299,6 +312,7 @@ int agrs_upload(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
 
 int agrs_download(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_download");
   if (nbytes == 0) return AGRS_OK;
   AGRS_NOT_CAPTURING(ctx, "agrs_download");
   AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_download: null pointer");
@@ -309,6 +323,7 @@ int agrs_download(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
 
 int agrs_upload_prefetch(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_upload_prefetch");
   if (nbytes == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_upload_prefetch: null pointer");
   if (!ctx->copy_stream) {
@@ -326,6 +341,7 @@ int agrs_upload_prefetch(agrs_ctx* ctx, void* dst, const void* src, size_t nbyte
 
 int agrs_prefetch_join(agrs_ctx* ctx) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_prefetch_join");
   if (!ctx->copy_stream) return AGRS_OK;
   AGRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
   return AGRS_OK;
@@ -333,6 +349,7 @@ int agrs_prefetch_join(agrs_ctx* ctx) {
 
 int agrs_copy(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_copy");
   if (nbytes == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, dst && src, AGRS_ERR_INVALID, "agrs_copy: null pointer");
   AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -341,6 +358,7 @@ int agrs_copy(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
 
 int agrs_set_gemm_path(agrs_ctx* ctx, int path) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_set_gemm_path");
   AGRS_REQUIRE(ctx, path >= AGRS_GEMM_AUTO && path <= AGRS_GEMM_SKINNY, AGRS_ERR_INVALID, "unknown gemm path %d", path);
   ctx->gemm_path = path;
   return AGRS_OK;

@@ -270,12 +270,14 @@ extern "C" {
 
 int agrs_next_output_absmax(agrs_ctx* ctx, uint32_t* out_bits) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_next_output_absmax");
   ctx->next_out_mx = out_bits;
   return AGRS_OK;
 }
 
 int agrs_absmax_f32(agrs_ctx* ctx, const float* x, size_t n, uint32_t* out_bits) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_absmax_f32");
   AGRS_REQUIRE(ctx, out_bits && (n == 0 || x), AGRS_ERR_INVALID, "agrs_absmax_f32: null pointer");
   AGRS_CUDA(ctx, cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), ctx->stream));
   if (n == 0) return AGRS_OK;
@@ -293,6 +295,7 @@ int agrs_absmax_f32(agrs_ctx* ctx, const float* x, size_t n, uint32_t* out_bits)
 
 int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fill_f32");
   if (n == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, x, AGRS_ERR_INVALID, "agrs_fill_f32: null pointer");
   if (value == 0.0f) {  // zero_grad / zeros: the copy engine's memset
@@ -313,33 +316,39 @@ int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n) {
 
 int agrs_relu_fwd_f32(agrs_ctx* ctx, const float* x, float* y, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_relu_fwd_f32");
   AGRS_REQUIRE(ctx, n == 0 || (x && y), AGRS_ERR_INVALID, "agrs_relu_fwd_f32: null pointer");
   return launch_unary(ctx, ReluFwd{}, y, x, n);
 }
 int agrs_relu_bwd_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_relu_bwd_f32");
   AGRS_REQUIRE(ctx, n == 0 || (x && g && dx), AGRS_ERR_INVALID, "agrs_relu_bwd_f32: null pointer");
   return launch_binary(ctx, ReluBwd{}, dx, x, g, n);
 }
 int agrs_sigmoid_fwd_f32(agrs_ctx* ctx, const float* x, float* y, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sigmoid_fwd_f32");
   AGRS_REQUIRE(ctx, n == 0 || (x && y), AGRS_ERR_INVALID, "agrs_sigmoid_fwd_f32: null pointer");
   return launch_unary(ctx, SigmoidFwd{}, y, x, n);
 }
 int agrs_sigmoid_bwd_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sigmoid_bwd_f32");
   AGRS_REQUIRE(ctx, n == 0 || (x && g && dx), AGRS_ERR_INVALID, "agrs_sigmoid_bwd_f32: null pointer");
   return launch_binary(ctx, SigmoidBwd{}, dx, x, g, n);
 }
 int agrs_mse_bwd_f32(agrs_ctx* ctx, const float* pred, const float* target, const float* upstream1, float batch, size_t n,
                      float* out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_mse_bwd_f32");
   AGRS_REQUIRE(ctx, n == 0 || (pred && target && upstream1 && out), AGRS_ERR_INVALID, "agrs_mse_bwd_f32: null pointer");
   return launch_binary(ctx, MseBwd{batch, upstream1}, out, pred, target, n);
 }
 
 int agrs_binary_f32(agrs_ctx* ctx, int op, float* out, const float* a, const float* b, size_t n, size_t nb, int bmode) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_binary_f32");
   AGRS_REQUIRE(ctx, n == 0 || (out && a && b), AGRS_ERR_INVALID, "agrs_binary_f32: null pointer");
   AGRS_REQUIRE(ctx, bmode == AGRS_BCAST_TRAILING || bmode == AGRS_BCAST_LEADING, AGRS_ERR_INVALID, "unknown broadcast mode %d", bmode);
   switch (op) {
@@ -352,6 +361,7 @@ int agrs_binary_f32(agrs_ctx* ctx, int op, float* out, const float* a, const flo
 
 int agrs_scalar_f32(agrs_ctx* ctx, int op, float* out, const float* a, float s, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_scalar_f32");
   AGRS_REQUIRE(ctx, n == 0 || (out && a), AGRS_ERR_INVALID, "agrs_scalar_f32: null pointer");
   switch (op) {
     case AGRS_SMUL: return launch_unary(ctx, SMul{s}, out, a, n);
@@ -364,12 +374,14 @@ int agrs_scalar_f32(agrs_ctx* ctx, int op, float* out, const float* a, float s, 
 
 int agrs_neg_f32(agrs_ctx* ctx, float* out, const float* a, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_neg_f32");
   AGRS_REQUIRE(ctx, n == 0 || (out && a), AGRS_ERR_INVALID, "agrs_neg_f32: null pointer");
   return launch_unary(ctx, NegOp{}, out, a, n);
 }
 
 int agrs_powi_f32(agrs_ctx* ctx, float* out, const float* a, int exp, size_t n) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_powi_f32");
   AGRS_REQUIRE(ctx, n == 0 || (out && a), AGRS_ERR_INVALID, "agrs_powi_f32: null pointer");
   if (exp == 2) return launch_unary(ctx, Sq{}, out, a, n);
   return launch_unary(ctx, PowiOp{exp}, out, a, n);
@@ -377,6 +389,7 @@ int agrs_powi_f32(agrs_ctx* ctx, float* out, const float* a, int exp, size_t n) 
 
 int agrs_sgd_step_f32(agrs_ctx* ctx, float* w, const float* g, float lr, size_t n, size_t ng) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sgd_step_f32");
   AGRS_REQUIRE(ctx, n == 0 || (w && g), AGRS_ERR_INVALID, "agrs_sgd_step_f32: null pointer");
   return launch_bcast(ctx, SgdOp{lr}, w, w, g, n, ng, AGRS_BCAST_TRAILING);
 }

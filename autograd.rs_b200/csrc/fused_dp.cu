@@ -341,6 +341,7 @@ extern "C" {
 
 int agrs_peer_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_peer_alloc");
   AGRS_NOT_CAPTURING(ctx, "agrs_peer_alloc");
   AGRS_REQUIRE(ctx, out && nbytes > 0, AGRS_ERR_INVALID, "agrs_peer_alloc: bad arguments");
   AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -352,6 +353,7 @@ int agrs_peer_alloc(agrs_ctx* ctx, size_t nbytes, void** out) {
 
 int agrs_peer_free(agrs_ctx* ctx, void* ptr) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_peer_free");
   if (!ptr) return AGRS_OK;
   AGRS_CUDA(ctx, cudaDeviceSynchronize());  // comm / copy streams of an exchange that used the arena included
   AGRS_CUDA(ctx, cudaFree(ptr));
@@ -360,6 +362,7 @@ int agrs_peer_free(agrs_ctx* ctx, void* ptr) {
 
 int agrs_peer_export(agrs_ctx* ctx, void* ptr, void* handle64) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_peer_export");
   AGRS_REQUIRE(ctx, ptr && handle64, AGRS_ERR_INVALID, "agrs_peer_export: null pointer");
   cudaIpcMemHandle_t h;
   static_assert(sizeof(h) == AGRS_PEER_HANDLE_BYTES, "IPC handle size");
@@ -370,6 +373,7 @@ int agrs_peer_export(agrs_ctx* ctx, void* ptr, void* handle64) {
 
 int agrs_peer_open(agrs_ctx* ctx, const void* handle64, void** out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_peer_open");
   AGRS_REQUIRE(ctx, handle64 && out, AGRS_ERR_INVALID, "agrs_peer_open: null pointer");
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, sizeof(h));
@@ -380,6 +384,7 @@ int agrs_peer_open(agrs_ctx* ctx, const void* handle64, void** out) {
 
 int agrs_peer_close(agrs_ctx* ctx, void* ptr) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_peer_close");
   if (ptr) AGRS_CUDA(ctx, cudaIpcCloseMemHandle(ptr));
   return AGRS_OK;
 }
@@ -390,6 +395,7 @@ int agrs_fused_max_buckets(void) { return kMaxBuckets; }
 int agrs_fused_create(agrs_ctx* ctx, int world, int rank, void* const* arenas, size_t w_off, size_t w_alt, size_t g_off, size_t total,
                       int granule_log2, agrs_fused** out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fused_create");
   AGRS_REQUIRE(ctx, out && arenas && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, AGRS_ERR_INVALID,
                "agrs_fused_create: bad arguments (world <= %d)", kMaxWorld);
   AGRS_REQUIRE(ctx, granule_log2 >= 5 && granule_log2 <= 24, AGRS_ERR_INVALID, "agrs_fused_create: granule_log2 must be 5 .. 24");
@@ -615,6 +621,7 @@ int agrs_fused_scatter_f32(agrs_fused* f, const float* src, size_t off, size_t n
   if (!f) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = f->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fused_scatter_f32");
   if (n == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, src && agrs_aligned16(src) && off % 4 == 0 && off + n <= f->args.total, AGRS_ERR_INVALID,
                "agrs_fused_scatter_f32: source must be 16-byte aligned and [off, off+n) a 4-aligned range of the gradient region");
@@ -632,6 +639,7 @@ int agrs_fused_begin_step(agrs_fused* f, float lr) {
   if (!f) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = f->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fused_begin_step");
   AGRS_NOT_CAPTURING(ctx, "agrs_fused_begin_step (flag generations are launch arguments)");
   AGRS_REQUIRE(ctx, !f->open, AGRS_ERR_INVALID, "agrs_fused_begin_step: the previous step was not finished");
   f->args.lr = lr;
@@ -669,6 +677,7 @@ int agrs_fused_bucket_ready(agrs_fused* f, int bucket, size_t off, size_t n) {
   if (!f) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = f->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fused_bucket_ready");
   const FusedArgs& a = f->args;
   const size_t GW = (size_t(1) << a.gshift) * size_t(a.world);
   AGRS_REQUIRE(ctx, f->open, AGRS_ERR_INVALID, "agrs_fused_bucket_ready outside agrs_fused_begin_step / agrs_fused_finish_step");
@@ -772,6 +781,7 @@ int agrs_fused_finish_step(agrs_fused* f) {
   if (!f) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = f->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fused_finish_step");
   AGRS_REQUIRE(ctx, f->open, AGRS_ERR_INVALID, "agrs_fused_finish_step without agrs_fused_begin_step");
   const FusedArgs& a = f->args;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -840,6 +850,7 @@ int agrs_fused_exposed_ms(agrs_fused* f, double* total_ms, uint64_t* steps) {
   if (!f) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = f->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fused_exposed_ms");
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   double ms = 0.0;
   for (auto& pr : f->exposed) {
@@ -866,6 +877,7 @@ int agrs_fused_sgd_step(agrs_fused* f, float lr) {
   if (!f) return AGRS_ERR_INVALID;
   agrs_ctx* ctx = f->ctx;
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_fused_sgd_step");
   AGRS_NOT_CAPTURING(ctx, "agrs_fused_sgd_step (its barrier generation is a launch argument)");
   AGRS_REQUIRE(ctx, !f->open, AGRS_ERR_INVALID, "agrs_fused_sgd_step inside an open bucket step");
   f->args.lr = lr;

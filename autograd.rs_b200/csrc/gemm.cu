@@ -35,6 +35,7 @@ extern "C" {
 
 int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_set_tuning");
   switch (key) {
     case AGRS_TUNE_TC_BN:
       AGRS_REQUIRE(ctx, value == 128 || value == 256, AGRS_ERR_INVALID, "AGRS_TUNE_TC_BN must be 128 or 256");
@@ -73,6 +74,7 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
 
 int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_get_tuning");
   AGRS_REQUIRE(ctx, value, AGRS_ERR_INVALID, "agrs_get_tuning: null out");
   switch (key) {
     case AGRS_TUNE_TC_BN: *value = ctx->tc_bn; return AGRS_OK;
@@ -91,6 +93,7 @@ int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value) {
 int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                   const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_gemm_f32");
   // magnitudes announced for this call (agrs_gemm_operand_absmax): consumed here whatever path the call takes
   const uint32_t *a_mx = ctx->gemm_a_mx, *b_mx = ctx->gemm_b_mx;
   ctx->gemm_a_mx = ctx->gemm_b_mx = nullptr;
@@ -140,6 +143,7 @@ int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
 
 int agrs_gemm_operand_absmax(agrs_ctx* ctx, const uint32_t* a_bits, const uint32_t* b_bits) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_gemm_operand_absmax");
   ctx->gemm_a_mx = a_bits;
   ctx->gemm_b_mx = b_bits;
   return AGRS_OK;
@@ -153,6 +157,7 @@ int agrs_gemm_wants_absmax(agrs_ctx* ctx, int64_t M, int64_t N, int64_t K) {
 
 int agrs_profile_enable(agrs_ctx* ctx, int on) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_profile_enable");
   AGRS_NOT_CAPTURING(ctx, "agrs_profile_enable");
   ctx->profiling = on != 0;
   return AGRS_OK;
@@ -160,6 +165,7 @@ int agrs_profile_enable(agrs_ctx* ctx, int on) {
 
 int agrs_profile_gemm(agrs_ctx* ctx, int path, uint64_t* launches, double* total_ms, double* total_flops) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_profile_gemm");
   AGRS_NOT_CAPTURING(ctx, "agrs_profile_gemm");
   AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   uint64_t n = 0;

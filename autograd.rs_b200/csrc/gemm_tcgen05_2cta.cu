@@ -949,6 +949,7 @@ void agrs_fused_scatter_target(const agrs_fused* f, float* const** bases, int* w
 extern "C" int agrs_gemm_f32_scatter(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                                      const float* B, int64_t ldb, float* C, const float* bias, agrs_fused* f, size_t off) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_gemm_f32_scatter");
   const uint32_t *a_mx = ctx->gemm_a_mx, *b_mx = ctx->gemm_b_mx;  // agrs_gemm_operand_absmax: consumed by this call
   ctx->gemm_a_mx = ctx->gemm_b_mx = nullptr;
   AGRS_REQUIRE(ctx, f, AGRS_ERR_INVALID, "agrs_gemm_f32_scatter: null exchange");

@@ -383,24 +383,28 @@ extern "C" {
 
 int agrs_sum_f32(agrs_ctx* ctx, const float* x, size_t n, float* out1) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sum_f32");
   AGRS_REQUIRE(ctx, out1 && (n == 0 || x), AGRS_ERR_INVALID, "agrs_sum_f32: null pointer");
   return launch_reduce_all(ctx, LoadId{x}, n, agrs_aligned16(x), 1.0f, out1);
 }
 
 int agrs_mean_f32(agrs_ctx* ctx, const float* x, size_t n, float* out1) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_mean_f32");
   AGRS_REQUIRE(ctx, out1 && x && n > 0, AGRS_ERR_INVALID, "agrs_mean_f32: empty or null input");
   return launch_reduce_all(ctx, LoadId{x}, n, agrs_aligned16(x), 1.0f / float(n), out1);
 }
 
 int agrs_mse_fwd_f32(agrs_ctx* ctx, const float* pred, const float* target, size_t n, float* out1) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_mse_fwd_f32");
   AGRS_REQUIRE(ctx, out1 && pred && target && n > 0, AGRS_ERR_INVALID, "agrs_mse_fwd_f32: empty or null input");
   return launch_reduce_all(ctx, LoadSqDiff{pred, target}, n, agrs_aligned16(pred) && agrs_aligned16(target), 1.0f / float(n), out1);
 }
 
 int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len, int64_t inner, float* out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sum_axis_f32");
   AGRS_REQUIRE(ctx, outer >= 0 && len >= 0 && inner >= 0, AGRS_ERR_INVALID, "agrs_sum_axis_f32: negative extent");
   int64_t out_elems = outer * inner;
   if (out_elems == 0) return AGRS_OK;
@@ -445,21 +449,25 @@ int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int64_t len,
 
 int agrs_relu_bwd_colsum_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, int64_t rows, int64_t cols, float* colsum) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_relu_bwd_colsum_f32");
   return fused_bwd_colsum(ctx, SrcReluBwd{x, g, dx}, "agrs_relu_bwd_colsum_f32", rows, cols, x, g, dx, colsum);
 }
 int agrs_sigmoid_bwd_colsum_f32(agrs_ctx* ctx, const float* x, const float* g, float* dx, int64_t rows, int64_t cols, float* colsum) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sigmoid_bwd_colsum_f32");
   return fused_bwd_colsum(ctx, SrcSigmoidBwd{x, g, dx}, "agrs_sigmoid_bwd_colsum_f32", rows, cols, x, g, dx, colsum);
 }
 int agrs_mse_bwd_colsum_f32(agrs_ctx* ctx, const float* pred, const float* target, const float* upstream1, float batch, int64_t rows, int64_t cols,
                             float* out, float* colsum) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_mse_bwd_colsum_f32");
   AGRS_REQUIRE(ctx, upstream1, AGRS_ERR_INVALID, "agrs_mse_bwd_colsum_f32: null upstream");
   return fused_bwd_colsum(ctx, SrcMseBwd{pred, target, upstream1, batch, out}, "agrs_mse_bwd_colsum_f32", rows, cols, pred, target, out, colsum);
 }
 
 int agrs_equal_f32(agrs_ctx* ctx, const float* a, const float* b, size_t n, int* host_equal) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_equal_f32");
   AGRS_NOT_CAPTURING(ctx, "agrs_equal_f32");
   AGRS_REQUIRE(ctx, host_equal && (n == 0 || (a && b)), AGRS_ERR_INVALID, "agrs_equal_f32: null pointer");
   unsigned* flag = ctx->counter + 8;  // second cache line of the counter block
@@ -480,6 +488,7 @@ int agrs_equal_f32(agrs_ctx* ctx, const float* a, const float* b, size_t n, int*
 
 int agrs_transpose_f32(agrs_ctx* ctx, const float* in, int64_t rows, int64_t cols, float* out) {
   AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_transpose_f32");
   AGRS_REQUIRE(ctx, rows >= 0 && cols >= 0, AGRS_ERR_INVALID, "agrs_transpose_f32: negative extent");
   if (rows == 0 || cols == 0) return AGRS_OK;
   AGRS_REQUIRE(ctx, in && out, AGRS_ERR_INVALID, "agrs_transpose_f32: null pointer");

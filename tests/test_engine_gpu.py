@@ -664,7 +664,7 @@ def test_example_rs_hand_written_step_tracks_oracle(dev):
     model = W.build_mlp(dev, ws, bs, "sigmoid")
     ol = [O.OLinearLayer(w.copy(), b.copy()) for w, b in zip(ws, bs)]
     oparams = [q for l in ol for q in l.parameters()]
-    lr = 0.1
+    lr = 0.01   # the example's 0.1 saturates the sigmoids on non-zero data (exp overflows): a parity check needs a conditioned problem
     for epoch in range(2):
         for i in (0, 8):
             x, y = T(dev, xt[i:i + 8]), T(dev, yt[i:i + 8])
