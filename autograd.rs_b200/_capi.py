@@ -58,6 +58,10 @@ def lib():
             "agrs_host_free": [vp, vp],
             "agrs_upload": [vp, vp, vp, sz],
             "agrs_download": [vp, vp, vp, sz],
+            "agrs_event_create": [vp, C.POINTER(vp)],
+            "agrs_event_destroy": [vp, vp],
+            "agrs_download_async": [vp, vp, vp, sz, vp],
+            "agrs_event_wait": [vp, vp],
             "agrs_copy": [vp, vp, vp, sz],
             "agrs_upload_prefetch": [vp, vp, vp, sz],
             "agrs_prefetch_join": [vp],

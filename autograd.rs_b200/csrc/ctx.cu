@@ -347,6 +347,55 @@ int agrs_prefetch_join(agrs_ctx* ctx) {
   return AGRS_OK;
 }
 
+struct agrs_event {
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+};
+
+int agrs_event_create(agrs_ctx* ctx, agrs_event** out) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, out, AGRS_ERR_INVALID, "agrs_event_create: null out");
+  *out = nullptr;
+  AGRS_CUDA(ctx, cudaSetDevice(ctx->device));
+  agrs_event* e = new agrs_event();
+  cudaError_t err = cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming);
+  if (err != cudaSuccess) {
+    delete e;
+    return agrs_fail(ctx, AGRS_ERR_CUDA, "agrs_event_create: %s", cudaGetErrorString(err));
+  }
+  *out = e;
+  return AGRS_OK;
+}
+
+int agrs_event_destroy(agrs_ctx* ctx, agrs_event* ev) {
+  AGRS_CHECK_CTX(ctx);
+  if (!ev) return AGRS_OK;
+  if (ev->ev) AGRS_CUDA(ctx, cudaEventDestroy(ev->ev));
+  delete ev;
+  return AGRS_OK;
+}
+
+int agrs_download_async(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes, agrs_event* done) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_download_async");
+  AGRS_NOT_CAPTURING(ctx, "agrs_download_async");
+  AGRS_REQUIRE(ctx, done && done->ev && (nbytes == 0 || (dst && src)), AGRS_ERR_INVALID, "agrs_download_async: null pointer");
+  if (nbytes) AGRS_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AGRS_CUDA(ctx, cudaEventRecord(done->ev, ctx->stream));
+  done->recorded = true;
+  return AGRS_OK;
+}
+
+int agrs_event_wait(agrs_ctx* ctx, agrs_event* ev) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_event_wait");
+  AGRS_NOT_CAPTURING(ctx, "agrs_event_wait");
+  AGRS_REQUIRE(ctx, ev && ev->ev, AGRS_ERR_INVALID, "agrs_event_wait: null event");
+  if (!ev->recorded) return AGRS_OK;  // nothing was ever enqueued behind it
+  AGRS_CUDA(ctx, cudaEventSynchronize(ev->ev));
+  return AGRS_OK;
+}
+
 int agrs_copy(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes) {
   AGRS_CHECK_CTX(ctx);
   AGRS_RANGE("agrs_copy");

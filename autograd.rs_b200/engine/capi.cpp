@@ -240,6 +240,37 @@ int agrs_eng_tensor_len(const agrs_tensor* t, int64_t* len) {
     *len = t->t.len();
   });
 }
+int agrs_eng_event_create(agrs_device* d, agrs_event** out) {
+  return guarded([&] {
+    need(d, "device");
+    need(out, "out");
+    d->dev.check(agrs_event_create(d->dev.ctx(), out));
+  });
+}
+int agrs_eng_event_destroy(agrs_device* d, agrs_event* ev) {
+  return guarded([&] {
+    need(d, "device");
+    d->dev.check(agrs_event_destroy(d->dev.ctx(), ev));
+  });
+}
+int agrs_eng_event_wait(agrs_device* d, agrs_event* ev) {
+  return guarded([&] {
+    need(d, "device");
+    need(ev, "event");
+    d->dev.check(agrs_event_wait(d->dev.ctx(), ev));
+  });
+}
+int agrs_eng_tensor_to_host_async(const agrs_tensor* t, float* host_out, int64_t n, agrs_event* done) {
+  return guarded([&] {
+    need(t, "tensor");
+    need(done, "event");
+    if (n != t->t.len()) throw Panic("to_host_async: buffer holds " + std::to_string(n) + " elements, tensor has " + std::to_string(t->t.len()));
+    if (n != 0) need(host_out, "out");
+    const Storage& s = *t->t.data;
+    if (s.transposed) throw Panic("to_host_async of a transposed view", AGRS_ERR_UNSUPPORTED);
+    s.dev()->check(agrs_download_async(s.dev()->ctx(), host_out, s.rptr(), size_t(n) * sizeof(float), done));
+  });
+}
 int agrs_eng_tensor_is_contiguous(const agrs_tensor* t, int* yes) {
   return guarded([&] {
     need(t, "tensor");

@@ -69,6 +69,10 @@ def lib():
         "agrs_eng_tensor_copy_from_host": [vp, vp, i64, i32],
         "agrs_eng_tensor_prefetch_from_host": [vp, vp, i64],
         "agrs_eng_device_prefetch_join": [vp],
+        "agrs_eng_event_create": [vp, C.POINTER(vp)],
+        "agrs_eng_event_destroy": [vp, vp],
+        "agrs_eng_event_wait": [vp, vp],
+        "agrs_eng_tensor_to_host_async": [vp, vp, i64, vp],
         "agrs_eng_tensor_clone": [vp, pvp],
         "agrs_eng_tensor_to_owned": [vp, pvp],
         "agrs_eng_tensor_free": [vp],
@@ -265,6 +269,31 @@ class Device:
         return arr
 
 
+class Event:
+    """Completion ticket of an asynchronous read-back (agrs_event)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        h = C.c_void_p()
+        _check(lib().agrs_eng_event_create(dev._h, C.byref(h)))
+        self._h = h
+
+    def wait(self):
+        _check(lib().agrs_eng_event_wait(self.dev._h, self._h))
+
+    def close(self):
+        if self._h:
+            lib().agrs_eng_event_destroy(self.dev._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.dev._h:
+                self.close()
+        except Exception:
+            pass
+
+
 class Graph:
     """A captured sequence of training steps (agrs_graph): every kernel, memset, allocation and collective of the step,
     replayed by the driver without the host walking the model again."""
@@ -390,6 +419,12 @@ class Tensor:
         return out
 
     numpy = data
+
+    def read_async(self, out, event):
+        """Enqueue the read-back of this tensor into the pinned array `out` (Device.pinned_empty) and return at once;
+        `event.wait()` blocks until it has landed.  The loss of step i can be read while step i+1 already runs."""
+        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+        _check(lib().agrs_eng_tensor_to_host_async(self._h, out.ctypes.data, int(out.size), event._h))
 
     def item(self):
         return float(self.data().reshape(-1)[0])

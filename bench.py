@@ -576,18 +576,27 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
         T2.requires_grad = False
         slots = [(X, T), (X2, T2)]
 
+        hl = [dev.pinned_empty((1,)), dev.pinned_empty((1,))]   # pinned landing slots of the per-step loss
+        evs = [F.Event(dev), F.Event(dev)]
+
         def e2e_loop(n):
             slots[0][0].prefetch_from_numpy(hx)     # step 0's inputs: pinned host -> device
             slots[0][1].prefetch_from_numpy(ht)
-            lv = None
+            losses = []
             for i in range(n):
                 dev.prefetch_join()                 # step i's inputs have landed
                 xs, ts = slots[i % 2]
-                if i + 1 < n:                       # step i+1's inputs start moving now, under step i's kernels
+                if i + 1 < n:                       # step i+1's inputs start moving once step i-1 (their slot's last reader) is done
                     slots[(i + 1) % 2][0].prefetch_from_numpy(hx)
                     slots[(i + 1) % 2][1].prefetch_from_numpy(ht)
-                lv = tr.step(xs, ts).item()         # device -> host read of the loss (4 bytes), blocks
-            return lv
+                tr.step(xs, ts).read_async(hl[i % 2], evs[i % 2])   # device -> host copy of the loss, enqueued behind the step
+                if i > 0:                           # the host reads step i-1's loss now that step i is in the queue:
+                    evs[(i - 1) % 2].wait()         # every step's loss reaches the host, the device never waits for the host
+                    losses.append(float(hl[(i - 1) % 2][0]))
+            evs[(n - 1) % 2].wait()
+            losses.append(float(hl[(n - 1) % 2][0]))
+            assert len(losses) == n
+            return losses[-1]
 
         e2e_loop(2)
         job.barrier()
@@ -603,7 +612,9 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
         assert np.isfinite(lv)
         res["e2e"] = {"value": cfg["rows"] * world * steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes + ht.nbytes),
                       "d2h_bytes_per_step": 4, "ms_per_step": ms_e / steps,
-                      "how": "X,T copied from pinned host memory every step on a copy stream (double-buffered, overlapping the previous step), loss read back every step"}
+                      "how": "X,T copied from pinned host memory every step on a copy stream (double-buffered, overlapping the previous step); every step's loss copied to pinned host memory behind the step and read by the host once the next step is enqueued (agrs_download_async / agrs_event_wait)"}
+        for ev in evs:
+            ev.close()
         del X2, T2, slots
     if dp is not None:
         dp.close()

@@ -71,6 +71,15 @@ AGRS_API int agrs_download(agrs_ctx* ctx, void* dst_host, const void* src_dev, s
  * agrs_prefetch_join makes the context's stream wait for all prefetches issued so far.  src_host must be pinned and stay alive. */
 AGRS_API int agrs_upload_prefetch(agrs_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);
 AGRS_API int agrs_prefetch_join(agrs_ctx* ctx);
+/* Read-back that does not stall the pipeline: the copy is enqueued on the context's stream behind the work that produces src_dev
+ * and the call returns; agrs_event_wait blocks the host until THAT copy has landed, not until the stream is empty.  A training
+ * loop reads step i's loss after it has enqueued step i+1 (examples/fit_sine.rs:64-93 reads `loss` every epoch): the device never
+ * idles while the host walks the next step's graph.  dst_host must be pinned (agrs_host_alloc) and stay alive until the wait. */
+typedef struct agrs_event agrs_event;
+AGRS_API int agrs_event_create(agrs_ctx* ctx, agrs_event** out);
+AGRS_API int agrs_event_destroy(agrs_ctx* ctx, agrs_event* ev);
+AGRS_API int agrs_download_async(agrs_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes, agrs_event* done);
+AGRS_API int agrs_event_wait(agrs_ctx* ctx, agrs_event* ev);                                     /* blocks the host */
 AGRS_API int agrs_copy(agrs_ctx* ctx, void* dst_dev, const void* src_dev, size_t nbytes);      /* to_owned() deep copy, tensor.rs:148,160 */
 AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);                     /* storage.rs:75; zeros/ones tensor.rs:67-84; zero_grad tensor.rs:135-140 */
 

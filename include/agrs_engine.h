@@ -71,6 +71,12 @@ AGRS_API int agrs_eng_tensor_shape(const agrs_tensor* t, int64_t* shape_out, int
 AGRS_API int agrs_eng_tensor_len(const agrs_tensor* t, int64_t* len);
 AGRS_API int agrs_eng_tensor_is_contiguous(const agrs_tensor* t, int* yes);
 AGRS_API int agrs_eng_tensor_to_host(const agrs_tensor* t, float* host_out, int64_t n); /* logical row-major order; blocks */
+/* the same read-back without stalling the pipeline (agrs_download_async): enqueued behind the work that produces t, returns at
+ * once; agrs_eng_event_wait blocks until that copy has landed.  `host_out` must be pinned and stay alive; contiguous tensors only. */
+AGRS_API int agrs_eng_event_create(agrs_device* dev, agrs_event** out);
+AGRS_API int agrs_eng_event_destroy(agrs_device* dev, agrs_event* ev);
+AGRS_API int agrs_eng_event_wait(agrs_device* dev, agrs_event* ev);
+AGRS_API int agrs_eng_tensor_to_host_async(const agrs_tensor* t, float* host_out, int64_t n, agrs_event* done);
 AGRS_API int agrs_eng_tensor_data_ptr(const agrs_tensor* t, void** device_ptr);         /* address identity tests (tensor.rs:474-492) */
 AGRS_API int agrs_eng_tensor_requires_grad(const agrs_tensor* t, int* yes);
 AGRS_API int agrs_eng_tensor_set_requires_grad(agrs_tensor* t, int yes);               /* field on the HANDLE, not shared (tensor.rs:28) */

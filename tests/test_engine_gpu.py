@@ -492,6 +492,43 @@ def test_no_host_sync_inside_a_step(dev):
     assert np.isfinite(loss.item())
 
 
+def test_async_loss_read_matches_blocking_read(dev):
+    """Tensor.read_async + Event.wait (agrs_download_async / agrs_event_wait): the loss of every step reaches the host, one step
+    late, with the values a blocking item() gives -- and the host is not held while the device works."""
+    import time
+    ws, bs = W.mlp_init(3, 2048, seed=51)
+    x, t = W.mlp_batch(4096, 2048, 2048, seed=52)
+    X, Tt = T(dev, x), T(dev, t)
+    Tt.requires_grad = False
+    want = []
+    tr = W.Trainer(W.build_mlp(dev, ws, bs, "relu"), 1e-4)
+    for _ in range(4):
+        want.append(tr.step(X, Tt).item())
+    tr = W.Trainer(W.build_mlp(dev, ws, bs, "relu"), 1e-4)   # same start, same data: bit-identical losses
+    slots = [dev.pinned_empty((1,)), dev.pinned_empty((1,))]
+    evs = [F.Event(dev), F.Event(dev)]
+    got = []
+    for i in range(4):
+        tr.step(X, Tt).read_async(slots[i % 2], evs[i % 2])
+        if i > 0:
+            evs[(i - 1) % 2].wait()
+            got.append(float(slots[(i - 1) % 2][0]))
+    dev.sync()
+    t0 = time.perf_counter()
+    tr.step(X, Tt).read_async(slots[0], evs[0])   # returns while the step is still running
+    t_enqueue = time.perf_counter() - t0
+    evs[0].wait()
+    t_total = time.perf_counter() - t0
+    evs[1].wait()
+    got.append(float(slots[1][0]))
+    assert got == want, (got, want)
+    assert t_enqueue < 0.5 * t_total, (t_enqueue, t_total)
+    fresh = F.Event(dev)
+    fresh.wait()                                   # an event nothing was enqueued behind does not block
+    for e in evs + [fresh]:
+        e.close()
+
+
 @pytest.mark.parametrize("unroll", [1, 5])
 def test_captured_steps_track_oracle(unroll):
     """fit_sine with the training step recorded as a CUDA graph (agrs_capture_*): 2 ordinary warm-up steps + replays must land
