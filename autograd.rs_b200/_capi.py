@@ -62,6 +62,8 @@ def lib():
             "agrs_event_destroy": [vp, vp],
             "agrs_download_async": [vp, vp, vp, sz, vp],
             "agrs_event_wait": [vp, vp],
+            "agrs_upload_prefetch_event": [vp, vp, vp, sz, vp],
+            "agrs_wait_event": [vp, vp],
             "agrs_copy": [vp, vp, vp, sz],
             "agrs_upload_prefetch": [vp, vp, vp, sz],
             "agrs_prefetch_join": [vp],

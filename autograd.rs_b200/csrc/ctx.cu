@@ -386,6 +386,24 @@ int agrs_download_async(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes
   return AGRS_OK;
 }
 
+int agrs_upload_prefetch_event(agrs_ctx* ctx, void* dst, const void* src, size_t nbytes, agrs_event* landed) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, landed && landed->ev, AGRS_ERR_INVALID, "agrs_upload_prefetch_event: null event");
+  if (int rc = agrs_upload_prefetch(ctx, dst, src, nbytes)) return rc;
+  if (nbytes == 0) return AGRS_OK;
+  AGRS_CUDA(ctx, cudaEventRecord(landed->ev, ctx->copy_stream));
+  landed->recorded = true;
+  return AGRS_OK;
+}
+
+int agrs_wait_event(agrs_ctx* ctx, agrs_event* ev) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_REQUIRE(ctx, ev && ev->ev, AGRS_ERR_INVALID, "agrs_wait_event: null event");
+  AGRS_NOT_CAPTURING(ctx, "agrs_wait_event (touch a prefetched tensor, or call agrs_prefetch_join, before the capture begins)");
+  if (ev->recorded) AGRS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev->ev, 0));
+  return AGRS_OK;
+}
+
 int agrs_event_wait(agrs_ctx* ctx, agrs_event* ev) {
   AGRS_CHECK_CTX(ctx);
   AGRS_RANGE("agrs_event_wait");

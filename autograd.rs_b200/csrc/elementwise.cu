@@ -279,7 +279,7 @@ int agrs_absmax_f32(agrs_ctx* ctx, const float* x, size_t n, uint32_t* out_bits)
   AGRS_CHECK_CTX(ctx);
   AGRS_RANGE("agrs_absmax_f32");
   AGRS_REQUIRE(ctx, out_bits && (n == 0 || x), AGRS_ERR_INVALID, "agrs_absmax_f32: null pointer");
-  AGRS_CUDA(ctx, cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), ctx->stream));
+  if (int rc = agrs_zero_word(ctx, out_bits)) return rc;
   if (n == 0) return AGRS_OK;
   const size_t n4 = agrs_aligned16(x) ? n / 4 : 0;
   if (n4) {

@@ -189,7 +189,11 @@ int agrs_eng_tensor_prefetch_from_host(agrs_tensor* t, const float* host, int64_
     need(host, "host data");
     Storage& s = *t->t.data;
     if (s.transposed) throw Panic("prefetch_from_host into a transposed view", AGRS_ERR_UNSUPPORTED);
-    s.dev()->check(agrs_upload_prefetch(s.dev()->ctx(), s.wptr(), host, size_t(n) * sizeof(float)));
+    float* dst = s.wptr();  // (orders this copy behind an earlier one into the same buffer that nobody has read yet)
+    Buffer& b = *s.buf;
+    if (!b.landing) s.dev()->check(agrs_event_create(s.dev()->ctx(), &b.landing));
+    s.dev()->check(agrs_upload_prefetch_event(s.dev()->ctx(), dst, host, size_t(n) * sizeof(float), b.landing));
+    b.landing_pending = true;  // the first kernel that touches the buffer waits for this copy and no other
   });
 }
 int agrs_eng_device_prefetch_join(agrs_device* d) {

@@ -54,6 +54,7 @@ Buffer::Buffer(Device* d, int64_t n_elems) : dev(d), keep(d->weak_from_this().lo
 }
 Buffer::Buffer(Device* d, float* external, int64_t n_elems) : dev(d), keep(d->weak_from_this().lock()), ptr(external), n(n_elems), owned(false) {}
 Buffer::~Buffer() {
+  if (landing) agrs_event_destroy(dev->ctx(), landing);
   if (mx) agrs_free(dev->ctx(), mx);
   if (ptr && owned) agrs_free(dev->ctx(), ptr);
 }
@@ -65,8 +66,14 @@ uint32_t* Buffer::mx_slot() {
   }
   return mx;
 }
+void Buffer::await_landing() {
+  if (!landing_pending) return;
+  landing_pending = false;
+  dev->check(agrs_wait_event(dev->ctx(), landing));
+}
 const uint32_t* Buffer::magnitude() {
   if (!mx_valid) {
+    await_landing();
     dev->check(agrs_absmax_f32(dev->ctx(), ptr, size_t(n), mx_slot()));
     mx_valid = true;
   }
@@ -84,6 +91,7 @@ Storage::Storage(Device* d, const Shape& s) : buf(std::make_shared<Buffer>(d, nu
 }
 
 float* Storage::wptr() {
+  buf->await_landing();
   if (buf.use_count() > 1) {  // aliased by a gradient hand-over: un-share before writing (the reference deep-copied up front)
     auto nb = std::make_shared<Buffer>(dev(), buf->n);
     dev()->check(agrs_copy(dev()->ctx(), nb->ptr, buf->ptr, size_t(buf->n) * sizeof(float)));
@@ -96,7 +104,7 @@ float* Storage::wptr() {
 
 StoragePtr Storage::deep_copy() const {
   auto nb = std::make_shared<Buffer>(dev(), buf->n);
-  dev()->check(agrs_copy(dev()->ctx(), nb->ptr, buf->ptr, size_t(buf->n) * sizeof(float)));
+  dev()->check(agrs_copy(dev()->ctx(), nb->ptr, rptr(), size_t(buf->n) * sizeof(float)));
   return std::make_shared<Storage>(nb, shape, transposed);
 }
 
@@ -104,7 +112,7 @@ StoragePtr Storage::contiguous_copy() const {
   if (!transposed) return deep_copy();
   auto out = std::make_shared<Storage>(dev(), shape);
   // memory is [shape[1], shape[0]] row-major; the logical array is its transpose
-  dev()->check(agrs_transpose_f32(dev()->ctx(), buf->ptr, shape[1], shape[0], out->buf->ptr));
+  dev()->check(agrs_transpose_f32(dev()->ctx(), rptr(), shape[1], shape[0], out->buf->ptr));
   return out;
 }
 

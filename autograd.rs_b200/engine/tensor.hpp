@@ -75,6 +75,12 @@ struct Buffer {
   // for the Linear layer below, whose db it is.  Single use: Linear::backward takes it; any write access drops it.
   std::shared_ptr<struct Storage> colsum;
   int64_t colsum_cols = 0;
+  // A host-to-device copy into this buffer that is still in flight on the copy stream (agrs_upload_prefetch_event): the first
+  // reader or writer makes the compute stream wait for exactly this copy (Storage::rptr / wptr), not for every prefetch
+  // issued so far -- a step's forward pass starts when X has landed while T is still on the bus.
+  agrs_event* landing = nullptr;
+  bool landing_pending = false;
+  void await_landing();
   Buffer(Device* d, int64_t n_elems);
   Buffer(Device* d, float* external, int64_t n_elems);  // non-owning
   ~Buffer();
@@ -95,7 +101,10 @@ struct Storage {
   int64_t len() const { return numel(shape); }
   size_t ndim() const { return shape.size(); }
   bool is_contiguous() const { return !transposed; }  // storage.rs:63-69 is_standard_layout
-  const float* rptr() const { return buf->ptr; }
+  const float* rptr() const {
+    if (buf->landing_pending) buf->await_landing();
+    return buf->ptr;
+  }
   // pointer for in-place writes: un-shares the buffer first if a gradient hand-over aliases it
   float* wptr();
   std::shared_ptr<Storage> deep_copy() const;              // ArrayD::to_owned / CudaData clone (tensor.rs:148,160)

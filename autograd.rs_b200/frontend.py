@@ -373,8 +373,9 @@ class Tensor:
         _check(lib().agrs_eng_tensor_copy_from_host(self._h, arr.ctypes.data, int(arr.size), int(blocking)))
 
     def prefetch_from_numpy(self, arr):
-        """Same, on the device's copy stream: overlaps the step already enqueued.  `arr` must be pinned (Device.pinned_empty);
-        call Device.prefetch_join() before enqueuing work that reads this tensor."""
+        """Same, on the device's copy stream: overlaps the step already enqueued.  `arr` must be pinned (Device.pinned_empty).
+        The tensor carries the copy's completion event: the first kernel that reads (or overwrites) it waits, on the device, for
+        this copy and no other.  (Device.prefetch_join() still makes the compute stream wait for every prefetch issued so far.)"""
         assert arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"]
         _check(lib().agrs_eng_tensor_prefetch_from_host(self._h, arr.ctypes.data, int(arr.size)))
 

@@ -71,11 +71,15 @@ AGRS_API int agrs_download(agrs_ctx* ctx, void* dst_host, const void* src_dev, s
  * agrs_prefetch_join makes the context's stream wait for all prefetches issued so far.  src_host must be pinned and stay alive. */
 AGRS_API int agrs_upload_prefetch(agrs_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);
 AGRS_API int agrs_prefetch_join(agrs_ctx* ctx);
+typedef struct agrs_event agrs_event;
+/* The same copy with its own completion event (agrs_event_create, below): agrs_wait_event makes the context's stream -- not the
+ * host -- wait for THAT copy only, so a consumer of the first tensor starts while the second is still on the bus. */
+AGRS_API int agrs_upload_prefetch_event(agrs_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes, agrs_event* landed);
+AGRS_API int agrs_wait_event(agrs_ctx* ctx, agrs_event* ev);
 /* Read-back that does not stall the pipeline: the copy is enqueued on the context's stream behind the work that produces src_dev
  * and the call returns; agrs_event_wait blocks the host until THAT copy has landed, not until the stream is empty.  A training
  * loop reads step i's loss after it has enqueued step i+1 (examples/fit_sine.rs:64-93 reads `loss` every epoch): the device never
  * idles while the host walks the next step's graph.  dst_host must be pinned (agrs_host_alloc) and stay alive until the wait. */
-typedef struct agrs_event agrs_event;
 AGRS_API int agrs_event_create(agrs_ctx* ctx, agrs_event** out);
 AGRS_API int agrs_event_destroy(agrs_ctx* ctx, agrs_event* ev);
 AGRS_API int agrs_download_async(agrs_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes, agrs_event* done);

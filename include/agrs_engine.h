@@ -57,8 +57,9 @@ AGRS_API int agrs_eng_tensor_kaiming_uniform(agrs_device* dev, const int64_t* sh
 /* overwrite t's data from a host buffer of t.len() floats.  blocking=0: asynchronous on the device's stream -- the
  * caller keeps `host` alive and unmodified until the next sync (pinned memory, agrs_host_alloc, for real overlap). */
 AGRS_API int agrs_eng_tensor_copy_from_host(agrs_tensor* t, const float* host, int64_t n, int blocking);
-/* the same copy on the device's COPY stream (agrs_upload_prefetch): overlaps the training step already enqueued; the data is
- * valid for kernels enqueued after agrs_eng_device_prefetch_join.  `host` must be pinned. */
+/* the same copy on the device's COPY stream (agrs_upload_prefetch_event): overlaps the training step already enqueued.  The
+ * tensor keeps the copy's completion event and the first engine call that reads or overwrites it makes the compute stream wait
+ * for that copy alone (agrs_eng_device_prefetch_join still waits for all of them).  `host` must be pinned. */
 AGRS_API int agrs_eng_tensor_prefetch_from_host(agrs_tensor* t, const float* host, int64_t n);
 AGRS_API int agrs_eng_device_prefetch_join(agrs_device* dev);
 AGRS_API int agrs_eng_tensor_clone(const agrs_tensor* t, agrs_tensor** out);    /* #[derive(Clone)]: shares data, grad, graph */

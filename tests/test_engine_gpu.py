@@ -580,6 +580,42 @@ def test_prefetch_copy_stream(dev):
     assert np.all(t.data() == 1.0)
 
 
+def test_prefetched_tensor_waits_for_its_own_copy(dev):
+    """no join: the first reader of a prefetched tensor waits for that tensor's copy (landing event kept with the buffer); a second
+    prefetch into a buffer nobody has read yet, a host read and an in-place write right after a prefetch are all ordered behind it"""
+    rng = np.random.default_rng(62)
+    ha, hb = dev.pinned_empty((1024, 2048)), dev.pinned_empty((1024, 2048))
+    a, b = F.Tensor.zeros(dev, (1024, 2048)), F.Tensor.zeros(dev, (1024, 2048))
+    for _ in range(3):
+        ha[...] = rng.standard_normal(ha.shape).astype(np.float32)
+        hb[...] = rng.standard_normal(hb.shape).astype(np.float32)
+        a.prefetch_from_numpy(ha)
+        b.prefetch_from_numpy(hb)
+        s = a + b                       # reads both: waits for both copies
+        assert np.array_equal(s.data(), ha + hb)
+    keep = ha.copy()
+    hb[...] = 7.0
+    a.prefetch_from_numpy(ha)
+    a.prefetch_from_numpy(hb)           # overwrites the first copy, in order
+    assert np.all(a.data() == 7.0)      # host read straight after a prefetch
+    a.prefetch_from_numpy(ha)
+    a *= 2.0                            # in-place write straight after a prefetch
+    assert np.array_equal(a.data(), keep * 2.0)
+    x, t = W.mlp_batch(1024, 2048, 2048, seed=63)
+    ws, bs = W.mlp_init(2, 2048, seed=64)
+    tr = W.Trainer(W.build_mlp(dev, ws, bs, "relu"), 1e-4)
+    X, Tt = T(dev, x), T(dev, t)
+    Tt.requires_grad = False
+    want = tr.step(X, Tt).item()
+    tr = W.Trainer(W.build_mlp(dev, ws, bs, "relu"), 1e-4)
+    ha[...] = x
+    hb[...] = t
+    a.prefetch_from_numpy(ha)           # X lands first, the forward pass starts; T is needed by the loss only
+    b.requires_grad = False
+    b.prefetch_from_numpy(hb)
+    assert tr.step(a, b).item() == want
+
+
 def test_data_parallel_two_gpus_tracks_oracle():
     """N=2 on real GPUs (NCCL over NVLink): tools/dp_parity.py under torchrun; skipped on a single-GPU box."""
     import os

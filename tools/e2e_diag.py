@@ -41,8 +41,6 @@ def main():
                 slots[0][1].prefetch_from_numpy(ht)
         loss = None
         for i in range(n):
-            if copies:
-                dev.prefetch_join()
             xs, ts = slots[i % 2]
             if copies and i + 1 < n:
                 slots[(i + 1) % 2][0].prefetch_from_numpy(hx)
@@ -62,8 +60,6 @@ def main():
             slots[0][1].prefetch_from_numpy(ht)
         last = None
         for i in range(n):
-            if copies:
-                dev.prefetch_join()
             xs, ts = slots[i % 2]
             if copies and i + 1 < n:
                 slots[(i + 1) % 2][0].prefetch_from_numpy(hx)
@@ -74,6 +70,24 @@ def main():
                 last = float(hl[(i - 1) % 2][0])
         evs[(n - 1) % 2].wait()
         return float(hl[(n - 1) % 2][0])
+
+    from autograd_rs_b200 import _capi
+    # the same two loops with every GEMM launch timed (event pairs): is the difference inside the GEMMs or between kernels?
+    for name, fn in (("device-resident, pipelined loss read", lambda n: pipelined(n, copies=False)),
+                     ("inputs copied every step, pipelined loss read", lambda n: pipelined(n, copies=True))) * 2:
+        fn(2)
+        dev.sync()
+        dev.profile_enable(True)
+        dev.profile_gemm(_capi.GEMM_TCGEN05)
+        n0 = dev.launches()
+        dev.timer_begin()
+        fn(steps)
+        ms = dev.timer_end()
+        launches = dev.launches() - n0
+        dev.profile_enable(False)
+        g_n, g_ms, g_fl = dev.profile_gemm(_capi.GEMM_TCGEN05)
+        print(json.dumps({"loop": name + " (GEMMs timed)", "ms_per_step": round(ms / steps, 3), "gemm_ms_per_step": round(g_ms / steps, 3),
+                          "other_ms_per_step": round((ms - g_ms) / steps, 3), "gemm_launches_per_step": g_n / steps, "launches_per_step": launches / steps}), flush=True)
 
     for name, fn in (("device-resident, every step's loss read one step late (read_async)", lambda n: pipelined(n, copies=False)),
                      ("inputs copied every step, every step's loss read one step late (bench.py e2e)", lambda n: pipelined(n, copies=True))):
