@@ -29,6 +29,7 @@ struct agrs_ctx {
   int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
   int tc_cross = 5;        // pair kernel split scheme (AGRS_TUNE_TC_CROSS): 0 tf32 x3, 1 / 2 tf32 + bf16 cross terms, 3 bf16 x3, 4 fp16 x3 scaled,
                            // 5 (default) = 4 when the caller announced operand magnitudes, else 1
+  int conv_tiled = 1;      // Conv2D backward, single input channel: 1 register-tiled kernel where the shape allows (AGRS_CONV_TILED=0: the generic one)
   int tc_epi_tma = 1;      // pair kernel epilogue: 1 staged in shared memory + TMA store / reduce-add, 0 direct st.global from registers
   int tc_reuse_scales = 0; // cross mode 4, measurement aid: 1 = reuse the operand magnitudes of the previous launch (same operands only)
   // operand magnitudes for the next GEMM call (agrs_gemm_operand_absmax) and the slot the next elementwise launch reports into

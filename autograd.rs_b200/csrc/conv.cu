@@ -471,6 +471,256 @@ __global__ void __launch_bounds__(256) k_conv1_bwd(const float* __restrict__ im,
   }
   if (threadIdx.x == 0) *ticket = 0;
 }
+
+// ---- register-tiled backward for the common small-image case (stride 1, no padding, k <= 5, H, W <= 32: the LeNet layer) ----
+// The kernel above feeds every FMA from shared memory (one or two loads per multiply-add): at the C3 size it runs at 119 us for
+// 0.2 GFMA, shared-memory bound (profiles/r2_conv_implicit.md).  Here every thread keeps a tile of results in registers and each
+// shared-memory vector feeds 10-17 multiply-adds:
+//   * the gradient of a sample is staged channel-PLANAR with a zero border, gb[o][y + K-1][x + 4], rows `gs` floats apart;
+//   * dx: thread = 4 x 4 tile of the input gradient.  For one channel it holds the K*K filter in registers and walks the
+//     (4 + K-1) x 8 window of gb above its tile: 2 vector loads per window row, 4 * K * K multiply-adds per output row;
+//   * dw / db: warp = (channel, filter row i), lane = output row y.  A lane slides along its row four positions at a time
+//     (one vector of g, one new vector of the image row y + i) and keeps the K taps dw[i][0..K-1][o] in registers, across all
+//     the samples of the CTA; the lanes are summed once, at the end.
+// Row strides are multiples of 4 floats whose quarter is odd: 8 lanes that differ in y (or in the tile column) then hit 8 distinct
+// 16-byte bank groups.  Four samples are resident per round (64 threads each for dx).  Sums run in a fixed order: deterministic.
+constexpr int kCtSamples = 4, kCtThreads = 256, kCtColBorder = 4;
+__host__ __device__ inline int ct_stride(int need) {  // smallest multiple of 4 >= need whose quarter is odd
+  int s = (need + 3) & ~3;
+  return ((s >> 2) & 1) ? s : s + 4;
+}
+struct CtGeom {
+  int gs, gr, gcs, is, img_sz;  // gb row stride / rows / channel stride; image row stride / floats per sample
+  int raw_g, raw_i;             // floats of the raw landing buffers
+  size_t smem;
+};
+__host__ __device__ inline CtGeom ct_geom(int H, int W, int K, int co) {
+  CtGeom g;
+  const int hx = H, wx = W;  // stride 1, no padding: the input gradient has the size of the image
+  g.gs = ct_stride(((wx + 3) / 4) * 4 + kCtColBorder);
+  g.gr = ((hx + 3) / 4) * 4 + (K - 1);
+  g.gcs = g.gr * g.gs + 4;   // + 4: the channels of one position spread over different banks while staging
+  g.is = ct_stride(W + 4);    // 4 zero columns after every image row: a window that slides past the row's end multiplies zeros by
+                              // the gradient tile's zero border, never a neighbouring row's value (which could be inf) by zero
+  g.img_sz = (H + 1) * g.is;
+  const int Ho = H - K + 1, Wo = W - K + 1;
+  g.raw_g = kCtSamples * Ho * Wo * co;  // the group's gradients and images exactly as they lie in global memory (bulk-copied)
+  g.raw_i = kCtSamples * H * W;
+  g.smem = (size_t(8) * 28 + size_t(kCtSamples) * (size_t(co) * g.gcs + g.img_sz) + size_t(g.raw_g) + size_t(g.raw_i)) * sizeof(float) + 16;
+  return g;
+}
+
+__device__ __forceinline__ uint32_t ct_smem(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ct_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {  // contiguous global -> shared, async
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ct_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(kCtThreads, 1) k_conv1_bwd_tiled(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ g,
+                                                                   int B, int H, int W, int co, float* __restrict__ dx, float* __restrict__ dw,
+                                                                   float* __restrict__ db, float* __restrict__ part, unsigned int* __restrict__ ticket) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ unsigned int s_ticket;
+  constexpr int BD = K - 1, KK = K * K, FP = 28;  // filter of one channel padded to 28 floats (K <= 5)
+  const int Ho = H - K + 1, Wo = W - K + 1, P = Ho * Wo;
+  const CtGeom ge = ct_geom(H, W, K, co);
+  float* fl = sm;                                   // [8][FP]
+  float* gb = fl + 8 * FP;                          // [S][co][gr][gs] (+4 per channel)
+  float* img = gb + kCtSamples * co * ge.gcs;       // [S][H + 1][is]
+  float* rawg = img + kCtSamples * ge.img_sz;       // [S][P][co]: landing buffer of the bulk copies (the next group's data arrives
+  float* rawi = rawg + ge.raw_g;                    // [S][H][W]    while this group is being computed)
+  const uint32_t bar = ct_smem(rawi + ge.raw_i);    // one mbarrier, 8-byte aligned
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int groups = (B + kCtSamples - 1) / kCtSamples;
+  auto fetch = [&](int grp) {  // thread 0: both blocks of group grp, completion counted in bytes on the barrier
+    const int b0 = grp * kCtSamples, ns = B - b0 < kCtSamples ? B - b0 : kCtSamples;
+    const uint32_t bg = uint32_t(ns) * uint32_t(P * co) * 4u, bi = uint32_t(ns) * uint32_t(H * W) * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bg + bi) : "memory");
+    ct_bulk_load(ct_smem(rawg), g + int64_t(b0) * P * co, bg, bar);
+    ct_bulk_load(ct_smem(rawi), im + int64_t(b0) * H * W, bi, bar);
+  };
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (int(blockIdx.x) < groups) fetch(blockIdx.x);
+  }
+  uint32_t phase = 0;
+  for (int e = tid; e < 8 * FP; e += kCtThreads) {
+    const int o = e / FP, t = e - o * FP;
+    fl[e] = (o < co && t < KK) ? __ldg(filt + t * co + o) : 0.f;
+  }
+  for (int e = tid; e < kCtSamples * (co * ge.gcs + ge.img_sz); e += kCtThreads) gb[e] = 0.f;  // borders, spare rows: zero for good
+
+  // dw / db: this warp's (channel, filter row) pairs c = warp, warp + 8, ..  (o = c / K, i = c % K); accumulators live across samples
+  constexpr int kMaxPairs = (8 * K + 7) / 8;  // co <= 8
+  float acc[kMaxPairs][K], accb[kMaxPairs];
+#pragma unroll
+  for (int q = 0; q < kMaxPairs; ++q) {
+    accb[q] = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[q][j] = 0.f;
+  }
+  // dx: slot = one of the resident samples, tile (tu, tv) of 4 x 4 input-gradient pixels
+  const int slot = tid >> 6, tt = tid & 63, tu = tt >> 3, tv = tt & 7;
+  const bool dx_thread = 4 * tu < H && 4 * tv < W;
+
+  __syncthreads();  // the barrier exists before anybody polls it
+  // the walk of a sample's gradient, e = p * co + o -> (o, y, x), starts at the same place for every sample: found once
+  const int p_first = tid / co, o_first = tid - p_first * co, y_first = p_first / Wo, x_first = p_first - y_first * Wo;
+  const int dp = kCtThreads / co, d_o = kCtThreads - dp * co;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int b0 = grp * kCtSamples;
+    const int ns = B - b0 < kCtSamples ? B - b0 : kCtSamples;
+    ct_wait(bar, phase);  // this group's raw blocks have landed
+    phase ^= 1u;
+    __syncthreads();      // the previous round's readers of gb / img are done (and the zero fill, the first time)
+    // ---- shared -> shared: image rows to their padded pitch, the gradient NHWC -> planar with border ----
+    for (int sidx = 0; sidx < ns; ++sidx) {
+      const float* src = rawi + sidx * H * W;
+      float* dsti = img + sidx * ge.img_sz;
+      for (int e = tid; e < (H * W) >> 2; e += kCtThreads) {  // W % 4 == 0: a vector never straddles two rows
+        const int row = (4 * e) / W, col = 4 * e - row * W;
+        *reinterpret_cast<float4*>(dsti + row * ge.is + col) = reinterpret_cast<const float4*>(src)[e];
+      }
+      const float* gsrc = rawg + sidx * P * co;
+      float* dstg = gb + sidx * co * ge.gcs;
+      int o = o_first, y = y_first, x = x_first;
+      for (int e = tid; e < P * co; e += kCtThreads) {
+        dstg[o * ge.gcs + (y + BD) * ge.gs + x + kCtColBorder] = gsrc[e];
+        o += d_o; x += dp;
+        if (o >= co) { o -= co; ++x; }
+        while (x >= Wo) { x -= Wo; ++y; }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my reads of the landing buffers come before the next bulk write
+    __syncthreads();
+    if (tid == 0 && grp + int(gridDim.x) < groups) fetch(grp + gridDim.x);  // lands while this group is computed
+    // ---- dx ----
+    if (slot < ns && dx_thread) {
+      float a[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[r][c] = 0.f;
+      const float* gp0 = gb + slot * co * ge.gcs + (4 * tu) * ge.gs + 4 * tv;
+      for (int o = 0; o < co; ++o) {
+        float f[FP];
+#pragma unroll
+        for (int q = 0; q < FP / 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(fl + o * FP + 4 * q);  // one address per warp: broadcast
+          f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+        }
+        const float* gp = gp0 + o * ge.gcs;
+#pragma unroll
+        for (int wr = 0; wr < 4 + BD; ++wr) {  // window row wr holds gradient row 4*tu + wr - BD
+          const float4 w0 = *reinterpret_cast<const float4*>(gp + wr * ge.gs), w1 = *reinterpret_cast<const float4*>(gp + wr * ge.gs + 4);
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = r + BD - wr;  // filter row that maps window row wr onto output row r
+            if (i < 0 || i >= K) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int j = 0; j < K; ++j) a[r][c] = fmaf(w[c + kCtColBorder - j], f[i * K + j], a[r][c]);
+          }
+        }
+      }
+      float* dst = dx + int64_t(b0 + slot) * H * W;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int u = 4 * tu + r;
+        if (u < H) __stcs(reinterpret_cast<float4*>(dst + u * W + 4 * tv), make_float4(a[r][0], a[r][1], a[r][2], a[r][3]));  // W % 4 == 0
+      }
+    }
+    // ---- dw / db ----
+    if (lane < Ho) {
+#pragma unroll
+      for (int q = 0; q < kMaxPairs; ++q) {
+        const int c = warp + 8 * q;
+        if (c >= co * K) break;
+        const int o = c / K, i = c - o * K;
+        for (int sidx = 0; sidx < ns; ++sidx) {
+          const float* ip = img + sidx * ge.img_sz + (lane + i) * ge.is;
+          const float* gp = gb + sidx * co * ge.gcs + o * ge.gcs + (lane + BD) * ge.gs + kCtColBorder;
+          float4 prev = *reinterpret_cast<const float4*>(ip);
+          for (int x = 0; x < Wo; x += 4) {  // past Wo the gradient vector holds border zeros, the image vector padding zeros
+            const float4 gv = *reinterpret_cast<const float4*>(gp + x);
+            const float4 nxt = *reinterpret_cast<const float4*>(ip + x + 4);
+            const float w[8] = {prev.x, prev.y, prev.z, prev.w, nxt.x, nxt.y, nxt.z, nxt.w};
+            const float gq[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int xx = 0; xx < 4; ++xx)
+#pragma unroll
+              for (int j = 0; j < K; ++j) acc[q][j] = fmaf(w[xx + j], gq[xx], acc[q][j]);
+            if (i == 0) accb[q] += (gq[0] + gq[1]) + (gq[2] + gq[3]);
+            prev = nxt;
+          }
+        }
+      }
+    }
+  }
+  // ---- this CTA's sums: lanes (output rows) folded in a fixed tree, then [kk][co] dw followed by [co] db ----
+  const int nacc = KK * co + co;
+#pragma unroll
+  for (int q = 0; q < kMaxPairs; ++q) {
+    const int c = warp + 8 * q;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      float v = acc[q][j];
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, sft);
+      acc[q][j] = v;
+    }
+    float vb = accb[q];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) vb += __shfl_xor_sync(0xFFFFFFFFu, vb, sft);
+    if (lane == 0 && c < co * K) {
+      const int o = c / K, i = c - o * K;
+#pragma unroll
+      for (int j = 0; j < K; ++j) part[int64_t(blockIdx.x) * nacc + (i * K + j) * co + o] = acc[q][j];
+      if (i == 0) part[int64_t(blockIdx.x) * nacc + KK * co + o] = vb;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  if (tid < nacc) {  // last CTA: partials added in CTA order, loads batched 8 at a time
+    const float* src = part + tid;
+    float t = 0.f;
+    unsigned c = 0;
+    for (; c + 8 <= gridDim.x; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __ldcg(src + int64_t(c + q) * nacc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += v[q];
+    }
+    for (; c < gridDim.x; ++c) t += __ldcg(src + int64_t(c) * nacc);
+    if (tid < KK * co) dw[tid] = t;
+    else               db[tid - KK * co] = t;
+  }
+  if (tid == 0) *ticket = 0;
+}
+
+static bool conv1_tiled_ok(int64_t B, int64_t H, int64_t W, int64_t k, int64_t co, int64_t stride, int64_t pad, const float* im, const float* g,
+                           const float* dx) {
+  if (stride != 1 || pad != 0 || (k != 3 && k != 5) || co < 1 || co > 8 || H > 32 || W > 32 || H < k || W < k || B < 1) return false;
+  if (W % 4 != 0) return false;  // image rows staged and dx rows stored as whole 16-byte vectors
+  if (k * k * co + co > kCtThreads) return false;
+  if (!agrs_aligned16(im) || !agrs_aligned16(g) || !agrs_aligned16(dx)) return false;
+  if (((H - k + 1) * (W - k + 1) * co) % 4 != 0) return false;  // every sample's gradient block starts 16-byte aligned (bulk copies)
+  return ct_geom(int(H), int(W), int(k), int(co)).smem <= 220 * 1024;
+}
+
 }  // namespace
 
 extern "C" {
@@ -615,9 +865,33 @@ int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
                "agrs_conv2d_bwd_f32: shape outside the implicit-GEMM kernels: use the im2col path");
   AGRS_REQUIRE(ctx, im && filt && grad && dx && dw && db, AGRS_ERR_INVALID, "agrs_conv2d_bwd_f32: null pointer");
   const int Ho = int((H - k + 2 * pad) / stride + 1), Wo = int((W - k + 2 * pad) / stride + 1);
+  const size_t nacc = size_t(k * k * c_out + c_out);
+  if (ctx->conv_tiled && conv1_tiled_ok(B, H, W, k, c_out, stride, pad, im, grad, dx)) {
+    const CtGeom ge = ct_geom(int(H), int(W), int(k), int(c_out));
+    const int64_t groups = (B + kCtSamples - 1) / kCtSamples;
+    const int64_t tgrid = groups < ctx->sm_count ? groups : ctx->sm_count;
+    int rc = agrs_ensure_workspace(ctx, size_t(tgrid) * nacc * sizeof(float));
+    if (rc) return rc;
+    if (!ctx->tickets) {
+      AGRS_NOT_CAPTURING(ctx, "allocating the ticket array (run one ordinary step before capturing)");
+      AGRS_CUDA(ctx, cudaMalloc(&ctx->tickets, 4096 * sizeof(unsigned int)));
+      AGRS_CUDA(ctx, cudaMemsetAsync(ctx->tickets, 0, 4096 * sizeof(unsigned int), ctx->stream));
+      ctx->tickets_n = 4096;
+    }
+    if (k == 5) {
+      static bool attr5 = false;
+      if (!attr5) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr5 = true; }
+      k_conv1_bwd_tiled<5><<<unsigned(tgrid), kCtThreads, ge.smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(c_out), dx, dw, db, ctx->workspace, ctx->tickets);
+    } else {
+      static bool attr3 = false;
+      if (!attr3) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr3 = true; }
+      k_conv1_bwd_tiled<3><<<unsigned(tgrid), kCtThreads, ge.smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(c_out), dx, dw, db, ctx->workspace, ctx->tickets);
+    }
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
   const int64_t cap = int64_t(ctx->sm_count) * 4;
   const int64_t grid = B < cap ? B : cap;
-  const size_t nacc = size_t(k * k * c_out + c_out);
   int rc = agrs_ensure_workspace(ctx, size_t(grid) * nacc * sizeof(float));
   if (rc) return rc;
   if (ctx->tickets_n < 1) {

@@ -779,7 +779,8 @@ def test_save_and_load_parameters(dev, tmp_path):
         wrong.load(path)
 
 
-@pytest.mark.parametrize("B,H,Wd,co,k,s,p", [(64, 28, 28, 6, 5, 1, 0), (3, 9, 11, 8, 3, 1, 1), (5, 12, 10, 4, 3, 2, 1), (1, 7, 7, 5, 2, 2, 0), (300, 28, 28, 6, 5, 1, 0)])
+@pytest.mark.parametrize("B,H,Wd,co,k,s,p", [(64, 28, 28, 6, 5, 1, 0), (3, 9, 11, 8, 3, 1, 1), (5, 12, 10, 4, 3, 2, 1), (1, 7, 7, 5, 2, 2, 0), (300, 28, 28, 6, 5, 1, 0),
+                                                 (7, 16, 20, 8, 3, 1, 0), (5, 32, 32, 3, 5, 1, 0), (9, 13, 12, 1, 3, 1, 0), (2, 5, 8, 2, 5, 1, 0)])
 def test_conv2d_implicit_gemm_matches_oracle_and_literal_path(dev, B, H, Wd, co, k, s, p):
     """f3: Conv2D with one input channel through the implicit-GEMM kernels (no col matrix): forward and all three gradients against
     the oracle's literal restatement, and against the device's own im2col + GEMM path; the node keeps three variables."""
