@@ -160,6 +160,91 @@ __global__ void __launch_bounds__(128) k_gemm_dot(int64_t M, int N, int64_t K, c
   }
 }
 
+// ------------------------------------------------------------------ dot, K sliced over CTAs, two output rows per warp
+// The kernel above re-stages B in 512-row chunks for every four rows of C and feeds every FMA from its own shared-memory word:
+// Linear(3456, 10) forward on 1024 rows took 47 us for 14 MB of A (profiles/r2_c3_timeline.md).  Here a CTA owns a slice of K
+// (a few 128-wide steps) and a group of rows: it stages its slice of B once, transposed -- Bt[n][k], k contiguous -- and each warp
+// walks row pairs of A with 16-byte coalesced loads: lane l holds k = 4l .. 4l+3 of a step, reads the matching four k of column n
+// as one conflict-free vector and feeds 8 multiply-adds with it.  Lanes are folded by a shuffle tree, slices by the last CTA of
+// the row group to finish, in slice order (ticket counter): one launch, no float atomics, deterministic.
+template <int NT>
+__global__ void __launch_bounds__(256) k_gemm_dot_sliced(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                         int64_t ldb, int transB, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
+                                                         int steps_per_slice, int rows_per_cta, float* __restrict__ part, unsigned int* __restrict__ tickets) {
+  extern __shared__ __align__(16) float Bt[];
+  __shared__ unsigned int s_ticket;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int slice = blockIdx.x, slices = gridDim.x, rg = blockIdx.y;
+  const int ks = steps_per_slice * 128, pitch = ks + 4;  // + 4: rows of Bt start in different bank groups
+  const int64_t k0 = int64_t(slice) * ks;
+  for (int kk = tid; kk < ks; kk += 256) {  // thread = one k of the slice: N consecutive floats of B in, N conflict-free stores out
+    const int64_t k = k0 + kk;
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+      if (n < N) Bt[n * pitch + kk] = k < K ? (transB ? __ldg(B + int64_t(n) * ldb + k) : __ldg(B + k * ldb + n)) : 0.f;
+  }
+  __syncthreads();
+  const int64_t r0 = int64_t(rg) * rows_per_cta;
+  const int rows = int(M - r0 < rows_per_cta ? M - r0 : rows_per_cta);
+  for (int pr = w; 2 * pr < rows; pr += 8) {
+    const int64_t m0 = r0 + 2 * pr, m1 = 2 * pr + 1 < rows ? m0 + 1 : m0;
+    const float *a0 = A + m0 * lda + k0, *a1 = A + m1 * lda + k0;
+    float acc0[NT], acc1[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc0[n] = acc1[n] = 0.f;
+#pragma unroll 4
+    for (int st = 0; st < steps_per_slice; ++st) {
+      const int kk = st * 128 + 4 * lane;
+      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+      if (k0 + kk + 3 < K) {  // K % 4 == 0 (checked by the host): a vector is whole or absent
+        x0 = __ldcs(reinterpret_cast<const float4*>(a0 + kk));
+        x1 = __ldcs(reinterpret_cast<const float4*>(a1 + kk));
+      }
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        if (n < N) {
+          const float4 b = *reinterpret_cast<const float4*>(Bt + n * pitch + kk);
+          acc0[n] = fmaf(x0.x, b.x, acc0[n]); acc0[n] = fmaf(x0.y, b.y, acc0[n]); acc0[n] = fmaf(x0.z, b.z, acc0[n]); acc0[n] = fmaf(x0.w, b.w, acc0[n]);
+          acc1[n] = fmaf(x1.x, b.x, acc1[n]); acc1[n] = fmaf(x1.y, b.y, acc1[n]); acc1[n] = fmaf(x1.z, b.z, acc1[n]); acc1[n] = fmaf(x1.w, b.w, acc1[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      float v0 = acc0[n], v1 = acc1[n];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      }
+      if (lane == n && n < N) {
+        if (slices == 1) {
+          const float bv = bias ? bias[n] : 0.f;
+          C[m0 * ldc + n] = v0 + bv;
+          if (m1 != m0) C[m1 * ldc + n] = v1 + bv;
+        } else {
+          part[(int64_t(slice) * M + m0) * N + n] = v0;
+          if (m1 != m0) part[(int64_t(slice) * M + m1) * N + n] = v1;
+        }
+      }
+    }
+  }
+  if (slices == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(tickets + rg, 1u);
+  __syncthreads();
+  if (s_ticket != unsigned(slices) - 1u) return;
+  __threadfence();
+  for (int e = tid; e < rows * N; e += 256) {  // the group's last CTA: slices added in order
+    const int r = e / N, n = e - r * N;
+    float t = bias ? bias[n] : 0.f;
+    for (int sl = 0; sl < slices; ++sl) t += __ldcg(part + (int64_t(sl) * M + r0 + r) * N + n);
+    C[(r0 + r) * ldc + n] = t;
+  }
+  if (tid == 0) tickets[rg] = 0;
+}
+
 // ------------------------------------------------------------------ tn_small: C[M,N] = A[K,M]^T . B[K,N] with M*N <= 160, K huge
 // (the conv filter gradient: 25 x 6 outputs over K = B*P rows).  A and B are contiguous streams of short rows; a block stages
 // 256 rows of each with coalesced loads, and output (m, n) is owned by ONE thread (two row-parity groups of 160 threads) that
@@ -376,6 +461,36 @@ int agrs_gemm_skinny(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N
 #undef AGRS_ROWS
     AGRS_LAUNCHED(ctx);
     return AGRS_OK;
+  }
+  // dot with K sliced over CTAs: long K, 16-byte loadable rows of A
+  if (K >= 512 && K % 4 == 0 && lda % 4 == 0 && agrs_aligned16(A) && M >= 64) {
+    const int64_t steps = (K + 127) / 128;
+    // about two CTAs per SM: row groups of 32 rows (two row pairs per warp), then as many K slices as that takes
+    const int rows_per_cta = 32;
+    const int64_t rgs = (M + rows_per_cta - 1) / rows_per_cta;
+    int64_t slices = (2 * int64_t(ctx->sm_count) + rgs - 1) / rgs;
+    if (slices > steps) slices = steps;
+    if (slices < 1) slices = 1;
+    const int sps = int((steps + slices - 1) / slices);
+    slices = (steps + sps - 1) / sps;
+    if (rgs <= 65535 && size_t(n) * size_t(sps * 128 + 4) * sizeof(float) <= 48 * 1024) {
+      float* part = nullptr;
+      if (slices > 1) {
+        int rc = agrs_ensure_workspace(ctx, size_t(slices) * size_t(M) * size_t(n) * sizeof(float));
+        if (rc) return rc;
+        rc = ensure_tickets(ctx, size_t(rgs));
+        if (rc) return rc;
+        part = ctx->workspace;
+      }
+      const size_t smem = size_t(n) * size_t(sps * 128 + 4) * sizeof(float);
+      dim3 grid((unsigned)slices, (unsigned)rgs);
+      if (n <= 4)       k_gemm_dot_sliced<4><<<grid, 256, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias, sps, rows_per_cta, part, ctx->tickets);
+      else if (n <= 8)  k_gemm_dot_sliced<8><<<grid, 256, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias, sps, rows_per_cta, part, ctx->tickets);
+      else if (n <= 12) k_gemm_dot_sliced<12><<<grid, 256, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias, sps, rows_per_cta, part, ctx->tickets);
+      else              k_gemm_dot_sliced<16><<<grid, 256, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, transB, C, ldc, bias, sps, rows_per_cta, part, ctx->tickets);
+      AGRS_LAUNCHED(ctx);
+      return AGRS_OK;
+    }
   }
   {
     const int64_t groups = (M + 3) / 4, cap = int64_t(ctx->sm_count) * 8;
