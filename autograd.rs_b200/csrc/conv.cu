@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) k_conv1_fwd(const float* __restrict__ im,
 // to finish folds the partials in CTA order.  dw / db: thread = (tap, half of the channels, slice of the positions), accumulators
 // live in registers across all the samples of the CTA; dx: thread per pixel, channel vectors of 8 from shared memory.  The
 // gradient tile is staged with a zero border of k-1 positions, so for stride 1 the dx loops carry no bounds checks (profiling the
-// first version showed 7 integer / branch instructions per FFMA: profiles/r2_conv_implicit.md).  KT = compile-time k (0: run-time).
+// first version showed 7 integer / branch instructions per FFMA: profiles/r2_c3_timeline.md).  KT = compile-time k (0: run-time).
 template <bool S1, int KT>
 __global__ void __launch_bounds__(256) k_conv1_bwd(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ g,
                                                    int B, int H, int W, int k_rt, int co, int s, int pad, int Ho, int Wo, float* __restrict__ dx,
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(256) k_conv1_bwd(const float* __restrict__ im,
 
 // ---- register-tiled backward for the common small-image case (stride 1, no padding, k <= 5, H, W <= 32: the LeNet layer) ----
 // The kernel above feeds every FMA from shared memory (one or two loads per multiply-add): at the C3 size it runs at 119 us for
-// 0.2 GFMA, shared-memory bound (profiles/r2_conv_implicit.md).  Here every thread keeps a tile of results in registers and each
+// 0.2 GFMA, shared-memory bound (profiles/r2_c3_timeline.md).  Here every thread keeps a tile of results in registers and each
 // shared-memory vector feeds 10-17 multiply-adds:
 //   * the gradient of a sample is staged channel-PLANAR with a zero border, gb[o][y + K-1][x + 4], rows `gs` floats apart;
 //   * dx: thread = 4 x 4 tile of the input gradient.  For one channel it holds the K*K filter in registers and walks the

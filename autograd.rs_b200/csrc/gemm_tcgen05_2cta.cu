@@ -235,6 +235,17 @@ __device__ __forceinline__ void split_row_bf16(uint32_t raw, uint32_t out_lo, ui
 #ifndef AGRS_RAW_EARLY_RELEASE
 #define AGRS_RAW_EARLY_RELEASE 1
 #endif
+// Suspend-time hints (ns) of the long waits: epilogue warps on their accumulator stage, TMA producer on a free raw stage.  0 = plain polling.
+#ifndef AGRS_EPI_WAIT_NS
+#define AGRS_EPI_WAIT_NS 4000
+#endif
+#ifndef AGRS_TMA_WAIT_NS
+#define AGRS_TMA_WAIT_NS 500
+#endif
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity, uint32_t ns) {
+  if (ns) mbar_wait_relaxed(bar, parity, ns);
+  else    mbar_wait(bar, parity);
+}
 template <int CROSS>
 __device__ __forceinline__ constexpr bool raw_early() { return AGRS_RAW_EARLY_RELEASE && AGRS_SPLIT_EARLY_CONVERT && CROSS >= 3; }
 __device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
@@ -518,7 +529,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const Work w = work_item(t);
         const int32_t m0 = int32_t(w.mb * 2 * BM + rank * BM), n0 = int32_t(w.nb * BN + rank * BNH);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          mbar_wait(raw_free(r), rph ^ 1u);
+          mbar_wait_long(raw_free(r), rph ^ 1u, AGRS_TMA_WAIT_NS);
           const uint32_t a_dst = smem_base + r * RAW_BYTES, b_dst = a_dst + A_BYTES;
           mbar_arrive_expect_tx(raw_full(r), RAW_BYTES);
           const int32_t k0 = kb * BK;
@@ -718,7 +729,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           scale_of_max(mx_scalar ? __ldg(a_max) : (row0 + lane < M ? __ldg(a_max + row0 + lane) : 0u), mu, inv_a);
         }
         for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
-          mbar_wait(tfull_bar(acc), acc_ph);
+          mbar_wait_long(tfull_bar(acc), acc_ph, AGRS_EPI_WAIT_NS);
           tc_fence_after();
           // the reductions of this chunk go to the addresses the previous chunk's pieces went to: those must have landed
           if (ch > 0 && lane == 0) bulk_wait_all();
@@ -788,7 +799,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         scale_of_max(mx_scalar ? __ldg(a_max) : (row < M ? __ldg(a_max + row) : 0u), mu, inv_a);
       }
       for (int c0 = w.kb0, ch = 0; c0 < w.kb1; c0 += kb_per_chunk, ++ch) {
-        mbar_wait(tfull_bar(acc), acc_ph);
+        mbar_wait_long(tfull_bar(acc), acc_ph, AGRS_EPI_WAIT_NS);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
 #pragma unroll 1
