@@ -37,7 +37,8 @@ struct agrs_ctx {
   const uint32_t* gemm_a_mx = nullptr;
   const uint32_t* gemm_b_mx = nullptr;
   uint32_t* next_out_mx = nullptr;
-  int64_t tc_min_flops = 1LL << 24;  // AUTO path: below this many MACs the SIMT kernel wins on launch+fill latency
+  int64_t tc_min_flops = (1LL << 24) + 1;  // AUTO path: up to 256^3 MACs the SIMT kernel wins on launch + pipeline-fill latency (7.5 vs 12.1 us
+                                           // of device time at 256^3; 512^3: 17.2 vs 13.9 -- profiles/r2_gemm_sweep_small_graph.txt)
   // small scratch for reductions (block partials + completion counter), allocated once
   float* scratch = nullptr;
   size_t scratch_bytes = 0;

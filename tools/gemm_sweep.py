@@ -16,6 +16,8 @@ from autograd_rs_b200 import _capi  # noqa: E402
 
 REUSE_SCALES = False
 AUTO = False
+GRAPH = False
+SIMT = False
 ANNOUNCE = False  # announce one magnitude per operand before every call (what the host engine does): the default mode then runs fp16 x3
 
 
@@ -26,7 +28,7 @@ def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_2CTA, pair)
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_KCHUNK, kchunk)
     ctx.call("agrs_set_tuning", _capi.TUNE_TC_SPLITK, splitk)
-    ctx.call("agrs_set_gemm_path", _capi.GEMM_AUTO if AUTO else _capi.GEMM_TCGEN05)
+    ctx.call("agrs_set_gemm_path", _capi.GEMM_SIMT if SIMT else (_capi.GEMM_AUTO if AUTO else _capi.GEMM_TCGEN05))
     dA, dB, dC = ctx.to_device(A), ctx.to_device(B), ctx.empty(M * N)
     dbias = ctx.to_device(bv) if bias else None
     args = (int(ta), int(tb), M, N, K, dA.ptr, A.shape[1], dB.ptr, B.shape[1], dC.ptr, N, dbias.ptr if bias else None)
@@ -65,6 +67,22 @@ def run_case(ctx, M, N, K, ta, tb, pair, iters, kchunk, rng, check_rows=48, bias
         ctx.call("agrs_timer_end", C.byref(ms))
         res["ms"] = ms.value / iters
         res["tflops"] = 2.0 * M * N * K / (res["ms"] * 1e-3) / 1e12
+        if GRAPH:  # the same launches replayed from a CUDA graph: device time per launch without the host's per-call work
+            g = C.c_void_p()
+            ctx.call("agrs_capture_begin")
+            try:
+                for _ in range(20):
+                    call("agrs_gemm_f32", *args)
+            finally:
+                ctx.call("agrs_capture_end", C.byref(g))
+            ctx.call("agrs_graph_launch", g, 2)
+            ctx.sync()
+            ctx.call("agrs_timer_begin")
+            ctx.call("agrs_graph_launch", g, 5)
+            ctx.call("agrs_timer_end", C.byref(ms))
+            ctx.L.agrs_graph_destroy(ctx.h, g)
+            res["us_in_graph"] = ms.value * 1e3 / 100
+            res["tflops_in_graph"] = 2.0 * M * N * K / (res["us_in_graph"] * 1e-6) / 1e12
         if REUSE_SCALES:  # cross mode 4 without its absmax passes: the magnitudes of the launches above are still in the workspace
             ctx.call("agrs_set_tuning", _capi.TUNE_TC_REUSE_SCALES, 1)
             ctx.call("agrs_timer_begin")
@@ -88,13 +106,17 @@ def main():
     ap.add_argument("--reuse-scales", action="store_true", help="cross mode 4: also time the kernel without its absmax passes")
     ap.add_argument("--announce", action="store_true", help="announce one magnitude per operand before every call, as the host engine does")
     ap.add_argument("--auto", action="store_true", help="let AUTO path selection choose the kernel instead of forcing the tcgen05 path")
+    ap.add_argument("--simt", action="store_true", help="force the FP32 SIMT kernel (what small problems fall back to)")
+    ap.add_argument("--graph", action="store_true", help="also time 20 launches captured into a CUDA graph (device time per launch, no host work)")
     ap.add_argument("--odd", action="store_true", help="ragged shapes (partial tiles in M, N and K)")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--kchunk", type=int, default=1024)
     ap.add_argument("--splitk", default="0", help="comma list of forced K splits for the pair kernel (0 = automatic)")
     ap.add_argument("--majors", default="00,01,10", help="ta tb pairs for the square sizes: 00 = X.W, 01 = G.W^T, 10 = X^T.G, 11")
     a = ap.parse_args()
-    global REUSE_SCALES, ANNOUNCE, AUTO
+    global REUSE_SCALES, ANNOUNCE, AUTO, GRAPH, SIMT
+    GRAPH = a.graph
+    SIMT = a.simt
     REUSE_SCALES = a.reuse_scales
     ANNOUNCE = a.announce
     AUTO = a.auto
