@@ -31,6 +31,7 @@ struct agrs_ctx {
                            // 5 (default) = 4 when the caller announced operand magnitudes, else 1
   int conv_tiled = 1;      // Conv2D backward, single input channel: 1 register-tiled kernel where the shape allows (AGRS_CONV_TILED=0: the generic one)
   int tc_epi_tma = 1;      // pair kernel epilogue: 1 staged in shared memory + TMA store / reduce-add, 0 direct st.global from registers
+  int tc_wave_sync = 2;    // pair kernel: the TMA producers of a wave start their tiles together (0 off, 1 always, 2 large problems; AGRS_TC_WAVE_SYNC)
   int tc_reuse_scales = 0; // cross mode 4, measurement aid: 1 = reuse the operand magnitudes of the previous launch (same operands only)
   // operand magnitudes for the next GEMM call (agrs_gemm_operand_absmax) and the slot the next elementwise launch reports into
   // (agrs_next_output_absmax); both are consumed by the call they apply to

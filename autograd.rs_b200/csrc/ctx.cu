@@ -35,6 +35,10 @@ static int ctx_init(int device, cudaStream_t stream, bool own, agrs_ctx** out) {
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
   if (const char* e = getenv("AGRS_CONV_TILED")) ctx->conv_tiled = atoi(e) != 0;
+  if (const char* e = getenv("AGRS_TC_WAVE_SYNC")) {
+    const int v = atoi(e);
+    if (v >= 0 && v <= 2) ctx->tc_wave_sync = v;
+  }
   if (const char* e = getenv("AGRS_TC_CROSS")) {  // default of AGRS_TUNE_TC_CROSS (agrs.h)
     const int v = atoi(e);
     if (v >= 0 && v <= 5) ctx->tc_cross = v;

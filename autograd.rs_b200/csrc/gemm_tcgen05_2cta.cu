@@ -452,7 +452,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
                    const __grid_constant__ ScatterArgs sc, const __grid_constant__ CUtensorMap tmap_c,
                    const __grid_constant__ CUtensorMap tmap_w, int epi_tma, const uint32_t* __restrict__ a_max,
-                   const uint32_t* __restrict__ b_max, int mx_scalar) {
+                   const uint32_t* __restrict__ b_max, int mx_scalar, unsigned int* wave_sync) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
@@ -525,9 +525,25 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (lane == 0) {
       int r = 0;
       uint32_t rph = 0;
+      unsigned long long started = 0;  // work items started by all pairs once every pair has begun its (wave+1)-th item
       for (int64_t t = pair; t < num_tiles; t += num_pairs) {
         const Work w = work_item(t);
         const int32_t m0 = int32_t(w.mb * 2 * BM + rank * BM), n0 = int32_t(w.nb * BN + rank * BNH);
+        // Wave alignment (large problems only, see launch()): the pairs of a wave share A row-blocks and B column-blocks through
+        // the L2, but only while they walk K within a few dozen k-blocks of each other; left alone they drift apart tile after tile
+        // (16384^3: 64 GB of DRAM reads for 2 GB of operands).  The leader's producer therefore announces each work item and waits,
+        // for a bounded time, until every pair has announced its item of the same wave.  A performance hint, not a dependency:
+        // when the wait times out (pairs not co-resident) the loads simply start.
+        started = started + num_pairs < (unsigned long long)num_tiles ? started + num_pairs : (unsigned long long)num_tiles;
+        if (wave_sync && rank == 0) {
+          atomicAdd(wave_sync, 1u);
+          for (int polls = 0; polls < 2048; ++polls) {
+            unsigned int seen;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(wave_sync) : "memory");
+            if (seen >= (unsigned int)started) break;
+            __nanosleep(64);
+          }
+        }
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait_long(raw_free(r), rph ^ 1u, AGRS_TMA_WAIT_NS);
           const uint32_t a_dst = smem_base + r * RAW_BYTES, b_dst = a_dst + A_BYTES;
@@ -869,6 +885,8 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
+__global__ void k_zero_u32(unsigned int* p) { *p = 0u; }
+
 // C[m, n] += P_1[m, n] + P_2[m, n] + ..  (split order; P_s contiguous [M][N])
 __global__ void __launch_bounds__(256) k_add_partials(float* __restrict__ C, int64_t ldc, const float* __restrict__ P, int nparts, int64_t M,
                                                       int64_t N) {
@@ -972,7 +990,16 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   }
   const int64_t items = tiles * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0);
+  // wave alignment of the TMA producers: 1 = whenever there is more than one wave; 2 (default) = problems beyond the training shapes
+  // (>= 4 waves of >= 128 k-blocks and (M + N) * K >= 2^28, i.e. from about 11600^3).  Measured (profiles/r2_gemm_wave_sync.txt):
+  // 16384^3 312 -> 385 TFLOP/s, DRAM reads 64.4 -> 17.8 GB, L2 hit rate 50 -> 76 %; 8192^3 +1 %; the C2 shapes unchanged.
+  unsigned int* wave_sync = nullptr;
+  if (items > pairs && (ctx->tc_wave_sync == 1 || (ctx->tc_wave_sync == 2 && items >= 4 * pairs && num_kb / splits >= 128 && (M + N) * K >= (int64_t(1) << 28)))) {
+    wave_sync = ctx->counter + 12;  // its own 4 bytes of the context's counter block
+    k_zero_u32<<<1, 1, 0, ctx->stream>>>(wave_sync);
+    AGRS_LAUNCHED(ctx);
+  }
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0, wave_sync);
   AGRS_LAUNCHED(ctx);
   if (splits > 1) {
     const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
