@@ -452,7 +452,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
                    const __grid_constant__ ScatterArgs sc, const __grid_constant__ CUtensorMap tmap_c,
                    const __grid_constant__ CUtensorMap tmap_w, int epi_tma, const uint32_t* __restrict__ a_max,
-                   const uint32_t* __restrict__ b_max, int mx_scalar, unsigned int* wave_sync) {
+                   const uint32_t* __restrict__ b_max, int mx_scalar, unsigned int* wave_sync, int64_t split_from) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
@@ -471,11 +471,14 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int64_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
   const int num_kb = int((K + BK - 1) / BK);
-  // Work items = output tiles x K splits.  Splitting K fills the last wave when the tile count is just above a multiple of the
-  // 74 CTA pairs (dW of the 4096-wide layers: 256 tiles = 3.46 waves): split s > 0 writes its partial to the workspace Cw
-  // ([splits-1][M][N]) and a small kernel adds the partials to C in split order afterwards (deterministic).
+  // Work items: tiles [0, split_from) whole, tiles [split_from, tiles_mn) cut into `splits` pieces of K.  Splitting K fills the
+  // last wave when the tile count is just above a multiple of the 74 CTA pairs (dW of the 4096-wide layers: 256 tiles = 3.46
+  // waves: the 34 tiles of the last wave are halved): piece s > 0 writes its partial to plane s-1 of the workspace Cw
+  // ([splits-1][M][N]) and a small kernel adds the partials of the split tiles to C in split order afterwards (deterministic).
+  // split_from = 0 splits every tile (a forced AGRS_TUNE_TC_SPLITK, or few tiles).
   const int64_t tiles_mn = m_tiles * n_tiles;
-  const int64_t num_tiles = tiles_mn * splits;
+  const int64_t tail_tiles = tiles_mn - split_from;
+  const int64_t num_tiles = split_from + tail_tiles * splits;
   const int kb_per_split = (num_kb + splits - 1) / splits;
   struct Work {
     int64_t mb, nb;
@@ -483,8 +486,16 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   };
   auto work_item = [&](int64_t t) {
     Work w;
-    w.split = int(t / tiles_mn);
-    tile_coords(t - w.split * tiles_mn, m_tiles, n_tiles, w.mb, w.nb);
+    if (t < split_from) {
+      w.split = 0;
+      tile_coords(t, m_tiles, n_tiles, w.mb, w.nb);
+      w.kb0 = 0;
+      w.kb1 = num_kb;
+      return w;
+    }
+    const int64_t u = t - split_from;
+    w.split = int(u / tail_tiles);
+    tile_coords(split_from + (u - w.split * tail_tiles), m_tiles, n_tiles, w.mb, w.nb);
     w.kb0 = w.split * kb_per_split;
     w.kb1 = w.kb0 + kb_per_split < num_kb ? w.kb0 + kb_per_split : num_kb;
     return w;
@@ -911,22 +922,71 @@ __global__ void __launch_bounds__(256) k_add_partials(float* __restrict__ C, int
   }
 }
 
-// K splits that fill the last wave of CTA pairs: efficiency = work items / (waves * pairs)
-static int choose_splits(int64_t tiles, int64_t pairs, int64_t num_kb, int forced) {
-  if (forced > 0) return int(forced < num_kb ? forced : num_kb);
-  auto eff = [&](int64_t items) { return double(items) / double(((items + pairs - 1) / pairs) * pairs); };
-  int best = 1;
-  double best_eff = eff(tiles);
-  for (int s = 2; s <= 4; ++s) {
-    if (num_kb / s < 8) break;  // at least 256 of K per split
-    const double e = eff(tiles * s);
-    if (e > best_eff * 1.05) {  // worth a second pass over C only for a real gain
-      best = s;
-      best_eff = e;
+// the same for the tiles [tile_from, tiles_mn) only (tile order of the GEMM: tile_coords): one block per tile and pass
+__global__ void __launch_bounds__(256) k_add_partials_tiles(float* __restrict__ C, int64_t ldc, const float* __restrict__ P, int nparts, int64_t M, int64_t N,
+                                                            int64_t m_tiles, int64_t n_tiles, int64_t tile_from, int64_t tiles_mn) {
+  const bool vec = (N & 3) == 0 && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(P)) & 15u) == 0;
+  const int64_t total = M * N;
+  for (int64_t t = tile_from + blockIdx.x; t < tiles_mn; t += gridDim.x) {
+    int64_t mb, nb;
+    tile_coords(t, m_tiles, n_tiles, mb, nb);
+    const int64_t r0 = mb * 2 * BM, c0 = nb * BN;
+    const int rows = int(M - r0 < 2 * BM ? M - r0 : 2 * BM), cols = int(N - c0 < BN ? N - c0 : BN);
+    if (vec) {  // cols is a multiple of 4 (N and the tile width are)
+      const int c4n = cols >> 2;
+      for (int e = threadIdx.x; e < rows * c4n; e += 256) {
+        const int r = e / c4n, c = (e - r * c4n) << 2;
+        float4 acc = *reinterpret_cast<const float4*>(C + (r0 + r) * ldc + c0 + c);
+        for (int sp = 0; sp < nparts; ++sp) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(P + int64_t(sp) * total + (r0 + r) * N + c0 + c));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4*>(C + (r0 + r) * ldc + c0 + c) = acc;
+      }
+    } else {
+      for (int e = threadIdx.x; e < rows * cols; e += 256) {
+        const int r = e / cols, c = e - r * cols;
+        float acc = C[(r0 + r) * ldc + c0 + c];
+        for (int sp = 0; sp < nparts; ++sp) acc += P[int64_t(sp) * total + (r0 + r) * N + c0 + c];
+        C[(r0 + r) * ldc + c0 + c] = acc;
+      }
+    }
+  }
+}
+
+// K splits that fill the last wave of CTA pairs.  Time in units of one whole tile on one pair: no split ceil(T / P); every tile in s
+// pieces ceil(T s / P) / s; only the tiles of the last, partial wave in s pieces: floor(T / P) + 1 / s, possible when those tiles
+// times s still fit one wave.  The last form adds partial planes for a few tiles only, so it wins ties.
+struct SplitPlan {
+  int splits;          // pieces of K per split tile (1: nothing is split)
+  int64_t split_from;  // first split tile (0: all of them)
+};
+static SplitPlan choose_plan(int64_t tiles, int64_t pairs, int64_t num_kb, int forced) {
+  if (forced > 0) return {int(forced < num_kb ? forced : num_kb), 0};
+  const double none = double((tiles + pairs - 1) / pairs);
+  SplitPlan best{1, 0};
+  double best_t = none;
+  for (int sp = 2; sp <= 4; ++sp) {
+    if (num_kb / sp < 8) break;  // at least 256 of K per piece
+    const double t = double((tiles * sp + pairs - 1) / pairs) / sp;
+    if (t < best_t / 1.05) {  // worth a second pass over C only for a real gain
+      best = {sp, 0};
+      best_t = t;
+    }
+  }
+  const int64_t full = tiles / pairs, rem = tiles - full * pairs;
+  if (full >= 1 && rem > 0) {
+    int sp = int(pairs / rem);
+    if (sp > 4) sp = 4;
+    while (sp >= 2 && num_kb / sp < 8) --sp;
+    if (sp >= 2) {
+      const double t = double(full) + 1.0 / sp;
+      if (t < none / 1.05 && t <= best_t * 1.001) best = {sp, full * pairs};
     }
   }
   return best;
 }
+static int choose_splits(int64_t tiles, int64_t pairs, int64_t num_kb, int forced) { return choose_plan(tiles, pairs, num_kb, forced).splits; }
 
 template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
 static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
@@ -936,11 +996,13 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int64_t pairs = ctx->sm_count / 2;
   const int64_t num_kb = (K + BK - 1) / BK;
-  int splits = SCATTER ? 1 : choose_splits(tiles, pairs, num_kb, ctx->tc_splitk);  // the scattering epilogue writes final values only
+  SplitPlan plan = SCATTER ? SplitPlan{1, 0} : choose_plan(tiles, pairs, num_kb, ctx->tc_splitk);  // the scattering epilogue writes final values only
+  int splits = plan.splits;
   {  // the kernel gives every split ceil(num_kb / splits) k-blocks: drop splits that would be left with none
     const int64_t kps = (num_kb + splits - 1) / splits;
     splits = int((num_kb + kps - 1) / kps);
   }
+  const int64_t split_from = splits > 1 ? plan.split_from : 0;
   // workspace = [row magnitudes of op(A) | column magnitudes of op(B)] (CROSS 4 only) followed by the split-K partial planes
   const size_t a_slots = (size_t(M) + 63) / 64 * 64, b_slots = (size_t(N) + 63) / 64 * 64;
   // cross mode 4 with magnitudes supplied by the caller (agrs_gemm_operand_absmax: one per operand): no passes, no scale region
@@ -988,7 +1050,7 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     if (rc) return rc;
     epi_tma = 1;
   }
-  const int64_t items = tiles * splits;
+  const int64_t items = split_from + (tiles - split_from) * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
   // wave alignment of the TMA producers: 1 = whenever there is more than one wave; 2 (default) = problems beyond the training shapes
   // (>= 4 waves of >= 128 k-blocks and (M + N) * K >= 2^28, i.e. from about 11600^3).  Measured (profiles/r2_gemm_wave_sync.txt):
@@ -999,9 +1061,13 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     k_zero_u32<<<1, 1, 0, ctx->stream>>>(wave_sync);
     AGRS_LAUNCHED(ctx);
   }
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0, wave_sync);
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0, wave_sync, split_from);
   AGRS_LAUNCHED(ctx);
-  if (splits > 1) {
+  if (splits > 1 && split_from > 0) {  // only the tiles of the last wave were split
+    const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
+    k_add_partials_tiles<<<unsigned(tiles - split_from), 256, 0, ctx->stream>>>(C, ldc, Cw, splits - 1, M, N, m_tiles, n_tiles, split_from, tiles);
+    AGRS_LAUNCHED(ctx);
+  } else if (splits > 1) {
     const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
     k_add_partials<<<unsigned(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap), 256, 0, ctx->stream>>>(C, ldc, Cw, splits - 1, M, N);
     AGRS_LAUNCHED(ctx);
