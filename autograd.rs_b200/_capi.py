@@ -19,7 +19,7 @@ ADD, SUB, MUL = 0, 1, 2
 SMUL, SDIV, SRSUB, SADD = 0, 1, 2, 3
 BCAST_TRAILING, BCAST_LEADING = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SKINNY = 0, 1, 2, 3
-TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK, TUNE_TC_2CTA, TUNE_TC_SPLITK, TUNE_TC_CROSS, TUNE_TC_EPI_TMA, TUNE_TC_REUSE_SCALES = 0, 1, 2, 3, 4, 5, 6, 7, 8
+TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK, TUNE_TC_2CTA, TUNE_TC_SPLITK, TUNE_TC_CROSS, TUNE_TC_EPI_TMA, TUNE_TC_REUSE_SCALES, TUNE_TC_WAVE_SYNC = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 _lib = None
 

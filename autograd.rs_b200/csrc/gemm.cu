@@ -65,6 +65,10 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
     case AGRS_TUNE_TC_REUSE_SCALES:
       ctx->tc_reuse_scales = value ? 1 : 0;
       return AGRS_OK;
+    case AGRS_TUNE_TC_WAVE_SYNC:
+      AGRS_REQUIRE(ctx, value >= 0 && value <= 2, AGRS_ERR_INVALID, "AGRS_TUNE_TC_WAVE_SYNC must be 0, 1 or 2");
+      ctx->tc_wave_sync = int(value);
+      return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS:
       ctx->tc_min_flops = value;
       return AGRS_OK;
@@ -85,6 +89,7 @@ int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value) {
     case AGRS_TUNE_TC_CROSS: *value = ctx->tc_cross; return AGRS_OK;
     case AGRS_TUNE_TC_EPI_TMA: *value = ctx->tc_epi_tma; return AGRS_OK;
     case AGRS_TUNE_TC_REUSE_SCALES: *value = ctx->tc_reuse_scales; return AGRS_OK;
+    case AGRS_TUNE_TC_WAVE_SYNC: *value = ctx->tc_wave_sync; return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS: *value = ctx->tc_min_flops; return AGRS_OK;
   }
   return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown tuning key %d", key);

@@ -139,8 +139,12 @@ enum agrs_tuning_key {
                                    overrides the default at context creation */
   AGRS_TUNE_TC_EPI_TMA = 7,     /* pair kernel epilogue: 1 (default) = 32x32 pieces staged in shared memory, written by TMA tensor stores and
                                    folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
-  AGRS_TUNE_TC_REUSE_SCALES = 8 /* cross mode 4, measurement aid: 1 = skip the absmax kernels and reuse the operand magnitudes the previous
+  AGRS_TUNE_TC_REUSE_SCALES = 8,/* cross mode 4, measurement aid: 1 = skip the absmax kernels and reuse the operand magnitudes the previous
                                    launch left in the workspace -- only meaningful when the operands have not changed.  Default 0 */
+  AGRS_TUNE_TC_WAVE_SYNC = 9    /* pair kernel: the TMA producers of a wave of tiles start together so that the CTA pairs keep sharing
+                                   operand blocks through the L2 (a bounded wait, never a dependency; results do not change).  0 = off,
+                                   1 = whenever there is more than one wave, 2 (default) = very large problems only (from about
+                                   11600^3).  Env AGRS_TC_WAVE_SYNC overrides the default at context creation */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
 AGRS_API int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value);

@@ -349,6 +349,47 @@ def test_gemm_pair_cross_modes_and_epilogues(ctx, M, N, Kd, ta, tb, cross, split
         ctx.call("agrs_set_tuning", K.TUNE_TC_EPI_TMA, 1)
 
 
+@pytest.mark.parametrize("M,N,Kd,ta,tb", [(4096, 4096, 512, 1, 0), (4096, 4096, 1024, 0, 0), (3900, 4000, 800, 0, 1)])
+def test_gemm_pair_splits_only_the_last_wave(ctx, M, N, Kd, ta, tb):
+    """256 tiles on 74 CTA pairs = 3.46 waves: the automatic plan cuts only the 34 tiles of the last wave along K and adds their
+    partial planes tile by tile (k_add_partials_tiles).  Same 2e-5 bar against f64 as every other plan, and within 1e-5 of the
+    unsplit result; a forced uniform split still works."""
+    rng = np.random.default_rng(M + N + Kd)
+    A = rng.uniform(-1, 1, (Kd, M) if ta else (M, Kd)).astype(np.float32)
+    B = rng.uniform(-1, 1, (N, Kd) if tb else (Kd, N)).astype(np.float32)
+    bias = rng.uniform(-1, 1, N).astype(np.float32)
+    truth = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64) + bias
+    scale = np.abs(truth).max()
+    got = {}
+    try:
+        for splitk in (0, 1, 2):
+            ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, splitk)
+            got[splitk] = ctx.gemm(A, B, bool(ta), bool(tb), bias, K.GEMM_TCGEN05)
+            assert np.abs(got[splitk] - truth).max() / scale < 2e-5
+    finally:
+        ctx.call("agrs_set_tuning", K.TUNE_TC_SPLITK, 0)
+    assert np.abs(got[0] - got[1]).max() / scale < 1e-5 and np.abs(got[2] - got[1]).max() / scale < 1e-5
+    assert not np.array_equal(got[0], got[1])  # the automatic plan did split something at these shapes
+
+
+def test_gemm_pair_wave_alignment_changes_no_bit(ctx):
+    """AGRS_TUNE_TC_WAVE_SYNC: the producers of a wave wait (bounded) for each other before they load a tile -- a scheduling hint for
+    L2 reuse on very large problems; forced on for a 7-wave problem it must give the bits it gives when off"""
+    rng = np.random.default_rng(77)
+    M, N, Kd = 8192, 4096, 512
+    A = rng.uniform(-1, 1, (M, Kd)).astype(np.float32)
+    B = rng.uniform(-1, 1, (Kd, N)).astype(np.float32)
+    assert tuning(ctx, K.TUNE_TC_WAVE_SYNC) == 2
+    out = []
+    try:
+        for mode in (0, 1):
+            ctx.call("agrs_set_tuning", K.TUNE_TC_WAVE_SYNC, mode)
+            out.append(ctx.gemm(A, B, False, False, None, K.GEMM_TCGEN05))
+    finally:
+        ctx.call("agrs_set_tuning", K.TUNE_TC_WAVE_SYNC, 2)
+    assert np.array_equal(out[0], out[1])
+
+
 def test_gemm_pair_epilogues_agree_bitwise(ctx):
     """the staged TMA epilogue (store, then reduce-add per K chunk in L2) and the direct one (read-modify-write from registers)
     perform the same round-to-nearest f32 adds in the same order: identical bits, K chunks, bias and ragged edges included"""
