@@ -711,6 +711,101 @@ __global__ void __launch_bounds__(kCtThreads, 1) k_conv1_bwd_tiled(const float* 
   if (tid == 0) *ticket = 0;
 }
 
+// ---- register-tiled forward for the same small-image case ----
+// Thread = four neighbouring output positions of one row x all (<= 8, zero-padded) channels: 32 accumulators.  Per filter row it
+// reads 8 image values of row y + i with two 16-byte loads and each tap's 8 channel weights as two broadcast loads: 160 multiply-adds
+// per 12 loads (k = 5), where k_conv1_fwd does 8 per 3.  Four samples per CTA round land by one bulk copy (the next group's under
+// this group's arithmetic); the results are staged [p][co] in shared memory and leave as one coalesced 16-byte stream (NHWC).
+constexpr int kCfSamples = 4, kCfThreads = 256;
+__host__ __device__ inline size_t cf_smem(int H, int W, int K, int co) {
+  const int Ho = H - K + 1, Wo = W - K + 1;
+  return (size_t(K * K + 1) * 8 + size_t(kCfSamples) * H * W + 8 + size_t(kCfSamples) * Ho * Wo * co) * sizeof(float) + 16;
+}
+template <int K>
+__global__ void __launch_bounds__(kCfThreads) k_conv1_fwd_tiled(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ bias,
+                                                                int B, int H, int W, int co, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int KK = K * K;
+  const int Ho = H - K + 1, Wo = W - K + 1, P = Ho * Wo, strips_x = (Wo + 3) >> 2, strips = Ho * strips_x;
+  float* fl = sm;                                   // [KK + 1][8]: taps, then the bias row
+  float* raw = fl + (KK + 1) * 8;                   // [S][H][W] as in global memory (+ 8 floats a window may look past the end)
+  float* stage = raw + kCfSamples * H * W + 8;      // [S][P][co]
+  const uint32_t bar = ct_smem(stage + kCfSamples * P * co);
+  const int tid = threadIdx.x;
+  const int groups = (B + kCfSamples - 1) / kCfSamples;
+  auto fetch = [&](int grp) {
+    const int b0 = grp * kCfSamples, ns = B - b0 < kCfSamples ? B - b0 : kCfSamples;
+    const uint32_t bytes = uint32_t(ns) * uint32_t(H * W) * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    ct_bulk_load(ct_smem(raw), im + int64_t(b0) * H * W, bytes, bar);
+  };
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (int(blockIdx.x) < groups) fetch(blockIdx.x);
+  }
+  for (int e = tid; e < (KK + 1) * 8; e += kCfThreads) {
+    const int t = e >> 3, o = e & 7;
+    fl[e] = o < co ? (t < KK ? __ldg(filt + t * co + o) : __ldg(bias + o)) : 0.f;
+  }
+  if (tid < 8) raw[kCfSamples * H * W + tid] = 0.f;
+  __syncthreads();
+  uint32_t phase = 0;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int b0 = grp * kCfSamples, ns = B - b0 < kCfSamples ? B - b0 : kCfSamples;
+    ct_wait(bar, phase);
+    phase ^= 1u;
+    for (int item = tid; item < ns * strips; item += kCfThreads) {
+      const int sidx = item / strips, rem = item - sidx * strips, y = rem / strips_x, x0 = (rem - y * strips_x) << 2;
+      float acc[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[q][o] = 0.f;
+      const float* ip = raw + sidx * H * W + y * W + x0;   // W % 4 == 0: 16-byte aligned
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const float4 w0 = *reinterpret_cast<const float4*>(ip + i * W), w1 = *reinterpret_cast<const float4*>(ip + i * W + 4);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < K; ++j) {  // t = i*K + j ascending: the GEMM's order over K
+          const float4 f0 = *reinterpret_cast<const float4*>(fl + (i * K + j) * 8), f1 = *reinterpret_cast<const float4*>(fl + (i * K + j) * 8 + 4);
+          const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[q][o] = fmaf(w[q + j], f[o], acc[q][o]);
+        }
+      }
+      float* st = stage + (sidx * P + y * Wo + x0) * co;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (x0 + q < Wo) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o)
+            if (o < co) st[q * co + o] = acc[q][o] + fl[KK * 8 + o];  // taps in ascending order, then the bias: k_conv1_fwd's bits
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();  // results staged; everybody is done reading the landing buffer
+    if (tid == 0 && grp + int(gridDim.x) < groups) fetch(grp + gridDim.x);
+    float* dst = out + int64_t(b0) * P * co;  // the group's samples are contiguous in NHWC
+    const int n = ns * P * co;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+      for (int e = tid; e < n >> 2; e += kCfThreads) __stcs(reinterpret_cast<float4*>(dst) + e, reinterpret_cast<const float4*>(stage)[e]);
+    } else {
+      for (int e = tid; e < n; e += kCfThreads) dst[e] = stage[e];
+    }
+    __syncthreads();  // the staging area is free for the next group
+  }
+}
+
+static bool conv1_fwd_tiled_ok(int64_t B, int64_t H, int64_t W, int64_t k, int64_t co, int64_t stride, int64_t pad, const float* im) {
+  if (stride != 1 || pad != 0 || (k != 3 && k != 5) || co < 1 || co > 8 || H < k || W < k || B < 1 || W % 4 != 0 || H > 64 || W > 64) return false;
+  if (!agrs_aligned16(im)) return false;
+  return cf_smem(int(H), int(W), int(k), int(co)) <= 100 * 1024;
+}
+
 static bool conv1_tiled_ok(int64_t B, int64_t H, int64_t W, int64_t k, int64_t co, int64_t stride, int64_t pad, const float* im, const float* g,
                            const float* dx) {
   if (stride != 1 || pad != 0 || (k != 3 && k != 5) || co < 1 || co > 8 || H > 32 || W > 32 || H < k || W < k || B < 1) return false;
@@ -845,6 +940,22 @@ int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
                "agrs_conv2d_fwd_f32: shape outside the implicit-GEMM kernels (single input channel, C_out <= %d, k*k*C_out + C_out <= 256): use im2col + GEMM", kConvCo);
   AGRS_REQUIRE(ctx, im && filt && bias && out, AGRS_ERR_INVALID, "agrs_conv2d_fwd_f32: null pointer");
   const int Ho = int((H - k + 2 * pad) / stride + 1), Wo = int((W - k + 2 * pad) / stride + 1);
+  if (ctx->conv_tiled && conv1_fwd_tiled_ok(B, H, W, k, c_out, stride, pad, im)) {
+    const size_t tsmem = cf_smem(int(H), int(W), int(k), int(c_out));
+    const int64_t groups = (B + kCfSamples - 1) / kCfSamples, tcap = int64_t(ctx->sm_count) * 2;
+    const unsigned tgrid = unsigned(groups < tcap ? groups : tcap);
+    if (k == 5) {
+      static bool a5 = false;
+      if (!a5) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); a5 = true; }
+      k_conv1_fwd_tiled<5><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out);
+    } else {
+      static bool a3 = false;
+      if (!a3) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); a3 = true; }
+      k_conv1_fwd_tiled<3><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out);
+    }
+    AGRS_LAUNCHED(ctx);
+    return AGRS_OK;
+  }
   const int64_t cap = int64_t(ctx->sm_count) * 4;
   static bool attr_set = false;
   if (!attr_set) {
