@@ -371,6 +371,106 @@ __global__ void __launch_bounds__(256) k_gemm_tn(int64_t M, int N, int64_t K, co
   if (threadIdx.x == 0) tickets[blockIdx.y] = 0;
 }
 
+// ------------------------------------------------------------------ tn, four columns of A per thread
+// The same product with 16-byte loads: block = 32 lanes x 4 k-lanes, a lane owns 4 consecutive m (one float4 of a row of A, 512
+// coalesced bytes per warp) and keeps 4 x N sums; the block's slice of B sits in shared memory, rows padded to NP = 4, 8, 12 or 16
+// floats, and is read as broadcast vectors: 4 N multiply-adds per 1 + NP/4 loads where k_gemm_tn issues N per 1 + N.
+// dW of Linear(3456, 10) on 1024 rows: 19 -> see profiles/r2_c3_timeline.md.  Needs M % 4 == 0, lda % 4 == 0, A 16-byte aligned.
+template <int NT>
+__global__ void __launch_bounds__(128) k_gemm_tn_v4(int64_t M, int N, int64_t K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                    int64_t ldb, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int64_t k_per_split,
+                                                    float* __restrict__ part, unsigned int* __restrict__ tickets) {
+  extern __shared__ __align__(16) float smv[];
+  __shared__ unsigned int s_ticket;
+  float* Bs = smv;                               // [k_per_split][NT]
+  float* red = smv + k_per_split * NT;           // [4][32][4 * NT + 4]
+  constexpr int RP = 4 * NT + 4;
+  const int mx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int64_t m = (int64_t(blockIdx.y) * 32 + mx) * 4;
+  const int64_t k0 = int64_t(blockIdx.x) * k_per_split, k1 = k0 + k_per_split < K ? k0 + k_per_split : K;
+  const int kn = int(k1 - k0);
+  for (int e = threadIdx.x; e < kn * NT; e += 128) {
+    const int kk = e / NT, n = e - kk * NT;
+    Bs[e] = n < N ? __ldg(B + (k0 + kk) * ldb + n) : 0.f;
+  }
+  __syncthreads();
+  float acc[4][NT];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[q][n] = 0.f;
+  if (m < M) {
+#pragma unroll 4
+    for (int kk = ky; kk < kn; kk += 4) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(A + (k0 + kk) * lda + m));
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int n4 = 0; n4 < NT / 4; ++n4) {
+        const float4 b = *reinterpret_cast<const float4*>(Bs + kk * NT + 4 * n4);  // one address per warp: broadcast
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[q][4 * n4 + j] = fmaf(av[q], bv[j], acc[q][4 * n4 + j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) red[(ky * 32 + mx) * RP + q * NT + n] = acc[q][n];
+  __syncthreads();
+  const int splits = gridDim.x;
+  // 128 x N outputs of this block, element e = (column of the block, n): the 4 k-lanes folded in order
+  for (int e = threadIdx.x; e < 128 * N; e += 128) {
+    const int mc = e / N, n = e - mc * N, lane = mc >> 2, q = mc & 3;
+    const int64_t mm = int64_t(blockIdx.y) * 128 + mc;
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sum += red[(r * 32 + lane) * RP + q * NT + n];
+    if (mm < M) {
+      if (splits == 1) C[mm * ldc + n] = sum + (bias ? bias[n] : 0.f);
+      else part[(int64_t(blockIdx.x) * M + mm) * N + n] = sum;
+    }
+  }
+  if (splits == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[blockIdx.y], 1u);
+  __syncthreads();
+  if (s_ticket != unsigned(splits - 1)) return;
+  __threadfence();
+  // the m-tile's last block: thread t owns outputs e = t, t + 128, .. (N of them); splits are added in order, and the loads of one
+  // split for all of a thread's outputs (and of the next split) are in flight together
+  {
+    float t[NT];
+    const float* src[NT];
+    const int64_t plane = M * N;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      t[i] = 0.f;
+      const int e = threadIdx.x + 128 * i, mc = e / N, n = e - mc * N;
+      const int64_t mm = int64_t(blockIdx.y) * 128 + mc;
+      src[i] = (i < N && mm < M) ? part + mm * N + n : nullptr;
+    }
+#pragma unroll 2
+    for (int z = 0; z < splits; ++z) {
+      float v[NT];
+#pragma unroll
+      for (int i = 0; i < NT; ++i) v[i] = src[i] ? __ldcg(src[i] + z * plane) : 0.f;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) t[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      if (!src[i]) continue;
+      const int e = threadIdx.x + 128 * i, mc = e / N, n = e - mc * N;
+      C[(int64_t(blockIdx.y) * 128 + mc) * ldc + n] = t[i] + (bias ? bias[n] : 0.f);
+    }
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.y] = 0;
+}
+
 int ensure_tickets(agrs_ctx* ctx, size_t need) {
   if (need <= ctx->tickets_n) return AGRS_OK;
   AGRS_NOT_CAPTURING(ctx, "growing the ticket array (run one ordinary step before capturing)");
@@ -417,6 +517,37 @@ int agrs_gemm_skinny(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N
     k_gemm_tn_small<<<unsigned(blocks), 320, smem, ctx->stream>>>(int(M), n, K, A, lda, B, ldb, C, ldc, bias, rpb, part, ctx->tickets);
     AGRS_LAUNCHED(ctx);
     return AGRS_OK;
+  }
+  if (transA && M % 4 == 0 && lda % 4 == 0 && agrs_aligned16(A) && M >= 512 && K >= 64) {  // tn with 16-byte loads
+    const int64_t my = (M + 127) / 128;
+    if (my <= 65535) {
+      // about two blocks per SM, at least 32 rows of K per block
+      int64_t want = (2 * int64_t(ctx->sm_count) + my - 1) / my, maxs = (K + 31) / 32;
+      int64_t splits = want < maxs ? want : maxs;
+      if (splits < 1) splits = 1;
+      int64_t kps = (K + splits - 1) / splits;
+      kps = (kps + 3) / 4 * 4;
+      splits = (K + kps - 1) / kps;
+      const int nt = n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 12 ? 12 : 16));
+      const size_t smem = (size_t(kps) * nt + size_t(128) * (4 * nt + 4)) * sizeof(float);
+      if (smem <= 48 * 1024) {
+        float* part = nullptr;
+        if (splits > 1) {
+          int rc = agrs_ensure_workspace(ctx, size_t(splits) * size_t(M) * size_t(N) * sizeof(float));
+          if (rc) return rc;
+          rc = ensure_tickets(ctx, size_t(my));
+          if (rc) return rc;
+          part = ctx->workspace;
+        }
+        dim3 grid((unsigned)splits, (unsigned)my);
+        if (nt == 4)       k_gemm_tn_v4<4><<<grid, 128, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, C, ldc, bias, kps, part, ctx->tickets);
+        else if (nt == 8)  k_gemm_tn_v4<8><<<grid, 128, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, C, ldc, bias, kps, part, ctx->tickets);
+        else if (nt == 12) k_gemm_tn_v4<12><<<grid, 128, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, C, ldc, bias, kps, part, ctx->tickets);
+        else               k_gemm_tn_v4<16><<<grid, 128, smem, ctx->stream>>>(M, n, K, A, lda, B, ldb, C, ldc, bias, kps, part, ctx->tickets);
+        AGRS_LAUNCHED(ctx);
+        return AGRS_OK;
+      }
+    }
   }
   if (transA) {
     const int64_t my = (M + 31) / 32;
