@@ -12,3 +12,13 @@ def test_splitter_and_epilogue_address_algebra():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.check() == []
+
+
+def test_conv_tile_index_algebra():
+    """Host model of the register-tiled Conv2D kernels (tools/conv_tile_check.py): the bordered planar gradient tile, the 4 x 4 dx
+    tiles and their windows, the (channel, filter row) x output-row dw mapping and the forward strips reproduce the oracle's literal
+    lowering; no access leaves its buffer; the pitches keep a quarter warp's 16-byte accesses in 8 distinct bank groups."""
+    spec = importlib.util.spec_from_file_location("conv_tile_check", os.path.join(ROOT, "tools", "conv_tile_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check() == []
