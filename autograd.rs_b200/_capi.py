@@ -126,6 +126,7 @@ def lib():
             "agrs_mean_f32": [vp, vp, sz, vp],
             "agrs_sum_axis_f32": [vp, vp, i64, i64, i64, vp],
             "agrs_sgd_step_f32": [vp, vp, vp, f32, sz, sz],
+            "agrs_sgd_step_multi_f32": [vp, i32, vp, vp, vp, vp, f32],
             "agrs_im2col_f32": [vp, vp, i64, i64, i64, i64, i64, i64, i64, vp],
             "agrs_col2im_f32": [vp, vp, i64, i64, i64, i64, i64, i64, vp],
             "agrs_broadcast_filter_f32": [vp, vp, i64, i64, i64, vp],

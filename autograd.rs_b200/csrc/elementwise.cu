@@ -247,6 +247,61 @@ __global__ void __launch_bounds__(kThreads) k_absmax(const float* __restrict__ x
   mag_commit(m, mx);
 }
 
+// ---- SGD on up to 16 parameters in ONE launch (SGD::step walks the parameter list, optim.rs:25-34) ----
+// blockIdx.y = parameter; the blocks of a parameter stride over it like k_binary_v4 does.  The launch-bound configurations pay one
+// launch instead of one per tensor (LeNet: 4 parameters, fit_sine: 4, each a ~1.3 us kernel otherwise); the arithmetic is SgdOp's.
+constexpr int kMultiMax = 16;
+struct SgdMulti {
+  float* w[kMultiMax];
+  const float* g[kMultiMax];
+  size_t n[kMultiMax];
+  uint32_t* mx[kMultiMax];  // magnitude word of the updated parameter, or null
+  int count;
+  float lr;
+};
+__global__ void k_zero_words(SgdMulti a) {
+  if (int(threadIdx.x) < a.count && a.mx[threadIdx.x]) *a.mx[threadIdx.x] = 0u;
+}
+__global__ void __launch_bounds__(kThreads) k_sgd_multi(const __grid_constant__ SgdMulti a) {
+  const int t = blockIdx.y;
+  float* w = a.w[t];
+  const float* g = a.g[t];
+  const size_t n = a.n[t];
+  uint32_t* mx = a.mx[t];
+  const SgdOp f{a.lr};
+  const bool vec = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g)) & 15u) == 0;
+  const size_t n4 = vec ? n / 4 : 0, stride = size_t(gridDim.x) * kThreads;
+  if (size_t(blockIdx.x) * kThreads >= (n4 ? n4 : n)) return;  // more blocks than this (small) parameter needs; warp-uniform
+  uint32_t m = 0;
+  size_t i = size_t(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + (kUnroll - 1) * stride < n4; i += kUnroll * stride) {
+    float4 x[kUnroll], y[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      x[u] = ld4(w + 4 * (i + u * stride));
+      y[u] = ld4(g + 4 * (i + u * stride));
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const float4 r = make_float4(f(x[u].x, y[u].x), f(x[u].y, y[u].y), f(x[u].z, y[u].z), f(x[u].w, y[u].w));
+      m = mag4(m, r);
+      st4(w + 4 * (i + u * stride), r);
+    }
+  }
+  for (; i < n4; i += stride) {
+    const float4 x = ld4(w + 4 * i), y = ld4(g + 4 * i);
+    const float4 r = make_float4(f(x.x, y.x), f(x.y, y.y), f(x.z, y.z), f(x.w, y.w));
+    m = mag4(m, r);
+    st4(w + 4 * i, r);
+  }
+  for (size_t e = n4 * 4 + size_t(blockIdx.x) * kThreads + threadIdx.x; e < n; e += stride) {  // ragged tail / unaligned parameter
+    const float r = f(w[e], g[e]);
+    m = max(m, mag_bits(r));
+    w[e] = r;
+  }
+  if (mx) mag_commit(m, mx);  // block-uniform branch: every lane of every warp that got here arrives
+}
+
 template <class F>
 int launch_bcast(agrs_ctx* ctx, F f, float* out, const float* a, const float* b, size_t n, size_t nb, int bmode) {
   if (n == 0) return AGRS_OK;
@@ -385,6 +440,37 @@ int agrs_powi_f32(agrs_ctx* ctx, float* out, const float* a, int exp, size_t n) 
   AGRS_REQUIRE(ctx, n == 0 || (out && a), AGRS_ERR_INVALID, "agrs_powi_f32: null pointer");
   if (exp == 2) return launch_unary(ctx, Sq{}, out, a, n);
   return launch_unary(ctx, PowiOp{exp}, out, a, n);
+}
+
+int agrs_sgd_step_multi_f32(agrs_ctx* ctx, int count, float* const* w, const float* const* g, const size_t* n, uint32_t* const* out_absmax, float lr) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_sgd_step_multi_f32");
+  AGRS_REQUIRE(ctx, count >= 0 && (count == 0 || (w && g && n)), AGRS_ERR_INVALID, "agrs_sgd_step_multi_f32: null pointer");
+  for (int base = 0; base < count; base += kMultiMax) {
+    SgdMulti a{};
+    a.count = count - base < kMultiMax ? count - base : kMultiMax;
+    a.lr = lr;
+    size_t largest = 0;
+    bool any_mx = false;
+    for (int i = 0; i < a.count; ++i) {
+      AGRS_REQUIRE(ctx, n[base + i] == 0 || (w[base + i] && g[base + i]), AGRS_ERR_INVALID, "agrs_sgd_step_multi_f32: null parameter %d", base + i);
+      a.w[i] = w[base + i];
+      a.g[i] = g[base + i];
+      a.n[i] = n[base + i];
+      a.mx[i] = out_absmax ? out_absmax[base + i] : nullptr;
+      any_mx = any_mx || a.mx[i];
+      if (a.n[i] > largest) largest = a.n[i];
+    }
+    if (largest == 0) continue;
+    if (any_mx) {
+      k_zero_words<<<1, kMultiMax, 0, ctx->stream>>>(a);
+      AGRS_LAUNCHED(ctx);
+    }
+    dim3 grid(unsigned(grid_for(ctx, (largest + 3) / 4, kUnroll)), unsigned(a.count));
+    k_sgd_multi<<<grid, kThreads, 0, ctx->stream>>>(a);
+    AGRS_LAUNCHED(ctx);
+  }
+  return AGRS_OK;
 }
 
 int agrs_sgd_step_f32(agrs_ctx* ctx, float* w, const float* g, float lr, size_t n, size_t ng) {

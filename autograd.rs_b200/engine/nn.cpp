@@ -58,6 +58,13 @@ void zero_grad(const std::vector<Tensor>& params) {
 void NN::zero_grad() const { nn::zero_grad(parameters()); }
 
 void sgd_step(const std::vector<Tensor>& params, float lr) {
+  // parameters whose gradient has their own length (every Linear / Conv2D parameter after a backward pass) are updated by ONE
+  // launch (agrs_sgd_step_multi_f32); a gradient that broadcasts onto its parameter keeps the single-tensor call
+  std::vector<float*> ws;
+  std::vector<const float*> gs;
+  std::vector<size_t> ns;
+  std::vector<uint32_t*> mxs;
+  Device* dev = nullptr;
   for (auto& p : params) {
     if (!p.has_grad()) throw Panic("called `Option::unwrap()` on a `None` value");  // w_grad.as_ref().unwrap(), optim.rs:30
     Storage& w = *p.data;
@@ -67,9 +74,22 @@ void sgd_step(const std::vector<Tensor>& params, float lr) {
     if (k == Bcast::Leading) throw Panic("SGD: gradient " + shape_str(g.shape) + " broadcasts along rows of " + shape_str(w.shape), AGRS_ERR_UNSUPPORTED);
     // tmp = grad * lr; w -= tmp fused in one pass with the same two roundings
     float* wp = w.wptr();
-    if (w.len() == g.len()) w.expect_magnitude_report();  // the updated weights are the next step's GEMM operands
+    if (w.len() == g.len() && (dev == nullptr || dev == w.dev())) {
+      dev = w.dev();
+      uint32_t* mx = nullptr;
+      if (w.buf->n >= (int64_t(1) << 16) && dev->reports_magnitudes()) {  // the updated weights are the next step's GEMM operands
+        mx = w.buf->mx_slot();
+        w.buf->mx_valid = true;
+      }
+      ws.push_back(wp);
+      gs.push_back(g.rptr());
+      ns.push_back(size_t(w.len()));
+      mxs.push_back(mx);
+      continue;
+    }
     w.dev()->check(agrs_sgd_step_f32(w.dev()->ctx(), wp, g.rptr(), lr, size_t(w.len()), size_t(g.len())));
   }
+  if (!ws.empty()) dev->check(agrs_sgd_step_multi_f32(dev->ctx(), int(ws.size()), ws.data(), gs.data(), ns.data(), mxs.data(), lr));
 }
 void SGD::step() { sgd_step(parameters_, lr_); }
 

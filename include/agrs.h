@@ -219,6 +219,11 @@ AGRS_API int agrs_sum_axis_f32(agrs_ctx* ctx, const float* x, int64_t outer, int
 
 /* ---- optimiser (src/nn/optim.rs:25-34) ---- w[i] -= lr * g[i % ng]  (ng == n, or g broadcast: bias [1,O] -= [O]) */
 AGRS_API int agrs_sgd_step_f32(agrs_ctx* ctx, float* w, const float* g, float lr, size_t n, size_t ng);
+/* the same update for `count` parameters (each with a gradient of its own length) in one launch per 16 of them: SGD::step's loop
+ * over the parameter list (optim.rs:25-34) without one launch per tensor.  out_absmax (may be NULL, entries may be NULL): where to
+ * leave the magnitude word of each updated parameter (agrs_next_output_absmax's by-product, per tensor). */
+AGRS_API int agrs_sgd_step_multi_f32(agrs_ctx* ctx, int count, float* const* w, const float* const* g, const size_t* n,
+                                     uint32_t* const* out_absmax, float lr);
 
 /* ---- Conv2D lowering (src/operators/functional_ndarray.rs:40-138, operators.rs:330,341,364-376) ---- */
 /* col[b, y*Wo+x, c*k*k+i*k+j] = im[b,c,y*s-p+i,x*s-p+j] or 0;  col is [B, Ho*Wo, C*k*k] */
