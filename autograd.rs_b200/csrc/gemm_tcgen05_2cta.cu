@@ -1052,11 +1052,12 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   }
   const int64_t items = split_from + (tiles - split_from) * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
-  // wave alignment of the TMA producers: 1 = whenever there is more than one wave; 2 (default) = problems beyond the training shapes
-  // (>= 4 waves of >= 128 k-blocks and (M + N) * K >= 2^28, i.e. from about 11600^3).  Measured (profiles/r2_gemm_wave_sync.txt):
-  // 16384^3 312 -> 385 TFLOP/s, DRAM reads 64.4 -> 17.8 GB, L2 hit rate 50 -> 76 %; 8192^3 +1 %; the C2 shapes unchanged.
+  // wave alignment of the TMA producers: 1 = whenever there is more than one wave; 2 (default) = large problems (>= 4 waves of >= 128
+  // k-blocks and (M + N) * K >= 2^27, i.e. from 8192^3: the C5 layers, not the C2 ones).  Measured (profiles/r2_gemm_wave_sync.txt):
+  // 16384^3 312 -> 385 TFLOP/s, DRAM reads 64.4 -> 17.8 GB, L2 hit rate 50 -> 76 %; 8192^3 +1 % alone, +2 % inside the power-capped
+  // C5 step; the C2 shapes unchanged alone and 0..2 % slower in the step, hence the threshold.
   unsigned int* wave_sync = nullptr;
-  if (items > pairs && (ctx->tc_wave_sync == 1 || (ctx->tc_wave_sync == 2 && items >= 4 * pairs && num_kb / splits >= 128 && (M + N) * K >= (int64_t(1) << 28)))) {
+  if (items > pairs && (ctx->tc_wave_sync == 1 || (ctx->tc_wave_sync == 2 && items >= 4 * pairs && num_kb / splits >= 128 && (M + N) * K >= (int64_t(1) << 27)))) {
     wave_sync = ctx->counter + 12;  // its own 4 bytes of the context's counter block
     k_zero_u32<<<1, 1, 0, ctx->stream>>>(wave_sync);
     AGRS_LAUNCHED(ctx);

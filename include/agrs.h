@@ -143,8 +143,7 @@ enum agrs_tuning_key {
                                    launch left in the workspace -- only meaningful when the operands have not changed.  Default 0 */
   AGRS_TUNE_TC_WAVE_SYNC = 9    /* pair kernel: the TMA producers of a wave of tiles start together so that the CTA pairs keep sharing
                                    operand blocks through the L2 (a bounded wait, never a dependency; results do not change).  0 = off,
-                                   1 = whenever there is more than one wave, 2 (default) = very large problems only (from about
-                                   11600^3).  Env AGRS_TC_WAVE_SYNC overrides the default at context creation */
+                                   1 = whenever there is more than one wave, 2 (default) = large problems only (from 8192^3).  Env AGRS_TC_WAVE_SYNC overrides the default at context creation */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
 AGRS_API int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value);
