@@ -29,6 +29,7 @@ struct agrs_ctx {
   int tc_explicit_hi = 0;  // 1: splitter also writes the truncated hi tile back (does not rely on HW truncation)
   int tc_cross = 5;        // pair kernel split scheme (AGRS_TUNE_TC_CROSS): 0 tf32 x3, 1 / 2 tf32 + bf16 cross terms, 3 bf16 x3, 4 fp16 x3 scaled,
                            // 5 (default) = 4 when the caller announced operand magnitudes, else 1
+  uint32_t func_attr_done = 0;  // which kernels of conv.cu already have their dynamic shared-memory limit raised on THIS context's device
   int conv_tiled = 1;      // Conv2D backward, single input channel: 1 register-tiled kernel where the shape allows (AGRS_CONV_TILED=0: the generic one)
   int tc_epi_tma = 1;      // pair kernel epilogue: 1 staged in shared memory + TMA store / reduce-add, 0 direct st.global from registers
   int tc_wave_sync = 2;    // pair kernel: the TMA producers of a wave start their tiles together (0 off, 1 always, 2 large problems; AGRS_TC_WAVE_SYNC)

@@ -945,22 +945,19 @@ int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
     const int64_t groups = (B + kCfSamples - 1) / kCfSamples, tcap = int64_t(ctx->sm_count) * 2;
     const unsigned tgrid = unsigned(groups < tcap ? groups : tcap);
     if (k == 5) {
-      static bool a5 = false;
-      if (!a5) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); a5 = true; }
+      if (!(ctx->func_attr_done & 1u)) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); ctx->func_attr_done |= 1u; }
       k_conv1_fwd_tiled<5><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out);
     } else {
-      static bool a3 = false;
-      if (!a3) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); a3 = true; }
+      if (!(ctx->func_attr_done & 2u)) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); ctx->func_attr_done |= 2u; }
       k_conv1_fwd_tiled<3><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out);
     }
     AGRS_LAUNCHED(ctx);
     return AGRS_OK;
   }
   const int64_t cap = int64_t(ctx->sm_count) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->func_attr_done & 4u)) {  // per context: the attribute belongs to the device the context is on
     AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    ctx->func_attr_done |= 4u;
   }
   k_conv1_fwd<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo, out);
   AGRS_LAUNCHED(ctx);
@@ -990,12 +987,10 @@ int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
       ctx->tickets_n = 4096;
     }
     if (k == 5) {
-      static bool attr5 = false;
-      if (!attr5) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr5 = true; }
+      if (!(ctx->func_attr_done & 8u)) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); ctx->func_attr_done |= 8u; }
       k_conv1_bwd_tiled<5><<<unsigned(tgrid), kCtThreads, ge.smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(c_out), dx, dw, db, ctx->workspace, ctx->tickets);
     } else {
-      static bool attr3 = false;
-      if (!attr3) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr3 = true; }
+      if (!(ctx->func_attr_done & 16u)) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); ctx->func_attr_done |= 16u; }
       k_conv1_bwd_tiled<3><<<unsigned(tgrid), kCtThreads, ge.smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(c_out), dx, dw, db, ctx->workspace, ctx->tickets);
     }
     AGRS_LAUNCHED(ctx);
@@ -1013,10 +1008,10 @@ int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
   }
 #define AGRS_CONV_BWD(S1_, KT_)                                                                                                            \
   do {                                                                                                                                   \
-    static bool attr_set = false;                                                                                                        \
-    if (!attr_set) {                                                                                                                     \
+    const uint32_t bit = 32u << ((S1_ ? 1 : 0) + (KT_ == 5 ? 2 : KT_ == 3 ? 4 : 0));                                                      \
+    if (!(ctx->func_attr_done & bit)) {                                                                                                  \
       AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_bwd<S1_, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));               \
-      attr_set = true;                                                                                                                   \
+      ctx->func_attr_done |= bit;                                                                                                        \
     }                                                                                                                                    \
     k_conv1_bwd<S1_, KT_><<<unsigned(grid), 256, smem, ctx->stream>>>(im, filt, grad, int(B), int(H), int(W), int(k), int(c_out), int(stride), \
                                                                       int(pad), Ho, Wo, dx, dw, db, ctx->workspace, ctx->tickets);        \
