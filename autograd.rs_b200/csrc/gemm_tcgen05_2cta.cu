@@ -922,16 +922,19 @@ __global__ void __launch_bounds__(256) k_add_partials(float* __restrict__ C, int
   }
 }
 
-// the same for the tiles [tile_from, tiles_mn) only (tile order of the GEMM: tile_coords): one block per tile and pass
+// the same for the tiles [tile_from, tiles_mn) only (tile order of the GEMM: tile_coords): eight blocks per tile, 32 rows each
 __global__ void __launch_bounds__(256) k_add_partials_tiles(float* __restrict__ C, int64_t ldc, const float* __restrict__ P, int nparts, int64_t M, int64_t N,
                                                             int64_t m_tiles, int64_t n_tiles, int64_t tile_from, int64_t tiles_mn) {
   const bool vec = (N & 3) == 0 && (ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(P)) & 15u) == 0;
   const int64_t total = M * N;
-  for (int64_t t = tile_from + blockIdx.x; t < tiles_mn; t += gridDim.x) {
+  constexpr int kSlices = 8, kSliceRows = 2 * BM / kSlices;
+  for (int64_t u = blockIdx.x; u < (tiles_mn - tile_from) * kSlices; u += gridDim.x) {
+    const int64_t t = tile_from + u / kSlices;
     int64_t mb, nb;
     tile_coords(t, m_tiles, n_tiles, mb, nb);
-    const int64_t r0 = mb * 2 * BM, c0 = nb * BN;
-    const int rows = int(M - r0 < 2 * BM ? M - r0 : 2 * BM), cols = int(N - c0 < BN ? N - c0 : BN);
+    const int64_t r0 = mb * 2 * BM + (u % kSlices) * kSliceRows, c0 = nb * BN;
+    if (r0 >= M) continue;
+    const int rows = int(M - r0 < kSliceRows ? M - r0 : kSliceRows), cols = int(N - c0 < BN ? N - c0 : BN);
     if (vec) {  // cols is a multiple of 4 (N and the tile width are)
       const int c4n = cols >> 2;
       for (int e = threadIdx.x; e < rows * c4n; e += 256) {
@@ -1066,7 +1069,7 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
   AGRS_LAUNCHED(ctx);
   if (splits > 1 && split_from > 0) {  // only the tiles of the last wave were split
     const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
-    k_add_partials_tiles<<<unsigned(tiles - split_from), 256, 0, ctx->stream>>>(C, ldc, Cw, splits - 1, M, N, m_tiles, n_tiles, split_from, tiles);
+    k_add_partials_tiles<<<unsigned((tiles - split_from) * 8), 256, 0, ctx->stream>>>(C, ldc, Cw, splits - 1, M, N, m_tiles, n_tiles, split_from, tiles);
     AGRS_LAUNCHED(ctx);
   } else if (splits > 1) {
     const int64_t blocks = (M * N / 4 + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
