@@ -53,6 +53,7 @@ def lib():
             "agrs_alloc": [vp, sz, C.POINTER(vp)],
             "agrs_free": [vp, vp],
             "agrs_pool_reserve": [vp, sz],
+            "agrs_pool_trim": [vp],
             "agrs_pool_stats": [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)],
             "agrs_host_alloc": [vp, sz, C.POINTER(vp)],
             "agrs_host_free": [vp, vp],

@@ -263,6 +263,18 @@ int agrs_pool_reserve(agrs_ctx* ctx, size_t nbytes) {
   return AGRS_OK;
 }
 
+int agrs_pool_trim(agrs_ctx* ctx) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_pool_trim");
+  AGRS_NOT_CAPTURING(ctx, "agrs_pool_trim");
+  AGRS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  AGRS_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
+  uint64_t zero = 0;
+  AGRS_CUDA(ctx, cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReservedMemHigh, &zero));
+  AGRS_CUDA(ctx, cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrUsedMemHigh, &zero));
+  return AGRS_OK;
+}
+
 int agrs_pool_stats(agrs_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes, size_t* reserved_high, size_t* used_high) {
   AGRS_CHECK_CTX(ctx);
   AGRS_RANGE("agrs_pool_stats");

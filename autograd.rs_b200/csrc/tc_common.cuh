@@ -27,10 +27,23 @@ static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) 
   printf("agrs tcgen05 gemm: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
   __trap();
 }
+// AGRS_WAIT_NS > 0: every wait carries that suspend-time hint (see mbar_wait_relaxed below); 0: plain try_wait, re-polled in a loop
+#ifndef AGRS_WAIT_NS
+#define AGRS_WAIT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
 #pragma unroll 1
   for (uint32_t spins = 0;; ++spins) {
+#if AGRS_WAIT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(uint32_t(AGRS_WAIT_NS))
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -38,6 +51,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     if (done) break;
     if (spins > (1u << 24)) mbar_timeout(bar, parity);
   }

@@ -242,6 +242,10 @@ class Device:
     def pool_reserve(self, nbytes):
         self._k("agrs_pool_reserve", int(nbytes))
 
+    def pool_trim(self):
+        """give the pool's unused blocks back to the driver and reset its high-water marks (blocks)"""
+        self._k("agrs_pool_trim")
+
     def pool_stats(self):
         """(reserved now, used now, reserved high-water mark, used high-water mark) in bytes"""
         a = [C.c_size_t() for _ in range(4)]

@@ -61,6 +61,9 @@ AGRS_API int agrs_alloc(agrs_ctx* ctx, size_t nbytes, void** out); /* stream-ord
  * the first training steps do not pay for pool growth -- a driver call that takes milliseconds per GB -- inside a timed region. */
 AGRS_API int agrs_pool_reserve(agrs_ctx* ctx, size_t nbytes);
 AGRS_API int agrs_pool_stats(agrs_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes, size_t* reserved_high, size_t* used_high);
+/* Hand the pool's unused blocks back to the driver (blocks: synchronises the stream first) and reset its high-water marks: between
+ * two workloads of very different footprint, so that the second starts from the pool a fresh process would have. */
+AGRS_API int agrs_pool_trim(agrs_ctx* ctx);
 AGRS_API int agrs_free(agrs_ctx* ctx, void* ptr);                  /* stream-ordered: safe with work in flight */
 AGRS_API int agrs_host_alloc(agrs_ctx* ctx, size_t nbytes, void** out); /* pinned host staging */
 AGRS_API int agrs_host_free(agrs_ctx* ctx, void* ptr);
