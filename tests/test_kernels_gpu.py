@@ -184,6 +184,83 @@ def test_sgd_step_exact(ctx, n, ng):
     assert np.array_equal(ctx.to_host(dw, (n,)), want.reshape(-1))
 
 
+def test_sgd_step_multi_matches_the_single_tensor_kernel(ctx):
+    """agrs_sgd_step_multi_f32: SGD::step's loop over the parameter list as one launch per 16 parameters -- the same bits as
+    agrs_sgd_step_f32 per tensor (two roundings), for aligned, ragged, tiny and empty tensors, and the magnitude words it leaves
+    are what agrs_absmax_f32 finds on the updated tensors"""
+    rng = np.random.default_rng(321)
+    sizes = [1, 3, 4, 17, 256, 1000003, 0, 4096 * 33, 5, 10, 6 * 25, 3456 * 10, 1 << 20, 12, 7, 64, 33, 2, 100]   # 19 tensors: two launches
+    ws = [rnd(rng, n) for n in sizes]
+    gs = [rnd(rng, n) for n in sizes]
+    dw = [ctx.to_device(w) for w in ws]
+    dg = [ctx.to_device(g) for g in gs]
+    mx = [ctx.empty(1) if n >= 256 else None for n in sizes]
+    for m in mx:
+        if m is not None:
+            ctx.call("agrs_fill_f32", m.ptr, ctypes.c_float(3.0), 1)   # stale contents must not survive
+    cnt = len(sizes)
+    PW, PS = ctypes.c_void_p * cnt, ctypes.c_size_t * cnt
+    ctx.call("agrs_sgd_step_multi_f32", cnt, PW(*[b.ptr for b in dw]), PW(*[b.ptr for b in dg]), PS(*sizes),
+             PW(*[m.ptr if m is not None else None for m in mx]), ctypes.c_float(1e-3))
+    for n, w, g, b, m in zip(sizes, ws, gs, dw, mx):
+        if n == 0:
+            continue
+        want = w.reshape(-1, n).copy()
+        O.sgd_step(want, g, 1e-3)
+        got = ctx.to_host(b, (n,))
+        assert np.array_equal(got, want.reshape(-1)), n
+        if m is not None:
+            bits = ctx.to_host(m, (1,)).view(np.uint32)[0]
+            assert bits == np.abs(got).max().view(np.uint32), n
+    with pytest.raises(K.AgrsError):
+        ctx.call("agrs_sgd_step_multi_f32", 2, PW(dw[0].ptr, None), PW(dg[0].ptr, dg[1].ptr), PS(1, 3), None, ctypes.c_float(1e-3))
+
+
+def test_async_download_and_events_at_the_c_abi(ctx):
+    """agrs_download_async / agrs_event_wait / agrs_upload_prefetch_event / agrs_wait_event: the calls of INTEGRATION.md section 6"""
+    n = 1 << 20
+    host_in, host_out = ctypes.c_void_p(), ctypes.c_void_p()
+    ctx.call("agrs_host_alloc", n * 4, ctypes.byref(host_in))
+    ctx.call("agrs_host_alloc", n * 4, ctypes.byref(host_out))
+    a = np.frombuffer((ctypes.c_float * n).from_address(host_in.value), dtype=np.float32)
+    b = np.frombuffer((ctypes.c_float * n).from_address(host_out.value), dtype=np.float32)
+    a[:] = np.arange(n, dtype=np.float32)
+    b[:] = -1
+    landed, read = ctypes.c_void_p(), ctypes.c_void_p()
+    ctx.call("agrs_event_create", ctypes.byref(landed))
+    ctx.call("agrs_event_create", ctypes.byref(read))
+    ctx.call("agrs_event_wait", read)                      # never recorded: returns at once
+    dev, dev2 = ctx.empty(n), ctx.empty(n)
+    ctx.call("agrs_upload_prefetch_event", dev.ptr, host_in, n * 4, landed)
+    ctx.call("agrs_wait_event", landed)                    # the stream, not the host, waits for the copy
+    ctx.call("agrs_scalar_f32", K.SMUL, dev2.ptr, dev.ptr, ctypes.c_float(2.0), n)
+    ctx.call("agrs_download_async", host_out, dev2.ptr, n * 4, read)
+    ctx.call("agrs_event_wait", read)
+    assert np.array_equal(b, 2 * a)
+    with pytest.raises(K.AgrsError):
+        ctx.call("agrs_download_async", host_out, dev2.ptr, n * 4, None)
+    ctx.call("agrs_event_destroy", landed)
+    ctx.call("agrs_event_destroy", read)
+    ctx.call("agrs_host_free", host_in)
+    ctx.call("agrs_host_free", host_out)
+
+
+def test_pool_trim_returns_memory(ctx):
+    """agrs_pool_trim: unused blocks go back to the driver, high-water marks restart"""
+    def stats():
+        v = [ctypes.c_size_t() for _ in range(4)]
+        ctx.call("agrs_pool_stats", *[ctypes.byref(x) for x in v])
+        return [int(x.value) for x in v]
+    ctx.call("agrs_pool_reserve", 512 << 20)
+    assert stats()[0] >= 512 << 20
+    ctx.call("agrs_pool_trim")
+    reserved, used, reserved_high, used_high = stats()
+    assert reserved < 512 << 20 and reserved_high <= reserved + (64 << 20) and used_high <= used + (64 << 20)
+    buf = ctx.empty(1 << 20)                               # the pool still serves allocations afterwards
+    ctx.call("agrs_fill_f32", buf.ptr, ctypes.c_float(1.5), 1 << 20)
+    assert np.all(ctx.to_host(buf, (1 << 20,)) == 1.5)
+
+
 @pytest.mark.parametrize("B,D", [(1, 1), (5, 3), (2000, 1), (256, 4096), (1023, 77)])
 def test_mse_fwd_bwd(ctx, B, D):
     rng = np.random.default_rng(B * 7 + D)
