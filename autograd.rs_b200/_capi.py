@@ -19,7 +19,7 @@ ADD, SUB, MUL = 0, 1, 2
 SMUL, SDIV, SRSUB, SADD = 0, 1, 2, 3
 BCAST_TRAILING, BCAST_LEADING = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SKINNY = 0, 1, 2, 3
-TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK, TUNE_TC_2CTA, TUNE_TC_SPLITK, TUNE_TC_CROSS, TUNE_TC_EPI_TMA, TUNE_TC_REUSE_SCALES, TUNE_TC_WAVE_SYNC = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+TUNE_TC_BN, TUNE_TC_EXPLICIT_HI, TUNE_TC_MIN_MACS, TUNE_TC_KCHUNK, TUNE_TC_2CTA, TUNE_TC_SPLITK, TUNE_TC_CROSS, TUNE_TC_EPI_TMA, TUNE_TC_REUSE_SCALES, TUNE_TC_WAVE_SYNC, TUNE_TC_ACT_WARPS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 _lib = None
 
@@ -70,6 +70,8 @@ def lib():
             "agrs_prefetch_join": [vp],
             "agrs_fill_f32": [vp, vp, f32, sz],
             "agrs_gemm_f32": [vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp],
+            "agrs_gemm_bias_act_f32": [vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, vp, i32, vp, i64],
+            "agrs_last_gemm_act_fused": [vp],
             "agrs_set_gemm_path": [vp, i32],
             "agrs_gemm_operand_absmax": [vp, vp, vp],
             "agrs_gemm_wants_absmax": [vp, i64, i64, i64],

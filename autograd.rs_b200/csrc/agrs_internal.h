@@ -33,12 +33,22 @@ struct agrs_ctx {
   int conv_tiled = 1;      // Conv2D backward, single input channel: 1 register-tiled kernel where the shape allows (AGRS_CONV_TILED=0: the generic one)
   int tc_epi_tma = 1;      // pair kernel epilogue: 1 staged in shared memory + TMA store / reduce-add, 0 direct st.global from registers
   int tc_wave_sync = 2;    // pair kernel: the TMA producers of a wave start their tiles together (0 off, 1 always, 2 large problems; AGRS_TC_WAVE_SYNC)
+  int tc_act_warps = 0;    // pair kernel, agrs_gemm_bias_act_f32: 1 = the activation warps write act(C) inside the GEMM (AGRS_TUNE_TC_ACT_WARPS), 0 = second pass
   int tc_reuse_scales = 0; // cross mode 4, measurement aid: 1 = reuse the operand magnitudes of the previous launch (same operands only)
   // operand magnitudes for the next GEMM call (agrs_gemm_operand_absmax) and the slot the next elementwise launch reports into
   // (agrs_next_output_absmax); both are consumed by the call they apply to
   const uint32_t* gemm_a_mx = nullptr;
   const uint32_t* gemm_b_mx = nullptr;
   uint32_t* next_out_mx = nullptr;
+  // the activation request of the agrs_gemm_bias_act_f32 call in flight, as the GEMM back ends see it: a back end that can write
+  // act(C) next to C from its epilogue does so and sets `fused`; otherwise the entry point runs the activation as a second pass
+  struct GemmAct {
+    int kind = 0;        // AGRS_ACT_NONE / AGRS_ACT_RELU / AGRS_ACT_SIGMOID
+    float* y = nullptr;  // [M, N], row pitch ldy
+    int64_t ldy = 0;
+    bool fused = false;
+  } gemm_act;
+  int last_act_fused = 0;  // agrs_last_gemm_act_fused
   int64_t tc_min_flops = (1LL << 24) + 1;  // AUTO path: up to 256^3 MACs the SIMT kernel wins on launch + pipeline-fill latency (7.5 vs 12.1 us
                                            // of device time at 256^3; 512^3: 17.2 vs 13.9 -- profiles/r2_gemm_sweep_small_graph.txt)
   // small scratch for reductions (block partials + completion counter), allocated once

@@ -43,6 +43,7 @@ static int ctx_init(int device, cudaStream_t stream, bool own, agrs_ctx** out) {
     const int v = atoi(e);
     if (v >= 0 && v <= 5) ctx->tc_cross = v;
   }
+  if (const char* e = getenv("AGRS_TC_ACT_WARPS")) ctx->tc_act_warps = atoi(e) ? 1 : 0;  // default of AGRS_TUNE_TC_ACT_WARPS
   if (const char* e = getenv("AGRS_TC_EPI_TMA")) ctx->tc_epi_tma = atoi(e) ? 1 : 0;  // default of AGRS_TUNE_TC_EPI_TMA
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }
   if (own) {

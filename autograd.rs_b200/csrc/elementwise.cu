@@ -4,6 +4,7 @@
 // grid-stride).  Streaming cache hints: nothing here is re-read by the same kernel.
 #include "agrs_internal.h"
 #include "mag.cuh"
+#include "act.cuh"
 
 namespace {
 
@@ -16,14 +17,14 @@ __device__ __forceinline__ void st4(float* p, float4 v) { __stcs(reinterpret_cas
 
 
 // ---- functors (semantics cited from the reference) ----
-struct ReluFwd {  // functional_ndarray.rs:14-22: x > 0 ? x : 0  (-0.0, NaN -> +0.0)
-  __device__ float operator()(float x) const { return x > 0.f ? x : 0.f; }
+struct ReluFwd {  // functional_ndarray.rs:14-22: x > 0 ? x : 0  (-0.0, NaN -> +0.0); act.cuh
+  __device__ float operator()(float x) const { return agrs_act_relu(x); }
 };
 struct ReluBwd {  // functional_ndarray.rs:23-34: x <= 0 ? 0 : g  (NaN x passes g)
   __device__ float operator()(float x, float g) const { return x <= 0.f ? 0.f : g; }
 };
-struct SigmoidFwd {  // operators.rs:190-199: 1/(1+exp(-x)) in f32 (full-precision expf, IEEE divide)
-  __device__ float operator()(float x) const { return 1.0f / (1.0f + expf(-x)); }
+struct SigmoidFwd {  // operators.rs:190-199: 1/(1+exp(-x)) in f32 (full-precision expf, IEEE divide); act.cuh
+  __device__ float operator()(float x) const { return agrs_act_sigmoid(x); }
 };
 struct SigmoidBwd {  // operators.rs:219-223: ((1 - s) * s) * g
   __device__ float operator()(float x, float g) const {

@@ -1,5 +1,7 @@
 // agrs_gemm_f32: argument checking and path selection for the two GEMM back ends.
 #include "agrs_internal.h"
+#include "act.cuh"
+#include "mag.cuh"
 
 static cudaEvent_t take_event(agrs_ctx* ctx) {
   if (!ctx->event_pool.empty()) {
@@ -31,7 +33,58 @@ int agrs_prof_end(agrs_ctx* ctx, const agrs_ctx::ProfRec& rec) {
   return AGRS_OK;
 }
 
+// second pass of agrs_gemm_bias_act_f32 for outputs with padded rows (the contiguous case runs the elementwise kernels)
+static __global__ void __launch_bounds__(256) k_act_rows(const float* __restrict__ Z, int64_t ldz, float* __restrict__ Y, int64_t ldy, int64_t M,
+                                                         int64_t N, int kind, uint32_t* mx) {
+  uint32_t mag = 0;
+  const int64_t total = M * N, stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t m = i / N, n = i - m * N;
+    const float z = Z[m * ldz + n];
+    const float y = kind == AGRS_ACT_RELU ? agrs_act_relu(z) : agrs_act_sigmoid(z);
+    Y[m * ldy + n] = y;
+    mag = max(mag, mag_bits(y));
+  }
+  if (mx) mag_commit(mag, mx);
+}
+
 extern "C" {
+
+int agrs_gemm_bias_act_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                           const float* B, int64_t ldb, float* Z, int64_t ldz, const float* bias, int act, float* Y, int64_t ldy) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_gemm_bias_act_f32");
+  AGRS_REQUIRE(ctx, act == AGRS_ACT_RELU || act == AGRS_ACT_SIGMOID, AGRS_ERR_INVALID, "agrs_gemm_bias_act_f32: unknown activation %d", act);
+  AGRS_REQUIRE(ctx, M <= 0 || N <= 0 || (Y && ldy >= N), AGRS_ERR_INVALID, "agrs_gemm_bias_act_f32: null Y or ldy < N");
+  AGRS_REQUIRE(ctx, Y != Z, AGRS_ERR_INVALID, "agrs_gemm_bias_act_f32: Y must not alias Z (the pre-activation stays a tensor of its own)");
+  ctx->gemm_act.kind = act;
+  ctx->gemm_act.y = Y;
+  ctx->gemm_act.ldy = ldy;
+  ctx->gemm_act.fused = false;
+  const int rc = agrs_gemm_f32(ctx, transA, transB, M, N, K, A, lda, B, ldb, Z, ldz, bias);
+  const bool fused = ctx->gemm_act.fused;
+  ctx->gemm_act = agrs_ctx::GemmAct{};
+  ctx->last_act_fused = fused ? 1 : 0;
+  if (rc) {
+    ctx->next_out_mx = nullptr;
+    return rc;
+  }
+  if (fused || M <= 0 || N <= 0) {
+    if (!fused) ctx->next_out_mx = nullptr;  // nothing was written
+    return AGRS_OK;
+  }
+  // the back end that ran could not write Y from its epilogue: the activation as a second pass over Z
+  if (ldz == N && ldy == N)
+    return act == AGRS_ACT_RELU ? agrs_relu_fwd_f32(ctx, Z, Y, size_t(M) * size_t(N)) : agrs_sigmoid_fwd_f32(ctx, Z, Y, size_t(M) * size_t(N));
+  uint32_t* mx = nullptr;
+  if (int trc = agrs_take_mx(ctx, &mx)) return trc;
+  const int64_t blocks = (M * N + 255) / 256, cap = int64_t(ctx->sm_count) * 8;
+  k_act_rows<<<unsigned(blocks < cap ? blocks : cap), 256, 0, ctx->stream>>>(Z, ldz, Y, ldy, M, N, act, mx);
+  AGRS_LAUNCHED(ctx);
+  return AGRS_OK;
+}
+
+int agrs_last_gemm_act_fused(agrs_ctx* ctx) { return ctx ? ctx->last_act_fused : 0; }
 
 int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
   AGRS_CHECK_CTX(ctx);
@@ -72,6 +125,9 @@ int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value) {
     case AGRS_TUNE_TC_MIN_MACS:
       ctx->tc_min_flops = value;
       return AGRS_OK;
+    case AGRS_TUNE_TC_ACT_WARPS:
+      ctx->tc_act_warps = value ? 1 : 0;
+      return AGRS_OK;
   }
   return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown tuning key %d", key);
 }
@@ -91,6 +147,7 @@ int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value) {
     case AGRS_TUNE_TC_REUSE_SCALES: *value = ctx->tc_reuse_scales; return AGRS_OK;
     case AGRS_TUNE_TC_WAVE_SYNC: *value = ctx->tc_wave_sync; return AGRS_OK;
     case AGRS_TUNE_TC_MIN_MACS: *value = ctx->tc_min_flops; return AGRS_OK;
+    case AGRS_TUNE_TC_ACT_WARPS: *value = ctx->tc_act_warps; return AGRS_OK;
   }
   return agrs_fail(ctx, AGRS_ERR_INVALID, "unknown tuning key %d", key);
 }

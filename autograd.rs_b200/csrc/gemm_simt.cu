@@ -4,8 +4,19 @@
 // combinations.  Skinny outputs with a long K (dW of the conv GEMM: 25x6 with K = B*P) are split
 // along K into a workspace and folded in a fixed order (deterministic).
 #include "agrs_internal.h"
+#include "act.cuh"
+#include "mag.cuh"
 
 namespace {
+
+// forward activation next to the pre-activation (agrs_gemm_bias_act_f32): y = act(c) written by the thread that holds c
+struct SimtAct {
+  int kind;       // AGRS_ACT_NONE: nothing to do
+  float* y;
+  int64_t ldy;
+  uint32_t* mx;   // magnitude word of y, or null
+};
+__device__ __forceinline__ float simt_act(int kind, float v) { return kind == AGRS_ACT_RELU ? agrs_act_relu(v) : agrs_act_sigmoid(v); }
 
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;  // 256 threads, 4x4 micro-tile each
 
@@ -13,7 +24,8 @@ constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;  // 256 threads, 4x4 mi
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) k_gemm_simt(int64_t M, int64_t N, int64_t K, const float* __restrict__ A, int64_t lda,
                                                    const float* __restrict__ B, int64_t ldb, float* __restrict__ C, int64_t ldc,
-                                                   const float* __restrict__ bias, int64_t k_per_split, float* __restrict__ part) {
+                                                   const float* __restrict__ bias, int64_t k_per_split, float* __restrict__ part,
+                                                   const SimtAct act) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -59,6 +71,7 @@ __global__ void __launch_bounds__(256) k_gemm_simt(int64_t M, int64_t N, int64_t
     }
     __syncthreads();
   }
+  uint32_t y_mag = 0;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int64_t gm = m0 + ty * TM + i;
@@ -73,20 +86,34 @@ __global__ void __launch_bounds__(256) k_gemm_simt(int64_t M, int64_t N, int64_t
         float v = acc[i][j];
         if (bias) v += bias[gn];
         C[gm * ldc + gn] = v;
+        if (act.kind) {
+          const float y = simt_act(act.kind, v);
+          act.y[gm * act.ldy + gn] = y;
+          y_mag = max(y_mag, mag_bits(y));
+        }
       }
     }
   }
+  if (act.kind && act.mx) mag_commit(y_mag, act.mx);
 }
 
 __global__ void k_fold_splitk(const float* __restrict__ part, int splits, int64_t M, int64_t N, float* __restrict__ C, int64_t ldc,
-                              const float* __restrict__ bias) {
+                              const float* __restrict__ bias, const SimtAct act) {
   int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= M * N) return;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += part[int64_t(z) * M * N + i];
-  int64_t m = i / N, n = i % N;
-  if (bias) s += bias[n];
-  C[m * ldc + n] = s;
+  uint32_t y_mag = 0;
+  if (i < M * N) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[int64_t(z) * M * N + i];
+    int64_t m = i / N, n = i % N;
+    if (bias) s += bias[n];
+    C[m * ldc + n] = s;
+    if (act.kind) {
+      const float y = simt_act(act.kind, s);
+      act.y[m * act.ldy + n] = y;
+      y_mag = mag_bits(y);
+    }
+  }
+  if (act.kind && act.mx) mag_commit(y_mag, act.mx);
 }
 
 __global__ void k_bias_rows(int64_t M, int64_t N, float* C, int64_t ldc, const float* bias) {
@@ -100,6 +127,15 @@ __global__ void k_bias_rows(int64_t M, int64_t N, float* C, int64_t ldc, const f
 int agrs_gemm_simt(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
                    const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias) {
   if (M == 0 || N == 0) return AGRS_OK;
+  // agrs_gemm_bias_act_f32: both kernels that write C hold its final value in a register, so they write act(C) as well
+  SimtAct act{AGRS_ACT_NONE, nullptr, 0, nullptr};
+  if (ctx->gemm_act.kind != AGRS_ACT_NONE && K > 0) {
+    act.kind = ctx->gemm_act.kind;
+    act.y = ctx->gemm_act.y;
+    act.ldy = ctx->gemm_act.ldy;
+    if (int rc = agrs_take_mx(ctx, &act.mx)) return rc;
+    ctx->gemm_act.fused = true;
+  }
   if (K == 0) {  // empty inner dimension: C = bias (ndarray: dot over an empty axis is 0)
     k_bias_rows<<<unsigned((M * N + 255) / 256), 256, 0, ctx->stream>>>(M, N, C, ldc, bias);
     AGRS_LAUNCHED(ctx);
@@ -131,8 +167,11 @@ int agrs_gemm_simt(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
     const float* Ar = transA ? A + r0 : A + r0 * lda;
     float* Cr = C + r0 * ldc;
     float* pr = part;  // split-K only happens when tiles < sm_count, i.e. a single slab
+    SimtAct act_r = act;
+    if (splits > 1) act_r.kind = AGRS_ACT_NONE;  // the fold kernel holds the final values
+    else if (act.kind) act_r.y = act.y + r0 * act.ldy;
 #define AGRS_SIMT(TA_, TB_) \
-  k_gemm_simt<TA_, TB_><<<grid, 256, 0, ctx->stream>>>(rows, N, K, Ar, lda, B, ldb, Cr, ldc, splits > 1 ? nullptr : bias, kps, pr)
+  k_gemm_simt<TA_, TB_><<<grid, 256, 0, ctx->stream>>>(rows, N, K, Ar, lda, B, ldb, Cr, ldc, splits > 1 ? nullptr : bias, kps, pr, act_r)
     if (transA && transB) AGRS_SIMT(true, true);
     else if (transA) AGRS_SIMT(true, false);
     else if (transB) AGRS_SIMT(false, true);
@@ -141,7 +180,7 @@ int agrs_gemm_simt(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
     AGRS_LAUNCHED(ctx);
   }
   if (splits > 1) {
-    k_fold_splitk<<<unsigned((M * N + 255) / 256), 256, 0, ctx->stream>>>(part, splits, M, N, C, ldc, bias);
+    k_fold_splitk<<<unsigned((M * N + 255) / 256), 256, 0, ctx->stream>>>(part, splits, M, N, C, ldc, bias, act);
     AGRS_LAUNCHED(ctx);
   }
   return AGRS_OK;

@@ -16,12 +16,16 @@
 // warps 4-7 epilogue, warps 8-15 splitters.  Cross-CTA signalling: splitters and epilogue warps of both CTAs arrive on
 // the LEADER's mbarriers (CTA-scope release); the leader's tcgen05.commit multicasts to the same barrier in both CTAs.
 #include "tc_common.cuh"
+#include "act.cuh"
+#include "mag.cuh"
 
 namespace tc2 {
 using namespace tc;
 
 constexpr int kThreads = 512;
 constexpr int kEpiWarp0 = 4;
+constexpr int kActWarp0 = 2;  // ACT instantiations: warps 2 and 3 (idle otherwise once TMEM is allocated) apply the activation
+constexpr int kActWarps = 2;
 constexpr int kSplitWarp0 = 8;
 constexpr int kSplitWarps = 8;
 #ifndef AGRS_SPLIT_GROUPS
@@ -103,6 +107,13 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
                    reinterpret_cast<uint64_t>(map)),
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+// the other direction (forward activation in the epilogue: the folded partial sum of the earlier K chunks comes back as a piece)
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -446,13 +457,31 @@ struct ScatterArgs {
   int gshift;       // log2 of the ownership granule in floats (>= 5)
 };
 
-template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
+// ACT (forward activation next to the pre-activation, agrs_gemm_bias_act_f32; staged epilogue, unsplit tiles only): the epilogue
+// is the plain one -- K chunks fold into Z by TMA store / reduce-add -- plus one signal per tile: "my pieces of Z have been
+// performed".  Warps 2 and 3, idle in the plain kernel, are the ACTIVATION WARPS: once the four epilogue warps of their CTA have
+// signalled a tile they read its 128 x 256 part of Z back from L2 (written microseconds ago; coalesced 16-byte loads, 16 in flight
+// per lane), apply the activation and store Y, while tensor cores, splitters and epilogue are on the next tile.  Y is thus computed
+// from exactly the bits a separate activation kernel would read, Z is never re-read from HBM, and nothing waits for it: the
+// epilogue warps are the tightest loop of the kernel after the splitters (two earlier versions did the work there -- adding the
+// fetched partial sum to the last chunk in registers, then a post-pass after releasing the accumulator -- and cost the forward
+// GEMMs of C2 / C5 8-14 %).  The largest finite |act(Z)| goes to y_max (the magnitude word of Y: the next layer's GEMM scales its
+// operand by it).
+struct ActArgs {
+  int kind;         // AGRS_ACT_RELU / AGRS_ACT_SIGMOID
+  float* y;         // [M, N], row pitch ldy (a multiple of 4 floats, 16-byte aligned base)
+  int64_t ldy;
+  uint32_t* y_max;  // may be null
+};
+template <bool A_MN, bool B_MN, bool SCATTER, int CROSS, bool ACT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, float* C, int64_t ldc,
                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int kb_per_chunk, int splits, float* Cw,
                    const __grid_constant__ ScatterArgs sc, const __grid_constant__ CUtensorMap tmap_c,
                    const __grid_constant__ CUtensorMap tmap_w, int epi_tma, const uint32_t* __restrict__ a_max,
-                   const uint32_t* __restrict__ b_max, int mx_scalar, unsigned int* wave_sync, int64_t split_from) {
+                   const uint32_t* __restrict__ b_max, int mx_scalar, unsigned int* wave_sync, int64_t split_from,
+                   const ActArgs act) {
+  static_assert(!(ACT && SCATTER), "the activation epilogue is the staged one; the scattering epilogue stores from registers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t lo_base = smem_base + R * RAW_BYTES;
@@ -465,6 +494,9 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * R + 2 * L + 4);
+  const uint32_t z_done_bar = bar_base + 8u * (2 * R + 2 * L + 5);    // ACT: the four epilogue warps have completed a tile of Z
+  const uint32_t act_done_bar = bar_base + 8u * (2 * R + 2 * L + 6);  // ACT: the two activation warps have finished with that tile
+  static_assert(8u * (2 * R + 2 * L + 7) <= 256u, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
@@ -517,6 +549,10 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 2 * 4);  // both CTAs' epilogue warps arrive on the leader's barrier
+    }
+    if constexpr (ACT) {
+      mbar_init(z_done_bar, 4);
+      mbar_init(act_done_bar, kActWarps);
     }
     fence_barrier_init();
   }
@@ -743,6 +779,26 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // ---- staged epilogue: TMEM -> registers -> swizzled shared memory -> TMA store / reduce-add (see tma_store_3d) ----
       const uint32_t stage0 = epi_base + uint32_t(q) * (2 * EPI_TILE);
       uint32_t issued = 0;  // pieces this warp has handed to the TMA (buffer = issued & 1)
+      // one 32 x 32 piece: registers -> swizzled shared memory -> TMA tensor store (or reduce-add)
+      auto hand_over = [&](const uint32_t (&v)[32], const CUtensorMap* map, bool reduce, int32_t col0, int32_t row0, int32_t plane) {
+        const uint32_t buf = stage0 + (issued & 1u) * EPI_TILE;
+        if (lane == 0) bulk_wait_read<1>();  // the piece staged in this buffer two pieces ago has been read out
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // row `lane` of the piece, 16-byte chunk j in slot j ^ (lane & 7): SWIZZLE_128B
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + uint32_t(lane) * 128u + (uint32_t(j ^ (lane & 7)) << 4)),
+                       "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (reduce) tma_reduce_add_3d(map, buf, col0, row0, plane);
+          else        tma_store_3d(map, buf, col0, row0, plane);
+          bulk_commit();
+        }
+        ++issued;
+      };
+      uint32_t tiles_done = 0;  // ACT: tiles this warp has finished (phase bookkeeping of the hand-over to the activation warps)
       for (int64_t t = pair; t < num_tiles; t += num_pairs) {
         const Work w = work_item(t);
         const int64_t row0 = w.mb * 2 * BM + rank * BM + q * 32;
@@ -760,6 +816,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tc_fence_after();
           // the reductions of this chunk go to the addresses the previous chunk's pieces went to: those must have landed
           if (ch > 0 && lane == 0) bulk_wait_all();
+          const bool final_chunk = ACT && c0 + kb_per_chunk >= w.kb1;  // ACT launches never split K over pairs: Z is final here
           const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN);
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
@@ -785,28 +842,25 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (col0 + j < N) v[j] = __float_as_uint(__ldg(bias_s + col0 + j) + __uint_as_float(v[j]));
                 }
               }
-              const uint32_t buf = stage0 + (issued & 1u) * EPI_TILE;
-              if (lane == 0) bulk_wait_read<1>();  // the piece staged in this buffer two pieces ago has been read out
-              __syncwarp();
-#pragma unroll
-              for (int j = 0; j < 8; ++j)  // row `lane` of the piece, 16-byte chunk j in slot j ^ (lane & 7): SWIZZLE_128B
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(buf + uint32_t(lane) * 128u + (uint32_t(j ^ (lane & 7)) << 4)),
-                             "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                             : "memory");
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                if (ch == 0) tma_store_3d(cmap, buf, int32_t(col0), int32_t(row0), plane);
-                else         tma_reduce_add_3d(cmap, buf, int32_t(col0), int32_t(row0), plane);
-                bulk_commit();
-              }
-              ++issued;
+              hand_over(v, cmap, ch != 0, int32_t(col0), int32_t(row0), plane);
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(tempty_remote + 8u * acc);
           if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+          if constexpr (ACT) {
+            if (final_chunk) {
+              // the tile's Z is final once this chunk's pieces have been performed: tell the activation warps (see below).  They
+              // are at most one tile behind: a tile is only announced after they have finished with the one before it.
+              if (lane == 0) {
+                bulk_wait_all();
+                if (tiles_done > 0) mbar_wait(act_done_bar, (tiles_done - 1u) & 1u);
+                mbar_arrive(z_done_bar);
+              }
+              ++tiles_done;
+            }
+          }
         }
       }
       if (lane == 0) bulk_wait_all();  // shared memory stays valid, and C is complete, before the CTA leaves
@@ -885,6 +939,53 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
     }
+  } else if (ACT && warp >= kActWarp0) {
+    // ===================== activation warps (ACT, both CTAs): my CTA's 128 x 256 part of every finished tile =====================
+    constexpr int kRowsPerWarp = BM / kActWarps;
+    constexpr int kBatch = 16;  // 16-byte loads in flight per lane
+    const int aw = warp - kActWarp0;
+    uint32_t ph = 0, y_mag = 0;
+    for (int64_t t = pair; t < num_tiles; t += num_pairs) {
+      const Work w = work_item(t);
+      mbar_wait_long(z_done_bar, ph, AGRS_EPI_WAIT_NS);  // the bulk operations that wrote Z have completed: visible to plain loads
+      ph ^= 1u;
+      const int64_t r0 = w.mb * 2 * BM + rank * BM + aw * kRowsPerWarp, c0 = w.nb * BN;
+      const int rows = r0 < M ? int(M - r0 < kRowsPerWarp ? M - r0 : kRowsPerWarp) : 0;
+      const int vpr = int((N - c0 < BN ? N - c0 : BN) >> 2);  // 16-byte vectors per row (N % 4 == 0 on this path)
+      const int total = rows * vpr;
+      const float* const z_tile = C + r0 * ldc + c0;
+      float* const y_tile = act.y + r0 * act.ldy + c0;
+#pragma unroll 1
+      for (int base = 0; base < total; base += kBatch * 32) {
+        float4 x[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          const int e = base + i * 32 + lane;
+          if (e < total) {
+            const int r = vpr == BN / 4 ? e >> 6 : e / vpr, v = e - r * vpr;
+            x[i] = __ldcg(reinterpret_cast<const float4*>(z_tile + r * ldc) + v);  // from L2, never through this SM's L1
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+          const int e = base + i * 32 + lane;
+          if (e < total) {
+            const int r = vpr == BN / 4 ? e >> 6 : e / vpr, v = e - r * vpr;
+            float4 y;
+            if (act.kind == AGRS_ACT_RELU) {
+              y = make_float4(agrs_act_relu(x[i].x), agrs_act_relu(x[i].y), agrs_act_relu(x[i].z), agrs_act_relu(x[i].w));
+            } else {
+              y = make_float4(agrs_act_sigmoid(x[i].x), agrs_act_sigmoid(x[i].y), agrs_act_sigmoid(x[i].z), agrs_act_sigmoid(x[i].w));
+            }
+            y_mag = mag4(y_mag, y);
+            *(reinterpret_cast<float4*>(y_tile + r * act.ldy) + v) = y;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(act_done_bar);
+    }
+    if (act.y_max) mag_commit(y_mag, act.y_max);
   }
 
   tc_fence_before();
@@ -991,10 +1092,10 @@ static SplitPlan choose_plan(int64_t tiles, int64_t pairs, int64_t num_kb, int f
 }
 static int choose_splits(int64_t tiles, int64_t pairs, int64_t num_kb, int forced) { return choose_plan(tiles, pairs, num_kb, forced).splits; }
 
-template <bool A_MN, bool B_MN, bool SCATTER, int CROSS>
+template <bool A_MN, bool B_MN, bool SCATTER, int CROSS, bool ACT = false>
 static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, float* C, int64_t ldc, const float* bias, int64_t M,
                   int64_t N, int64_t K, int kb_per_chunk, const ScatterArgs& sc, const float* A, int64_t lda, const float* B, int64_t ldb) {
-  auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN, SCATTER, CROSS>;
+  auto kern = k_gemm_3xtf32_2cta<A_MN, B_MN, SCATTER, CROSS, ACT>;
   AGRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   const int64_t tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   const int64_t pairs = ctx->sm_count / 2;
@@ -1006,6 +1107,13 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     splits = int((num_kb + kps - 1) / kps);
   }
   const int64_t split_from = splits > 1 ? plan.split_from : 0;
+  if constexpr (ACT) {
+    // the activation warps need Z final when the kernel's own epilogue has finished a tile (no K split over pairs, staged epilogue)
+    // and 16-byte vectors on both outputs; otherwise this launch is the plain one and the caller runs the activation as a second pass
+    const agrs_ctx::GemmAct& ga = ctx->gemm_act;
+    if (!(ctx->tc_epi_tma && (ldc & 3) == 0 && agrs_aligned16(C) && splits == 1 && (N & 3) == 0 && (ga.ldy & 3) == 0 && agrs_aligned16(ga.y)))
+      return launch<A_MN, B_MN, SCATTER, CROSS, false>(ctx, ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, sc, A, lda, B, ldb);
+  }
   // workspace = [row magnitudes of op(A) | column magnitudes of op(B)] (CROSS 4 only) followed by the split-K partial planes
   const size_t a_slots = (size_t(M) + 63) / 64 * 64, b_slots = (size_t(N) + 63) / 64 * 64;
   // cross mode 4 with magnitudes supplied by the caller (agrs_gemm_operand_absmax: one per operand): no passes, no scale region
@@ -1053,6 +1161,15 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     if (rc) return rc;
     epi_tma = 1;
   }
+  ActArgs act{0, nullptr, 0, nullptr};
+  if constexpr (ACT) {
+    agrs_ctx::GemmAct& ga = ctx->gemm_act;
+    if (int rc = agrs_take_mx(ctx, &act.y_max)) return rc;  // agrs_next_output_absmax: zeroed on the stream, filled by the activation warps
+    act.kind = ga.kind;
+    act.y = ga.y;
+    act.ldy = ga.ldy;
+    ga.fused = true;
+  }
   const int64_t items = split_from + (tiles - split_from) * splits;
   const int grid = int(2 * (items < pairs ? items : pairs));
   // wave alignment of the TMA producers: 1 = whenever there is more than one wave; 2 (default) = large problems (>= 4 waves of >= 128
@@ -1065,7 +1182,7 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     k_zero_u32<<<1, 1, 0, ctx->stream>>>(wave_sync);
     AGRS_LAUNCHED(ctx);
   }
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0, wave_sync, split_from);
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0, wave_sync, split_from, act);
   AGRS_LAUNCHED(ctx);
   if (splits > 1 && split_from > 0) {  // only the tiles of the last wave were split
     const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
@@ -1100,17 +1217,24 @@ static int gemm_tc_2cta_impl(agrs_ctx* ctx, int transA, int transB, int64_t M, i
   // mode 5 (the default): the fp16 split when the caller announced the operands' magnitudes (the host engine keeps one per
   // buffer, reported by the kernel that wrote it), bf16 correction terms when it did not -- no magnitude passes either way
   const int cross = ctx->tc_cross == 5 ? (ctx->gemm_a_mx && ctx->gemm_b_mx ? 4 : 1) : ctx->tc_cross;
+  // forward activation in the epilogue (agrs_gemm_bias_act_f32): built for the two split schemes the default mode chooses between
+  // and opt-in (AGRS_TUNE_TC_ACT_WARPS): measured time-neutral on C5 and 1-2 % slower on C2 against the activation as its own
+  // launch -- see DESIGN 4.1 -- so by default the entry point runs the activation as a second pass after this kernel
+  const bool want_act = !sc && ctx->tc_act_warps && ctx->gemm_act.kind != AGRS_ACT_NONE && (cross == 1 || cross == 4);
 #define AGRS_PAIR_X(AM, BMJ, X)                                                                                     \
   (sc ? tc2::launch<AM, BMJ, true, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, *sc, A, lda, B, ldb)                  \
       : tc2::launch<AM, BMJ, false, X>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none, A, lda, B, ldb))
+#define AGRS_PAIR_ACT(AM, BMJ, X) tc2::launch<AM, BMJ, false, X, true>(ctx, ta, tb, C, ldc, bias, M, N, K, kpc, none, A, lda, B, ldb)
 #define AGRS_PAIR(AM, BMJ)                                                                      \
-  (cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) \
+  (want_act ? (cross == 1 ? AGRS_PAIR_ACT(AM, BMJ, 1) : AGRS_PAIR_ACT(AM, BMJ, 4))             \
+   : cross == 1 ? AGRS_PAIR_X(AM, BMJ, 1) : cross == 2 ? AGRS_PAIR_X(AM, BMJ, 2) \
    : cross == 3 ? AGRS_PAIR_X(AM, BMJ, 3) : cross == 4 ? AGRS_PAIR_X(AM, BMJ, 4) : AGRS_PAIR_X(AM, BMJ, 0))
   if (A_MN && B_MN) return AGRS_PAIR(true, true);
   if (A_MN) return AGRS_PAIR(true, false);
   if (B_MN) return AGRS_PAIR(false, true);
   return AGRS_PAIR(false, false);
 #undef AGRS_PAIR
+#undef AGRS_PAIR_ACT
 #undef AGRS_PAIR_X
 }
 

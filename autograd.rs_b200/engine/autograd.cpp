@@ -9,7 +9,10 @@ StoragePtr contig(const StoragePtr& s) { return s->transposed ? s->contiguous_co
 
 // C = op(a) * op(b) (+ bias row).  `ta`/`tb` ask for the LOGICAL transpose of the operand; a storage that is
 // itself a transposed view flips the flag back.  Nothing is ever copied: majors go to the GEMM as flags.
-Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bias = nullptr, GradCell* scatter_to = nullptr) {
+// `act` != 0 (Linear feeding ReLU / Sigmoid, f2 fusion): the call also produces *y_out = act(C), from the GEMM's epilogue where
+// that kernel holds final values, as a second pass inside the same C call otherwise (agrs_gemm_bias_act_f32).
+Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bias = nullptr, GradCell* scatter_to = nullptr, int act = 0,
+            Tensor* y_out = nullptr) {
   if (a.ndim() != 2 || b.ndim() != 2) throw Panic("Ndarray only supports 1d/2d matmul!");
   if (a.dev() != b.dev()) throw Panic("Tensors must be on same device");
   const Shape& as = a.shape();
@@ -25,7 +28,13 @@ Tensor gemm(const Tensor& a, bool ta, const Tensor& b, bool tb, const float* bia
   auto out = std::make_shared<Storage>(a.dev(), Shape{M, N});
   if (a.dev()->gemm_wants_magnitudes(M, N, K))  // fp16 split mode: one magnitude per operand, kept with the buffer
     a.dev()->check(agrs_gemm_operand_absmax(a.dev()->ctx(), a.data->buf->magnitude(), b.data->buf->magnitude()));
-  if (scatter_to) {
+  if (act) {
+    auto y = std::make_shared<Storage>(a.dev(), Shape{M, N});
+    y->expect_magnitude_report();  // the activation is the next layer's GEMM operand: whoever writes it reports its magnitude
+    a.dev()->check(agrs_gemm_bias_act_f32(a.dev()->ctx(), fa, fb, M, N, K, a.data->rptr(), fa ? M : K, b.data->rptr(), fb ? K : N,
+                                          out->buf->ptr, N, bias, act, y->buf->ptr, N));
+    *y_out = Tensor(y);
+  } else if (scatter_to) {
     // data-parallel weight gradient: GEMM -> reduce-scatter in one kernel, the epilogue pushes each tile to its owner over NVLink
     a.dev()->check(agrs_gemm_f32_scatter(a.dev()->ctx(), fa, fb, M, N, K, a.data->rptr(), fa ? M : K, b.data->rptr(), fb ? K : N,
                                          out->buf->ptr, bias, scatter_to->scatter, scatter_to->scatter_off));
@@ -87,10 +96,15 @@ Tensor fwd(const Sigmoid&, std::vector<Tensor>& xs) {
   return Tensor(out);
 }
 
+// the bias of a Linear layer as the GEMM epilogue can add it: one contiguous row of w's width
+bool bias_is_row(const Tensor& w, const Tensor& b) {
+  return w.ndim() == 2 && b.is_contiguous() && b.len() == w.shapei(1) && broadcast_kind(Shape{1, w.shapei(1)}, b.shape()) == Bcast::Same;
+}
+
 Tensor fwd(const Linear&, std::vector<Tensor>& xs) {
   // x.dot(w) + b, b added in place into the fresh dot result (operators.rs:140-144): the add is the GEMM epilogue
   const Tensor &x = xs.at(0), &w = xs.at(1), &b = xs.at(2);
-  if (w.ndim() == 2 && b.is_contiguous() && b.len() == w.shapei(1) && broadcast_kind(Shape{1, w.shapei(1)}, b.shape()) == Bcast::Same)
+  if (bias_is_row(w, b))
     return gemm(x, false, w, false, b.data->rptr());
   return add_inplace(gemm(x, false, w, false), b);
 }
@@ -368,6 +382,24 @@ Tensor forward(const Operators& op, std::vector<Tensor> xs) {
   if (std::holds_alternative<Identity>(op)) t.graph = nullptr;
   attach_to_eager_graph(xs, t, op);
   return t;
+}
+
+// Linear followed by ReLU / Sigmoid (the Layer loop of layers.rs:24-43 on [Linear, act], or two consecutive layers of a model):
+// the same two graph nodes -- the activation's node keeps the pre-activation as its variable (operators.rs:120-129, :214-224) --
+// from ONE GEMM call whose epilogue writes the activation next to the pre-activation.
+Tensor forward_pair(const Operators& first, const Operators& second, std::vector<Tensor> xs) {
+  const int act = std::holds_alternative<ReLU>(second) ? AGRS_ACT_RELU : std::holds_alternative<Sigmoid>(second) ? AGRS_ACT_SIGMOID : AGRS_ACT_NONE;
+  if (act && std::holds_alternative<Linear>(first) && xs.size() == 3 && xs[0].dev()->fuse_forward_activation && xs[0].ndim() == 2 &&
+      xs[1].dev() == xs[0].dev() && bias_is_row(xs[1], xs[2])) {
+    Tensor y;
+    Tensor z = gemm(xs[0], false, xs[1], false, xs[2].data->rptr(), nullptr, act, &y);
+    attach_to_eager_graph(xs, z, first);
+    std::vector<Tensor> zs{z};
+    attach_to_eager_graph(zs, y, second);
+    return y;
+  }
+  Tensor z = forward(first, std::move(xs));
+  return forward(second, {z});
 }
 
 std::vector<Tensor> backward(const Operators& op, const std::vector<Tensor>& xs, const Tensor& grad) {

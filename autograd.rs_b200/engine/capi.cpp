@@ -125,6 +125,12 @@ int agrs_eng_device_set_fusions(agrs_device* d, int backward_colsum) {
     d->dev.fuse_backward_colsum = backward_colsum != 0;
   });
 }
+int agrs_eng_device_set_forward_fusion(agrs_device* d, int on) {
+  return guarded([&] {
+    need(d, "device");
+    d->dev.fuse_forward_activation = on != 0;
+  });
+}
 int agrs_eng_device_set_conv_implicit(agrs_device* d, int on) {
   return guarded([&] {
     need(d, "device");
@@ -506,6 +512,13 @@ int agrs_eng_op_forward(int op_kind, const int64_t* params, agrs_tensor* const* 
     need(out, "out");
     Operators op = make_op(op_kind, params);
     *out = wrap(forward(op, gather(xs, n_xs)));
+  });
+}
+int agrs_eng_op_forward_pair(int kind_first, const int64_t* params_first, int kind_second, const int64_t* params_second,
+                             agrs_tensor* const* xs, int n_xs, agrs_tensor** out) {
+  return guarded([&] {
+    need(out, "out");
+    *out = wrap(forward_pair(make_op(kind_first, params_first), make_op(kind_second, params_second), gather(xs, n_xs)));
   });
 }
 int agrs_eng_op_backward(int op_kind, const int64_t* params, agrs_tensor* const* xs, int n_xs, const agrs_tensor* grad,

@@ -47,6 +47,7 @@ class Device : public std::enable_shared_from_this<Device> {
   bool matmul_backward_literal = true;
   // Fusions across the Operator boundary; same results bit for bit, so on by default; switchable for A/B tests
   bool fuse_backward_colsum = true;
+  bool fuse_forward_activation = true;  // Linear + ReLU / Sigmoid: the activation written by the GEMM's epilogue (forward_pair)
   // Conv2D with one input channel: implicit-GEMM kernels, no col matrix.  Off = always the literal lowering
   // (im2col + GEMM, col cached as the node's 4th variable, operators.rs:386-388).
   bool conv_implicit = true;

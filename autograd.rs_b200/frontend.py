@@ -60,6 +60,7 @@ def lib():
         "agrs_eng_device_set_matmul_backward_literal": [vp, i32],
         "agrs_eng_device_set_fusions": [vp, i32],
         "agrs_eng_device_set_conv_implicit": [vp, i32],
+        "agrs_eng_device_set_forward_fusion": [vp, i32],
         "agrs_eng_save_parameters": [pvp, i32, C.c_char_p],
         "agrs_eng_load_parameters": [pvp, i32, C.c_char_p],
         "agrs_eng_tensor_from_host": [vp, vp, pi64, i32, pvp],
@@ -106,6 +107,7 @@ def lib():
         "agrs_eng_tensor_accumulate_grad": [vp, vp],
         "agrs_eng_tensor_backward": [vp],
         "agrs_eng_op_forward": [i32, pi64, pvp, i32, pvp],
+        "agrs_eng_op_forward_pair": [i32, pi64, i32, pi64, pvp, i32, pvp],
         "agrs_eng_op_backward": [i32, pi64, pvp, i32, vp, pvp, i32, pi32],
         "agrs_eng_im2col": [vp, i64, i64, i64, pvp],
         "agrs_eng_im2col_backward": [vp, i64, i64, i64, i64, pvp],
@@ -183,6 +185,11 @@ class Device:
     def set_fusions(self, backward_colsum=True):
         """operator-boundary fusions (on by default; bit-identical either way): db left by the backward kernel that produced the gradient"""
         _check(lib().agrs_eng_device_set_fusions(self._h, int(bool(backward_colsum))))
+
+    def set_forward_fusion(self, on=True):
+        """Linear feeding ReLU / Sigmoid as one GEMM call whose epilogue writes the activation next to the pre-activation
+        (default; bit-identical to the two separate forwards)"""
+        _check(lib().agrs_eng_device_set_forward_fusion(self._h, int(bool(on))))
 
     def set_conv_implicit(self, on=True):
         """Conv2D with one input channel: implicit-GEMM kernels without a col matrix (default) or the literal im2col lowering"""
@@ -589,6 +596,14 @@ class Operator:
         xs = list(xs)
         return Tensor._new(xs[0].dev, lib().agrs_eng_op_forward, self.kind, self._params(), _handles(xs), len(xs))
 
+    def forward_then(self, second, xs):
+        """second.forward([self.forward(xs)]) -- two consecutive iterations of Layer::forward_default's loop (layers.rs:24-43):
+        the same two graph nodes and the same bits, as ONE engine call.  Linear followed by ReLU / Sigmoid goes out as a single
+        GEMM whose epilogue writes the activation next to the pre-activation."""
+        xs = list(xs)
+        return Tensor._new(xs[0].dev, lib().agrs_eng_op_forward_pair, self.kind, self._params(), second.kind, second._params(),
+                           _handles(xs), len(xs))
+
     def backward(self, xs, grad):
         xs = list(xs)
         outs = (C.c_void_p * 8)()
@@ -669,8 +684,15 @@ class nn:
         def forward_default(self, xs):
             xs = list(xs)
             res = xs[0].clone()
-            for op in self.get_op_subgraph():
-                res = op.forward(xs)
+            ops = self.get_op_subgraph()
+            i = 0
+            while i < len(ops):
+                if i + 1 < len(ops) and type(ops[i]) is Linear and type(ops[i + 1]) in (ReLU, Sigmoid):
+                    res = ops[i].forward_then(ops[i + 1], xs)  # one GEMM call, two graph nodes
+                    i += 2
+                else:
+                    res = ops[i].forward(xs)
+                    i += 1
                 xs = [res.clone()]
             return res
 
@@ -770,9 +792,18 @@ class nn:
             return self._params
 
         def forward(self, xs):
+            # a Linear layer followed by a ReLU / Sigmoid layer: both operators in one engine call (same graph, same bits; the
+            # activation comes out of the GEMM's epilogue -- Operator.forward_then)
             t = xs[0]
-            for l in self._layers:
-                t = l.forward([t])
+            ls = self._layers
+            i = 0
+            while i < len(ls):
+                if i + 1 < len(ls) and type(ls[i]) is nn.Linear and type(ls[i + 1]) in (nn.ReLU, nn.Sigmoid):
+                    t = Linear().forward_then(ls[i + 1].get_op_subgraph()[0], [t] + ls[i].parameters())
+                    i += 2
+                else:
+                    t = ls[i].forward([t])
+                    i += 1
             return t
 
     class SGD:  # optim.rs:13-35

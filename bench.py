@@ -317,6 +317,11 @@ class Job:
             self.dist = dist
         from autograd_rs_b200 import frontend as F
         self.dev = F.Device(self.local)
+        if getattr(args, "no_forward_fusion", False):
+            self.dev.set_forward_fusion(False)  # A/B: Linear and its activation as two engine calls (same bits)
+        if getattr(args, "act_warps", False):
+            from autograd_rs_b200 import _capi
+            self.dev.set_tuning(_capi.TUNE_TC_ACT_WARPS, 1)  # A/B: the activation written inside the forward GEMM (same bits)
 
     def barrier(self):
         self.dev.sync()
@@ -567,6 +572,9 @@ def time_config(job, name, cfg, steps, warmup, sampler, do_e2e):
            "fused": fused_on,
            "exchange_exposed_ms_per_step": (job.max_over_ranks(exposed[0] / max(exposed[1], 1)) if exposed else None),
            "config": workload_config_for(name, cfg, world, fused_on, args.no_overlap, args.fused_mono)}
+    res["config"]["forward_activation"] = ("own engine call (A/B)" if getattr(args, "no_forward_fusion", False)
+                                           else "inside the forward GEMM, by its activation warps (A/B)" if getattr(args, "act_warps", False)
+                                           else "second pass of the forward GEMM's call (agrs_gemm_bias_act_f32)")
 
     # ---- end to end: host buffers in, loss out, every step ----
     # Every step's X and T come from pinned host memory (268 MB) and its loss goes back to the host.  The copy of step i+1
@@ -732,6 +740,8 @@ def main():
     ap.add_argument("--fused", action="store_true", help="N > 1: one fused reduce-scatter + SGD + all-gather kernel over NVLink peer memory "
                                                          "instead of NCCL all-reduce + SGD (the default)")
     ap.add_argument("--fused-mono", action="store_true", help="N > 1, fused exchange: ONE kernel after backward instead of per-layer exchanges under backward")
+    ap.add_argument("--no-forward-fusion", action="store_true", help="A/B: Linear and the activation behind it as two engine calls instead of one agrs_gemm_bias_act_f32")
+    ap.add_argument("--act-warps", action="store_true", help="A/B: AGRS_TUNE_TC_ACT_WARPS=1, the pair GEMM's activation warps write act(Z) inside the forward GEMM (default: second pass)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL all-reduce per parameter + SGD kernel (the baseline the fused kernel replaces)")
     args = ap.parse_args()
     claim_stdout()

@@ -107,6 +107,21 @@ AGRS_API int agrs_fill_f32(agrs_ctx* ctx, float* x, float value, size_t n);     
 AGRS_API int agrs_gemm_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
                   const float* A, int64_t lda, const float* B, int64_t ldb,
                   float* C, int64_t ldc, const float* bias);
+/* Linear::forward followed by an activation (the Layer loop of src/nn/layers.rs:24-43 feeding operators.rs:140-144 into
+ * :112-116 / :195-200) as ONE call: Z = op(A) op(B) + bias (the pre-activation -- it stays a tensor of its own because the
+ * activation's graph node keeps it as its variable, operators.rs:120-129, :214-224) and Y = act(Z), both [M,N].  Where the GEMM
+ * kernel produces the final value of an element itself it can also write the activation: the SIMT kernel does, from the register
+ * that holds the sum (small models are launch-bound: one launch fewer per layer); the pair kernel does under
+ * AGRS_TUNE_TC_ACT_WARPS = 1 -- once the K chunks of a tile have been folded into Z, two otherwise idle warps fetch the tile back
+ * from L2 and store act(Z) while the tensor cores are on the next tile.  Everywhere else (pair kernel by default, K split over CTA
+ * pairs, one-CTA and skinny kernels, outputs that are not 16-byte aligned) the activation runs as a second
+ * pass inside this call.  Either way Z and Y carry the bits of agrs_gemm_f32 followed by agrs_relu_fwd_f32 / agrs_sigmoid_fwd_f32.
+ * Honours agrs_gemm_operand_absmax (operands) and agrs_next_output_absmax (reports the magnitude of Y). */
+enum agrs_act { AGRS_ACT_NONE = 0, AGRS_ACT_RELU = 1, AGRS_ACT_SIGMOID = 2 };
+AGRS_API int agrs_gemm_bias_act_f32(agrs_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
+                  const float* A, int64_t lda, const float* B, int64_t ldb,
+                  float* Z, int64_t ldz, const float* bias, int act, float* Y, int64_t ldy);
+AGRS_API int agrs_last_gemm_act_fused(agrs_ctx* ctx);     /* 1 when the most recent agrs_gemm_bias_act_f32 wrote Y from the GEMM's epilogue */
 enum agrs_gemm_path { AGRS_GEMM_AUTO = 0, AGRS_GEMM_SIMT = 1, AGRS_GEMM_TCGEN05 = 2, AGRS_GEMM_SKINNY = 3 /* HBM-bound kernels for N <= 32 outputs */ };
 /* Operand magnitudes for the fp16 split mode (AGRS_TUNE_TC_CROSS 4): the bit pattern of the largest finite |x| of A and of B,
  * each ONE device word the caller keeps with its tensor (what CudaData would carry next to `ptr`, storage.rs:5-8).  Applies to the
@@ -144,9 +159,14 @@ enum agrs_tuning_key {
                                    folded across K chunks by TMA reduce-add; 0 = direct vector stores from registers.  Same values either way */
   AGRS_TUNE_TC_REUSE_SCALES = 8,/* cross mode 4, measurement aid: 1 = skip the absmax kernels and reuse the operand magnitudes the previous
                                    launch left in the workspace -- only meaningful when the operands have not changed.  Default 0 */
-  AGRS_TUNE_TC_WAVE_SYNC = 9    /* pair kernel: the TMA producers of a wave of tiles start together so that the CTA pairs keep sharing
+  AGRS_TUNE_TC_WAVE_SYNC = 9,   /* pair kernel: the TMA producers of a wave of tiles start together so that the CTA pairs keep sharing
                                    operand blocks through the L2 (a bounded wait, never a dependency; results do not change).  0 = off,
                                    1 = whenever there is more than one wave, 2 (default) = large problems only (from 8192^3).  Env AGRS_TC_WAVE_SYNC overrides the default at context creation */
+  AGRS_TUNE_TC_ACT_WARPS = 10   /* pair kernel under agrs_gemm_bias_act_f32: 1 = two otherwise idle warps per CTA read each finished tile of Z back from
+                                   L2 and write act(Z) while the tensor cores are on the next tile (no second launch, Z not re-read from HBM);
+                                   0 (default) = the activation runs as a second pass after the kernel.  Same bits either way.  Off by default because
+                                   it does not pay on a power-capped B200: time-neutral on 8 x Linear(8192) + Sigmoid, 1-2 % slower on
+                                   4 x Linear(4096) + ReLU.  Env AGRS_TC_ACT_WARPS overrides the default at context creation */
 };
 AGRS_API int agrs_set_tuning(agrs_ctx* ctx, int key, int64_t value);
 AGRS_API int agrs_get_tuning(agrs_ctx* ctx, int key, int64_t* value);

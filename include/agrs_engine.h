@@ -45,6 +45,10 @@ AGRS_API int agrs_eng_device_set_matmul_backward_literal(agrs_device* dev, int l
  * backward_colsum: ReLU / Sigmoid / MSE backward of a [B, O] tensor also leaves the sum over rows of its result with the buffer,
  * which Linear::backward of the layer below takes as db (operators.rs:161) instead of re-reading the gradient. */
 AGRS_API int agrs_eng_device_set_fusions(agrs_device* dev, int backward_colsum);
+/* forward_activation (on by default, bit-identical either way): a Linear operator feeding ReLU / Sigmoid -- inside one Layer's
+ * subgraph, or through agrs_eng_op_forward_pair -- runs as one agrs_gemm_bias_act_f32 call: the activation is written by the GEMM's
+ * epilogue next to the pre-activation, which stays the activation node's variable (operators.rs:120-129, :214-224). */
+AGRS_API int agrs_eng_device_set_forward_fusion(agrs_device* dev, int on);
 /* Conv2D with one input channel (on by default): implicit-GEMM kernels that never materialise col; the node then keeps its three
  * inputs only.  0 = always the literal lowering of operators.rs:350-449 (im2col + GEMM, col cached as the 4th variable). */
 AGRS_API int agrs_eng_device_set_conv_implicit(agrs_device* dev, int on);
@@ -122,6 +126,11 @@ enum agrs_op_kind {
 /* Operator::forward: computes, then attach_to_eager_graph (operators.rs:27-49) */
 AGRS_API int agrs_eng_op_forward(int op_kind, const int64_t* params, agrs_tensor* const* xs, int n_xs, agrs_tensor** out);
 /* Operator::backward: one gradient per input (MSE: one in total).  xs for Conv2D includes the cached col as xs[3]. */
+/* second.forward(vec![first.forward(xs)]) -- the loop body of Layer::forward_default (layers.rs:24-43) for two consecutive
+ * operators -- with the same two graph nodes and the same bits; Linear + ReLU / Sigmoid go out as one GEMM call (see
+ * agrs_eng_device_set_forward_fusion), every other pair as two calls. */
+AGRS_API int agrs_eng_op_forward_pair(int kind_first, const int64_t* params_first, int kind_second, const int64_t* params_second,
+                                      agrs_tensor* const* xs, int n_xs, agrs_tensor** out);
 AGRS_API int agrs_eng_op_backward(int op_kind, const int64_t* params, agrs_tensor* const* xs, int n_xs, const agrs_tensor* grad,
                                   agrs_tensor** grads_out, int cap, int* n_grads);
 AGRS_API int agrs_eng_im2col(const agrs_tensor* im, int64_t k, int64_t stride, int64_t pad, agrs_tensor** out);          /* operators.rs:324-332 */

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import autograd_rs_b200  # noqa: F401
+from autograd_rs_b200 import _capi as K
 from autograd_rs_b200 import frontend as F
 from autograd_rs_b200 import workloads as W
 from oracle import oracle_np as O
@@ -834,3 +835,58 @@ def test_lenet_implicit_and_literal_conv_train_alike(dev):
             dev.set_conv_implicit(True)
     assert np.allclose(runs[0][0], runs[1][0], rtol=1e-5)
     assert runs[0][1] < runs[1][1]  # fewer kernels per step
+
+
+# ====================================================================== f2: the forward activation out of the GEMM's epilogue
+@pytest.mark.parametrize("act,width,rows,layers,path", [("relu", 256, 512, 3, "tc"), ("sigmoid", 384, 640, 3, "tc"),
+                                                        ("relu", 1536, 384, 2, "tc"), ("sigmoid", 24, 9, 3, "auto")])
+def test_forward_fusion_is_bit_identical_and_keeps_the_graph(dev, act, width, rows, layers, path):
+    """Linear feeding ReLU / Sigmoid as ONE GEMM call (Operator.forward_then / agrs_eng_op_forward_pair; layers.rs:24-43): the same
+    losses and the same weights bit for bit as the two separate forwards over three training iterations, the same two graph nodes
+    (the activation's node keeps the pre-activation, operators.rs:120-129, :214-224), and one launch fewer per activation.
+    Width 1536 runs K in two chunks: Z only exists once the second has been reduce-added, the activation warps wait for that."""
+    ws, bs = W.mlp_init(layers, width, seed=41)
+    x, t = W.mlp_batch(rows, width, width, seed=42)
+    if path == "tc":
+        dev.set_gemm_path(K.GEMM_TCGEN05)
+        dev.set_tuning(K.TUNE_TC_SPLITK, 1)  # few tiles: the planner would split K over CTA pairs, which takes the second-pass form
+        dev.set_tuning(K.TUNE_TC_ACT_WARPS, 1)  # the pair kernel's activation warps are opt-in (DESIGN 4.1)
+    try:
+        runs = {}
+        for fused in (True, False):
+            dev.set_forward_fusion(fused)
+            model = W.build_mlp(dev, ws, bs, act)
+            X = T(dev, x)
+            y = model.forward([X.clone()])
+            assert y.graph_info() == ("Linear", 3, 1)  # the last layer has no activation
+            h = F.nn.Linear(dev, width, width, w=T(dev, ws[0]), bias=T(dev, bs[0]))
+            a = F.Linear().forward_then({"relu": F.ReLU, "sigmoid": F.Sigmoid}[act](), [X.clone()] + h.parameters())
+            assert a.graph_info() == ({"relu": "ReLU", "sigmoid": "Sigmoid"}[act], 1, 1)
+            n0 = dev.launches()
+            model.forward([X.clone()])
+            runs[fused] = (run_device_mlp(dev, x, t, ws, bs, act, 1e-4, 3), dev.launches() - n0, a.data())
+            dev.set_forward_fusion(True)
+        (lf, pf, _), nf, af = runs[True]
+        (lu, pu, _), nu, au = runs[False]
+        assert lf == lu
+        assert all(np.array_equal(p, q) for p, q in zip(pf, pu))
+        assert np.array_equal(af, au)
+        assert nf < nu  # the activation launches are gone (run_device_mlp's launches are counted on both sides)
+    finally:
+        dev.set_forward_fusion(True)
+        dev.set_tuning(K.TUNE_TC_SPLITK, 0)
+        dev.set_tuning(K.TUNE_TC_ACT_WARPS, 0)
+        dev.set_gemm_path(K.GEMM_AUTO)
+    want, _ = O.mlp_train(x, t, ws, bs, act, 1e-4, 3, np.float32)
+    assert max(abs(a - b) / abs(b) for a, b in zip(lf, want)) < TOL
+
+
+def test_forward_pair_of_other_operators_is_two_forwards(dev):
+    """agrs_eng_op_forward_pair on a pair it does not fuse: exactly second.forward([first.forward(xs)])"""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((6, 5)).astype(np.float32)
+    X = T(dev, x)
+    y = F.ReLU().forward_then(F.Sigmoid(), [X.clone()])
+    assert y.graph_info() == ("Sigmoid", 1, 1)
+    want = O.sigmoid_fwd(O.relu_fwd(x))
+    assert np.allclose(y.data(), want, rtol=4e-7)
