@@ -955,31 +955,51 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int total = rows * vpr;
       const float* const z_tile = C + r0 * ldc + c0;
       float* const y_tile = act.y + r0 * act.ldy + c0;
+      auto activate = [&](const float4 x) {
+        float4 y;
+        if (act.kind == AGRS_ACT_RELU) y = make_float4(agrs_act_relu(x.x), agrs_act_relu(x.y), agrs_act_relu(x.z), agrs_act_relu(x.w));
+        else y = make_float4(agrs_act_sigmoid(x.x), agrs_act_sigmoid(x.y), agrs_act_sigmoid(x.z), agrs_act_sigmoid(x.w));
+        y_mag = mag4(y_mag, y);
+        return y;
+      };
+      if (vpr == BN / 4) {
+        // a whole-width tile (all but the last column block): a batch is 8 rows, a lane owns vectors `lane` and `lane + 32` of each
+        // row -- every address is the batch's base plus a constant, no index arithmetic per vector (these two warps share their
+        // sub-partitions' issue slots with four splitter warps: a first version with a division per vector slowed THOSE down)
 #pragma unroll 1
-      for (int base = 0; base < total; base += kBatch * 32) {
-        float4 x[kBatch];
+        for (int rb = 0; rb < rows; rb += kBatch / 2) {
+          const float* zr = z_tile + int64_t(rb) * ldc + lane * 4;
+          float* yr = y_tile + int64_t(rb) * act.ldy + lane * 4;
+          float4 x[kBatch];
 #pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-          const int e = base + i * 32 + lane;
-          if (e < total) {
-            const int r = vpr == BN / 4 ? e >> 6 : e / vpr, v = e - r * vpr;
-            x[i] = __ldcg(reinterpret_cast<const float4*>(z_tile + r * ldc) + v);  // from L2, never through this SM's L1
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-          const int e = base + i * 32 + lane;
-          if (e < total) {
-            const int r = vpr == BN / 4 ? e >> 6 : e / vpr, v = e - r * vpr;
-            float4 y;
-            if (act.kind == AGRS_ACT_RELU) {
-              y = make_float4(agrs_act_relu(x[i].x), agrs_act_relu(x[i].y), agrs_act_relu(x[i].z), agrs_act_relu(x[i].w));
-            } else {
-              y = make_float4(agrs_act_sigmoid(x[i].x), agrs_act_sigmoid(x[i].y), agrs_act_sigmoid(x[i].z), agrs_act_sigmoid(x[i].w));
+          for (int i = 0; i < kBatch; i += 2, zr += ldc)
+            if (rb + (i >> 1) < rows) {  // from L2, never through this SM's L1
+              x[i] = __ldcg(reinterpret_cast<const float4*>(zr));
+              x[i + 1] = __ldcg(reinterpret_cast<const float4*>(zr + 128));
             }
-            y_mag = mag4(y_mag, y);
-            *(reinterpret_cast<float4*>(y_tile + r * act.ldy) + v) = y;
+#pragma unroll
+          for (int i = 0; i < kBatch; i += 2, yr += act.ldy)
+            if (rb + (i >> 1) < rows) {
+              *reinterpret_cast<float4*>(yr) = activate(x[i]);
+              *reinterpret_cast<float4*>(yr + 128) = activate(x[i + 1]);
+            }
+        }
+      } else {  // the clipped last column block: generic indexing, four vectors in flight
+        constexpr int kEdgeBatch = 4;
+#pragma unroll 1
+        for (int base = 0; base < total; base += kEdgeBatch * 32) {
+          float4 x[kEdgeBatch];
+          int r[kEdgeBatch], v[kEdgeBatch];
+#pragma unroll
+          for (int i = 0; i < kEdgeBatch; ++i) {
+            const int e = base + i * 32 + lane;
+            r[i] = e / vpr;
+            v[i] = e - r[i] * vpr;
+            if (e < total) x[i] = __ldcg(reinterpret_cast<const float4*>(z_tile + r[i] * ldc) + v[i]);
           }
+#pragma unroll
+          for (int i = 0; i < kEdgeBatch; ++i)
+            if (base + i * 32 + lane < total) *(reinterpret_cast<float4*>(y_tile + r[i] * act.ldy) + v[i]) = activate(x[i]);
         }
       }
       __syncwarp();
