@@ -34,6 +34,7 @@ struct agrs_ctx {
   int tc_epi_tma = 1;      // pair kernel epilogue: 1 staged in shared memory + TMA store / reduce-add, 0 direct st.global from registers
   int tc_wave_sync = 2;    // pair kernel: the TMA producers of a wave start their tiles together (0 off, 1 always, 2 large problems; AGRS_TC_WAVE_SYNC)
   int tc_act_warps = 0;    // pair kernel, agrs_gemm_bias_act_f32: 1 = the activation warps write act(C) inside the GEMM (AGRS_TUNE_TC_ACT_WARPS), 0 = second pass
+  int tc_l2_hint = 0;      // pair kernel: L2 eviction policies on the operand loads (env AGRS_TC_L2_HINT; see launch() in gemm_tcgen05_2cta.cu)
   int tc_reuse_scales = 0; // cross mode 4, measurement aid: 1 = reuse the operand magnitudes of the previous launch (same operands only)
   // operand magnitudes for the next GEMM call (agrs_gemm_operand_absmax) and the slot the next elementwise launch reports into
   // (agrs_next_output_absmax); both are consumed by the call they apply to

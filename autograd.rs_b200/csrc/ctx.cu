@@ -43,9 +43,17 @@ static int ctx_init(int device, cudaStream_t stream, bool own, agrs_ctx** out) {
     const int v = atoi(e);
     if (v >= 0 && v <= 5) ctx->tc_cross = v;
   }
+  if (const char* e = getenv("AGRS_TC_L2_HINT")) ctx->tc_l2_hint = atoi(e);
   if (const char* e = getenv("AGRS_TC_ACT_WARPS")) ctx->tc_act_warps = atoi(e) ? 1 : 0;  // default of AGRS_TUNE_TC_ACT_WARPS
   if (const char* e = getenv("AGRS_TC_EPI_TMA")) ctx->tc_epi_tma = atoi(e) ? 1 : 0;  // default of AGRS_TUNE_TC_EPI_TMA
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }
+  if (const char* e = getenv("AGRS_L2_PERSIST_MB")) {
+    // evict_last lines only persist inside the L2's persisting carve-out, which is empty by default (experiment of AGRS_TC_L2_HINT)
+    size_t want = size_t(atoi(e)) << 20;
+    if (want > size_t(prop.persistingL2CacheMaxSize)) want = size_t(prop.persistingL2CacheMaxSize);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) (void)cudaGetLastError();
+    fprintf(stderr, "agrs: persisting L2 carve-out %zu MB of at most %d MB (L2 %d MB)\n", want >> 20, prop.persistingL2CacheMaxSize >> 20, prop.l2CacheSize >> 20);
+  }
   if (own) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGRS_ERR_CUDA; }
     ctx->owns_stream = true;

@@ -480,7 +480,7 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const __grid_constant__ ScatterArgs sc, const __grid_constant__ CUtensorMap tmap_c,
                    const __grid_constant__ CUtensorMap tmap_w, int epi_tma, const uint32_t* __restrict__ a_max,
                    const uint32_t* __restrict__ b_max, int mx_scalar, unsigned int* wave_sync, int64_t split_from,
-                   const ActArgs act) {
+                   const ActArgs act, uint32_t l2_hint) {
   static_assert(!(ACT && SCATTER), "the activation epilogue is the staged one; the scattering epilogue stores from registers");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -573,6 +573,9 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int r = 0;
       uint32_t rph = 0;
       unsigned long long started = 0;  // work items started by all pairs once every pair has begun its (wave+1)-th item
+      // L2 eviction policies of the operand loads (launch(): AGRS_TC_L2_HINT): bit 0 = B evict_last, bit 1 = A evict_first
+      const uint64_t pol_b = l2_policy_evict_last(), pol_a = l2_policy_evict_first();
+      const bool hint_b = (l2_hint & 1u) != 0, hint_a = (l2_hint & 2u) != 0;
       for (int64_t t = pair; t < num_tiles; t += num_pairs) {
         const Work w = work_item(t);
         const int32_t m0 = int32_t(w.mb * 2 * BM + rank * BM), n0 = int32_t(w.nb * BN + rank * BNH);
@@ -598,15 +601,23 @@ k_gemm_3xtf32_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const int32_t k0 = kb * BK;
           if (A_MN) {  // A stored [K, M]: boxes of 32 (M, contiguous) x 32 (K rows)
 #pragma unroll
-            for (int g = 0; g < BM / 32; ++g) tma_load_2d(&tmap_a, raw_full(r), a_dst + g * 4096, m0 + g * 32, k0);
+            for (int g = 0; g < BM / 32; ++g) {
+              if (hint_a) tma_load_2d_hint(&tmap_a, raw_full(r), a_dst + g * 4096, m0 + g * 32, k0, pol_a);
+              else        tma_load_2d(&tmap_a, raw_full(r), a_dst + g * 4096, m0 + g * 32, k0);
+            }
           } else {     // A stored [M, K]: one box of 32 (K, contiguous) x 128 rows
-            tma_load_2d(&tmap_a, raw_full(r), a_dst, k0, m0);
+            if (hint_a) tma_load_2d_hint(&tmap_a, raw_full(r), a_dst, k0, m0, pol_a);
+            else        tma_load_2d(&tmap_a, raw_full(r), a_dst, k0, m0);
           }
           if (B_MN) {  // B stored [K, N]
 #pragma unroll
-            for (int g = 0; g < BNH / 32; ++g) tma_load_2d(&tmap_b, raw_full(r), b_dst + g * 4096, n0 + g * 32, k0);
+            for (int g = 0; g < BNH / 32; ++g) {
+              if (hint_b) tma_load_2d_hint(&tmap_b, raw_full(r), b_dst + g * 4096, n0 + g * 32, k0, pol_b);
+              else        tma_load_2d(&tmap_b, raw_full(r), b_dst + g * 4096, n0 + g * 32, k0);
+            }
           } else {     // B stored [N, K]
-            tma_load_2d(&tmap_b, raw_full(r), b_dst, k0, n0);
+            if (hint_b) tma_load_2d_hint(&tmap_b, raw_full(r), b_dst, k0, n0, pol_b);
+            else        tma_load_2d(&tmap_b, raw_full(r), b_dst, k0, n0);
           }
           if (++r == R) { r = 0; rph ^= 1u; }
         }
@@ -1202,7 +1213,19 @@ static int launch(agrs_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, f
     k_zero_u32<<<1, 1, 0, ctx->stream>>>(wave_sync);
     AGRS_LAUNCHED(ctx);
   }
-  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0, wave_sync, split_from, act);
+  // L2 eviction policies of the operand loads.  The raster walks 8 row-blocks of tiles per column sweep, so op(B) is read once per
+  // group of 8 row-blocks: when it is small enough to stay in the L2 next to the streams (and there is more than one group), its
+  // loads ask to be evicted last.  AGRS_TC_L2_HINT: 0 off, 1 that rule, 2 / 3 / 4 force (B last / B last + A first / A first).
+  uint32_t l2_hint = 0;
+  {
+    const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM);
+    const double b_bytes = double(N) * double(K) * 4.0;
+    if (ctx->tc_l2_hint == 1) l2_hint = (m_tiles > 8 && b_bytes >= double(8 << 20) && b_bytes <= double(80 << 20)) ? 1u : 0u;
+    else if (ctx->tc_l2_hint == 2) l2_hint = 1u;
+    else if (ctx->tc_l2_hint == 3) l2_hint = 3u;
+    else if (ctx->tc_l2_hint == 4) l2_hint = 2u;
+  }
+  kern<<<grid, kThreads, SMEM_BYTES, ctx->stream>>>(ta, tb, C, ldc, bias, M, N, K, kb_per_chunk, splits, Cw, sc, tc_map, tw_map, epi_tma, a_max, b_max, ext_mx ? 1 : 0, wave_sync, split_from, act, l2_hint);
   AGRS_LAUNCHED(ctx);
   if (splits > 1 && split_from > 0) {  // only the tiles of the last wave were split
     const int64_t m_tiles = (M + 2 * BM - 1) / (2 * BM), n_tiles = (N + BN - 1) / BN;
