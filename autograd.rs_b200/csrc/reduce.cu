@@ -13,10 +13,24 @@ constexpr int kThreads = 256;
 // The fused sources write the elementwise result AND feed it to the column sum in the same pass: the gradient that ReLU /
 // Sigmoid / MSE backward hand to the Linear layer below is exactly the tensor whose sum over rows that layer needs for db
 // (operators.rs:161), so the separate pass that re-read it disappears.  Same arithmetic as the functors of elementwise.cu.
+// Every source splits a 16-byte access into ld4 (the loads) and fin4 (arithmetic + the store of a writing source).  Written as one
+// function per row, the store of row l stands between the loads of rows l and l + 8 (the pointers may alias as far as the compiler
+// knows): one row in flight per thread.  Behind ReLU's two instructions and Sigmoid's expf that costs nothing measurable, and issuing
+// the loads of all four rows first costs THEM 10 us of an [8192, 4096] tensor's 70 - 78; behind MSE's four IEEE divisions per vector it
+// was 110 us instead of 82 (tools/gpu_r3_i.sh, gpu_r3_j.sh): kLoadsFirst chooses per source.  MSE's upstream scalar is read once per
+// thread (prep) instead of after every store.
+struct Raw2 {
+  float4 a, b;
+};
+struct NoPre {};
 struct SrcPlain {
   const float* x;
   static constexpr bool kWrites = false;
-  __device__ float4 at4(int64_t e) const { return __ldcs(reinterpret_cast<const float4*>(x + e)); }
+  static constexpr bool kLoadsFirst = false;
+  using Raw = float4;
+  __device__ NoPre prep() const { return NoPre{}; }
+  __device__ Raw ld4(int64_t e) const { return __ldcs(reinterpret_cast<const float4*>(x + e)); }
+  __device__ float4 fin4(int64_t, const Raw& r, NoPre) const { return r; }
   __device__ float at1(int64_t e) const { return __ldcs(x + e); }
 };
 struct SrcReluBwd {  // functional_ndarray.rs:23-34: x <= 0 ? 0 : g
@@ -24,8 +38,12 @@ struct SrcReluBwd {  // functional_ndarray.rs:23-34: x <= 0 ? 0 : g
   const float* g;
   float* out;
   static constexpr bool kWrites = true;
-  __device__ float4 at4(int64_t e) const {
-    const float4 a = __ldcs(reinterpret_cast<const float4*>(x + e)), b = __ldcs(reinterpret_cast<const float4*>(g + e));
+  static constexpr bool kLoadsFirst = false;
+  using Raw = Raw2;
+  __device__ NoPre prep() const { return NoPre{}; }
+  __device__ Raw ld4(int64_t e) const { return Raw{__ldcs(reinterpret_cast<const float4*>(x + e)), __ldcs(reinterpret_cast<const float4*>(g + e))}; }
+  __device__ float4 fin4(int64_t e, const Raw& v, NoPre) const {
+    const float4 a = v.a, b = v.b;
     const float4 r = make_float4(a.x <= 0.f ? 0.f : b.x, a.y <= 0.f ? 0.f : b.y, a.z <= 0.f ? 0.f : b.z, a.w <= 0.f ? 0.f : b.w);
     __stcs(reinterpret_cast<float4*>(out + e), r);
     return r;
@@ -37,12 +55,16 @@ struct SrcSigmoidBwd {  // operators.rs:219-223: ((1 - s) * s) * g, s recomputed
   const float* g;
   float* out;
   static constexpr bool kWrites = true;
+  static constexpr bool kLoadsFirst = false;
+  using Raw = Raw2;
   __device__ static float f(float x, float g) {
     const float s = 1.0f / (1.0f + expf(-x));
     return ((1.0f - s) * s) * g;
   }
-  __device__ float4 at4(int64_t e) const {
-    const float4 a = __ldcs(reinterpret_cast<const float4*>(x + e)), b = __ldcs(reinterpret_cast<const float4*>(g + e));
+  __device__ NoPre prep() const { return NoPre{}; }
+  __device__ Raw ld4(int64_t e) const { return Raw{__ldcs(reinterpret_cast<const float4*>(x + e)), __ldcs(reinterpret_cast<const float4*>(g + e))}; }
+  __device__ float4 fin4(int64_t e, const Raw& v, NoPre) const {
+    const float4 a = v.a, b = v.b;
     const float4 r = make_float4(f(a.x, b.x), f(a.y, b.y), f(a.z, b.z), f(a.w, b.w));
     __stcs(reinterpret_cast<float4*>(out + e), r);
     return r;
@@ -55,11 +77,18 @@ struct SrcMseBwd {  // operators.rs:249-253: ((p - t) * 2.0 / B) * grad
   const float* up;
   float batch;
   float* out;
+  float inv_batch;  // 1 / batch when batch is a power of two (dividing by it and multiplying by this then round identically), else 0
   static constexpr bool kWrites = true;
-  __device__ float f(float a, float b, float u) const { return (((a - b) * 2.0f) / batch) * u; }
-  __device__ float4 at4(int64_t e) const {
-    const float u = __ldg(up);
-    const float4 a = __ldcs(reinterpret_cast<const float4*>(p + e)), b = __ldcs(reinterpret_cast<const float4*>(t + e));
+  static constexpr bool kLoadsFirst = true;  // see above: the divisions sit between a row's loads and its store
+  using Raw = Raw2;
+  __device__ float f(float a, float b, float u) const {
+    const float d2 = (a - b) * 2.0f;
+    return (inv_batch != 0.f ? d2 * inv_batch : d2 / batch) * u;
+  }
+  __device__ float prep() const { return __ldg(up); }  // the upstream [1, 1] gradient: read once per thread
+  __device__ Raw ld4(int64_t e) const { return Raw{__ldcs(reinterpret_cast<const float4*>(p + e)), __ldcs(reinterpret_cast<const float4*>(t + e))}; }
+  __device__ float4 fin4(int64_t e, const Raw& v, float u) const {
+    const float4 a = v.a, b = v.b;
     const float4 r = make_float4(f(a.x, b.x, u), f(a.y, b.y, u), f(a.z, b.z, u), f(a.w, b.w, u));
     __stcs(reinterpret_cast<float4*>(out + e), r);
     return r;
@@ -178,15 +207,27 @@ __global__ void __launch_bounds__(256) k_sum_axis_mid(const S src, int64_t len, 
 #pragma unroll
   for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
   uint32_t m = 0;  // magnitude of what a writing source produces (agrs_next_output_absmax), when asked for
+  const auto pre = src.prep();
+  auto at4 = [&](int64_t e) { return src.fin4(e, src.ld4(e), pre); };
   if (col < inner) {
     const int64_t base = o * len * inner + col;
     int64_t l = l0 + ty;
     if (VEC == 4) {  // four independent 16-byte loads in flight per thread (rows l, l+8, l+16, l+24)
       for (; l + 24 < l1; l += 32) {
-        float4 v0 = src.at4(base + l * inner);
-        float4 v1 = src.at4(base + (l + 8) * inner);
-        float4 v2 = src.at4(base + (l + 16) * inner);
-        float4 v3 = src.at4(base + (l + 24) * inner);
+        float4 v0, v1, v2, v3;
+        if constexpr (S::kLoadsFirst) {
+          const int64_t e0 = base + l * inner, e1 = base + (l + 8) * inner, e2 = base + (l + 16) * inner, e3 = base + (l + 24) * inner;
+          const typename S::Raw r0 = src.ld4(e0), r1 = src.ld4(e1), r2 = src.ld4(e2), r3 = src.ld4(e3);
+          v0 = src.fin4(e0, r0, pre);
+          v1 = src.fin4(e1, r1, pre);
+          v2 = src.fin4(e2, r2, pre);
+          v3 = src.fin4(e3, r3, pre);
+        } else {
+          v0 = at4(base + l * inner);
+          v1 = at4(base + (l + 8) * inner);
+          v2 = at4(base + (l + 16) * inner);
+          v3 = at4(base + (l + 24) * inner);
+        }
         acc[0] += v0.x; acc[1 % VEC] += v0.y; acc[2 % VEC] += v0.z; acc[3 % VEC] += v0.w;
         acc[0] += v1.x; acc[1 % VEC] += v1.y; acc[2 % VEC] += v1.z; acc[3 % VEC] += v1.w;
         acc[0] += v2.x; acc[1 % VEC] += v2.y; acc[2 % VEC] += v2.z; acc[3 % VEC] += v2.w;
@@ -196,7 +237,7 @@ __global__ void __launch_bounds__(256) k_sum_axis_mid(const S src, int64_t len, 
     }
     for (; l < l1; l += 8) {
       if (VEC == 4) {
-        float4 v = src.at4(base + l * inner);
+        float4 v = at4(base + l * inner);
         acc[0] += v.x;
         acc[1 % VEC] += v.y;
         acc[2 % VEC] += v.z;
@@ -462,7 +503,11 @@ int agrs_mse_bwd_colsum_f32(agrs_ctx* ctx, const float* pred, const float* targe
   AGRS_CHECK_CTX(ctx);
   AGRS_RANGE("agrs_mse_bwd_colsum_f32");
   AGRS_REQUIRE(ctx, upstream1, AGRS_ERR_INVALID, "agrs_mse_bwd_colsum_f32: null upstream");
-  return fused_bwd_colsum(ctx, SrcMseBwd{pred, target, upstream1, batch, out}, "agrs_mse_bwd_colsum_f32", rows, cols, pred, target, out, colsum);
+  // batch = 2^k (8192 rows per GPU in C2 / C5): x / 2^k and x * 2^-k are the same single rounding of the same value, subnormal
+  // results included, and the multiplication spares four IEEE divisions per 16-byte vector
+  int ex = 0;
+  const float inv_batch = (batch > 0.f && frexpf(batch, &ex) == 0.5f && ex > -100 && ex < 100) ? 1.0f / batch : 0.f;
+  return fused_bwd_colsum(ctx, SrcMseBwd{pred, target, upstream1, batch, out, inv_batch}, "agrs_mse_bwd_colsum_f32", rows, cols, pred, target, out, colsum);
 }
 
 int agrs_equal_f32(agrs_ctx* ctx, const float* a, const float* b, size_t n, int* host_equal) {

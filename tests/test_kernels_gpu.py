@@ -773,6 +773,29 @@ def test_backward_colsum_fusions_bit_identical(ctx, rows, cols):
         assert _read_u32(ctx, slot) == _bits_of_max(a), name
 
 
+def test_mse_backward_power_of_two_batch_rounds_like_the_division(ctx):
+    """With a power-of-two batch the fused kernel multiplies by 1 / batch instead of dividing (reduce.cu): the same single rounding,
+    also where the result is subnormal or the intermediate overflows -- checked bit for bit against the dividing elementwise kernel
+    and against NumPy's f32 division (operators.rs:249-253: ((p - t) * 2.0 / B) * grad)."""
+    rows, cols = 256, 64
+    n = rows * cols
+    rng = np.random.default_rng(77)
+    scale = np.float32(10.0) ** rng.integers(-44, 38, n).astype(np.float32)       # from deep subnormal results to overflow of (p - t) * 2
+    p = (rng.standard_normal(n).astype(np.float32) * scale).astype(np.float32)
+    t = (rng.standard_normal(n).astype(np.float32) * scale * np.float32(0.5)).astype(np.float32)
+    up = np.array([1.0], np.float32)
+    dp, dt, dup = ctx.to_device(p), ctx.to_device(t), ctx.to_device(up)
+    o1, o2, c2 = ctx.empty(n), ctx.empty(n), ctx.empty(cols)
+    ctx.call("agrs_mse_bwd_f32", dp.ptr, dt.ptr, dup.ptr, float(rows), n, o1.ptr)
+    ctx.call("agrs_mse_bwd_colsum_f32", dp.ptr, dt.ptr, dup.ptr, float(rows), rows, cols, o2.ptr, c2.ptr)
+    a, b = ctx.to_host(o1, (n,)), ctx.to_host(o2, (n,))
+    with np.errstate(over="ignore", invalid="ignore"):
+        want = (((p - t) * np.float32(2.0)) / np.float32(rows)) * up[0]
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.array_equal(b.view(np.uint32), want.astype(np.float32).view(np.uint32))
+    assert np.count_nonzero((np.abs(want) < np.float32(1.1754944e-38)) & (want != 0)) > 100   # the subnormal range is exercised
+
+
 def test_backward_colsum_refuses_unaligned(ctx):
     d = ctx.empty(64 * 6)
     with pytest.raises(K.AgrsError) as e:

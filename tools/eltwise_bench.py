@@ -62,6 +62,10 @@ def main():
     timed("bias_add_rowvec", 8 * n, lambda i: ctx.call("agrs_binary_f32", _capi.ADD, A[i].ptr, A[i].ptr, small.ptr, n, 4096, 0))
     timed("sgd_step", 12 * n, lambda i: ctx.call("agrs_sgd_step_f32", A[i].ptr, B[i].ptr, 1e-6, n, n))
     timed("colsum (db, [8192,4096] -> [4096])", 4 * n, lambda i: ctx.call("agrs_sum_axis_f32", A[i].ptr, 1, 8192, 4096, small.ptr))
+    # the fused backward + column-sum kernels of the training step (f2): same bytes as the plain backward, db for free
+    timed("relu_bwd + colsum", 12 * n, lambda i: ctx.call("agrs_relu_bwd_colsum_f32", A[i].ptr, B[i].ptr, Cc[i].ptr, 8192, 4096, small.ptr))
+    timed("sigmoid_bwd + colsum", 12 * n, lambda i: ctx.call("agrs_sigmoid_bwd_colsum_f32", A[i].ptr, B[i].ptr, Cc[i].ptr, 8192, 4096, small.ptr))
+    timed("mse_bwd + colsum", 12 * n, lambda i: ctx.call("agrs_mse_bwd_colsum_f32", A[i].ptr, B[i].ptr, scal.ptr, 8192.0, 8192, 4096, Cc[i].ptr, small.ptr))
     timed("sum", 4 * n, lambda i: ctx.call("agrs_sum_f32", A[i].ptr, n, scal.ptr))
     timed("fill_zero (memset)", 4 * n, lambda i: ctx.call("agrs_fill_f32", Cc[i].ptr, 0.0, n))
     timed("fill_one", 4 * n, lambda i: ctx.call("agrs_fill_f32", Cc[i].ptr, 1.0, n))
