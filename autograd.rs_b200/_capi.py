@@ -134,6 +134,7 @@ def lib():
             "agrs_col2im_f32": [vp, vp, i64, i64, i64, i64, i64, i64, vp],
             "agrs_broadcast_filter_f32": [vp, vp, i64, i64, i64, vp],
             "agrs_conv2d_fwd_f32": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp],
+            "agrs_conv2d_fwd_act_f32": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp, i32, vp],
             "agrs_conv2d_bwd_f32": [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, vp, vp, vp],
         }
         for name, args in sig.items():

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 
 #include "agrs_internal.h"
+#include "act.cuh"
+#include "mag.cuh"
 
 namespace {
 
@@ -284,11 +286,48 @@ __device__ __forceinline__ float dot8(const F8& a, const F8& b) {  // sum over C
   return t;
 }
 
+// The forward kernels stage a group's output [p][co] in shared memory and stream it out; with an activation requested
+// (agrs_conv2d_fwd_act_f32: Conv2D feeding ReLU / Sigmoid) the same stream also writes y = act(out) -- the
+// pre-activation stays a tensor of its own, the activation's graph node keeps it -- and tracks the magnitude of y.
+struct ConvAct {
+  int kind;      // AGRS_ACT_NONE: plain forward
+  float* y;      // same layout as out
+  uint32_t* mx;  // magnitude word of y, or null
+};
+__device__ __forceinline__ float conv_act1(int kind, float v) { return kind == AGRS_ACT_RELU ? agrs_act_relu(v) : agrs_act_sigmoid(v); }
+__device__ __forceinline__ void conv_stream_out(const float* stage, float* dst, int64_t off, int n, const ConvAct& act, uint32_t& mag, int tid, int nthreads) {
+  float* const d = dst + off;
+  float* const y = act.kind ? act.y + off : nullptr;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) && (!y || (reinterpret_cast<uintptr_t>(y) & 15u) == 0)) {
+    for (int e = tid; e < n >> 2; e += nthreads) {
+      const float4 v = reinterpret_cast<const float4*>(stage)[e];
+      __stcs(reinterpret_cast<float4*>(d) + e, v);
+      if (y) {
+        const float4 r = make_float4(conv_act1(act.kind, v.x), conv_act1(act.kind, v.y), conv_act1(act.kind, v.z), conv_act1(act.kind, v.w));
+        __stcs(reinterpret_cast<float4*>(y) + e, r);
+        mag = mag4(mag, r);
+      }
+    }
+  } else {
+    for (int e = tid; e < n; e += nthreads) {
+      const float v = stage[e];
+      d[e] = v;
+      if (y) {
+        const float r = conv_act1(act.kind, v);
+        y[e] = r;
+        mag = max(mag, mag_bits(r));
+      }
+    }
+  }
+}
+
 // forward: thread per output position, the CTA's results staged in shared memory and written as one coalesced stream
 __global__ void __launch_bounds__(256) k_conv1_fwd(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ bias,
-                                                   int B, int H, int W, int k, int co, int s, int pad, int Ho, int Wo, float* __restrict__ out) {
+                                                   int B, int H, int W, int k, int co, int s, int pad, int Ho, int Wo, float* __restrict__ out,
+                                                   const ConvAct act) {
   extern __shared__ __align__(16) float sm[];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, kk = k * k, P = Ho * Wo;
+  uint32_t y_mag = 0;
   float* fl = sm;                          // [kk][8], zero padded
   float* bs = fl + kk * 8;                 // [8]
   float* img = bs + 8;                     // [Hp][Wp], zero border
@@ -327,14 +366,10 @@ __global__ void __launch_bounds__(256) k_conv1_fwd(const float* __restrict__ im,
         if (o < co) stage[p * co + o] = acc[o] + bs[o];
     }
     __syncthreads();
-    float* dst = out + int64_t(b) * P * co;  // NHWC (operators.rs:383): [P][co] contiguous per sample
-    const int n = P * co;
-    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-      for (int e = threadIdx.x; e < n / 4; e += blockDim.x) __stcs(reinterpret_cast<float4*>(dst) + e, reinterpret_cast<const float4*>(stage)[e]);
-    } else {
-      for (int e = threadIdx.x; e < n; e += blockDim.x) dst[e] = stage[e];
-    }
+    // NHWC (operators.rs:383): [P][co] contiguous per sample
+    conv_stream_out(stage, out, int64_t(b) * P * co, P * co, act, y_mag, threadIdx.x, blockDim.x);
   }
+  if (act.kind && act.mx) mag_commit(y_mag, act.mx);
 }
 
 // backward of the same layer: dx (padded size, per sample), and this CTA's partial sums of dw [kk][co] and db [co]; the last CTA
@@ -723,9 +758,10 @@ __host__ __device__ inline size_t cf_smem(int H, int W, int K, int co) {
 }
 template <int K>
 __global__ void __launch_bounds__(kCfThreads) k_conv1_fwd_tiled(const float* __restrict__ im, const float* __restrict__ filt, const float* __restrict__ bias,
-                                                                int B, int H, int W, int co, float* __restrict__ out) {
+                                                                int B, int H, int W, int co, float* __restrict__ out, const ConvAct act) {
   extern __shared__ __align__(16) float sm[];
   constexpr int KK = K * K;
+  uint32_t y_mag = 0;
   const int Ho = H - K + 1, Wo = W - K + 1, P = Ho * Wo, strips_x = (Wo + 3) >> 2, strips = Ho * strips_x;
   float* fl = sm;                                   // [KK + 1][8]: taps, then the bias row
   float* raw = fl + (KK + 1) * 8;                   // [S][H][W] as in global memory (+ 8 floats a window may look past the end)
@@ -789,15 +825,11 @@ __global__ void __launch_bounds__(kCfThreads) k_conv1_fwd_tiled(const float* __r
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();  // results staged; everybody is done reading the landing buffer
     if (tid == 0 && grp + int(gridDim.x) < groups) fetch(grp + gridDim.x);
-    float* dst = out + int64_t(b0) * P * co;  // the group's samples are contiguous in NHWC
-    const int n = ns * P * co;
-    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-      for (int e = tid; e < n >> 2; e += kCfThreads) __stcs(reinterpret_cast<float4*>(dst) + e, reinterpret_cast<const float4*>(stage)[e]);
-    } else {
-      for (int e = tid; e < n; e += kCfThreads) dst[e] = stage[e];
-    }
+    // the group's samples are contiguous in NHWC
+    conv_stream_out(stage, out, int64_t(b0) * P * co, ns * P * co, act, y_mag, tid, kCfThreads);
     __syncthreads();  // the staging area is free for the next group
   }
+  if (act.kind && act.mx) mag_commit(y_mag, act.mx);
 }
 
 static bool conv1_fwd_tiled_ok(int64_t B, int64_t H, int64_t W, int64_t k, int64_t co, int64_t stride, int64_t pad, const float* im) {
@@ -931,25 +963,46 @@ int agrs_conv2d_implicit_ok(int64_t B, int64_t C, int64_t H, int64_t W, int64_t 
   return C == 1 && conv1_shape_ok(B, H, W, k, c_out, stride, pad, &a, &b) ? 1 : 0;
 }
 
+static int conv2d_fwd(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W, int64_t k,
+                      int64_t c_out, int64_t stride, int64_t pad, float* out, int act_kind, float* y);
+
 int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W, int64_t k,
                         int64_t c_out, int64_t stride, int64_t pad, float* out) {
   AGRS_CHECK_CTX(ctx);
   AGRS_RANGE("agrs_conv2d_fwd_f32");
+  return conv2d_fwd(ctx, im, filt, bias, B, H, W, k, c_out, stride, pad, out, AGRS_ACT_NONE, nullptr);
+}
+
+int agrs_conv2d_fwd_act_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W, int64_t k,
+                            int64_t c_out, int64_t stride, int64_t pad, float* out, int act, float* y) {
+  AGRS_CHECK_CTX(ctx);
+  AGRS_RANGE("agrs_conv2d_fwd_act_f32");
+  AGRS_REQUIRE(ctx, act == AGRS_ACT_RELU || act == AGRS_ACT_SIGMOID, AGRS_ERR_INVALID, "agrs_conv2d_fwd_act_f32: unknown activation %d", act);
+  AGRS_REQUIRE(ctx, y && y != out, AGRS_ERR_INVALID, "agrs_conv2d_fwd_act_f32: null y, or y aliases out (the pre-activation stays a tensor of its own)");
+  return conv2d_fwd(ctx, im, filt, bias, B, H, W, k, c_out, stride, pad, out, act, y);
+}
+
+static int conv2d_fwd(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W, int64_t k,
+                      int64_t c_out, int64_t stride, int64_t pad, float* out, int act_kind, float* y) {
   size_t smem = 0, smem_b = 0;
   AGRS_REQUIRE(ctx, conv1_shape_ok(B, H, W, k, c_out, stride, pad, &smem, &smem_b), AGRS_ERR_UNSUPPORTED,
                "agrs_conv2d_fwd_f32: shape outside the implicit-GEMM kernels (single input channel, C_out <= %d, k*k*C_out + C_out <= 256): use im2col + GEMM", kConvCo);
   AGRS_REQUIRE(ctx, im && filt && bias && out, AGRS_ERR_INVALID, "agrs_conv2d_fwd_f32: null pointer");
   const int Ho = int((H - k + 2 * pad) / stride + 1), Wo = int((W - k + 2 * pad) / stride + 1);
+  ConvAct act{act_kind, y, nullptr};
+  if (act_kind) {
+    if (int rc = agrs_take_mx(ctx, &act.mx)) return rc;  // agrs_next_output_absmax reports on y
+  }
   if (ctx->conv_tiled && conv1_fwd_tiled_ok(B, H, W, k, c_out, stride, pad, im)) {
     const size_t tsmem = cf_smem(int(H), int(W), int(k), int(c_out));
     const int64_t groups = (B + kCfSamples - 1) / kCfSamples, tcap = int64_t(ctx->sm_count) * 2;
     const unsigned tgrid = unsigned(groups < tcap ? groups : tcap);
     if (k == 5) {
       if (!(ctx->func_attr_done & 1u)) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); ctx->func_attr_done |= 1u; }
-      k_conv1_fwd_tiled<5><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out);
+      k_conv1_fwd_tiled<5><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out, act);
     } else {
       if (!(ctx->func_attr_done & 2u)) { AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd_tiled<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); ctx->func_attr_done |= 2u; }
-      k_conv1_fwd_tiled<3><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out);
+      k_conv1_fwd_tiled<3><<<tgrid, kCfThreads, tsmem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(c_out), out, act);
     }
     AGRS_LAUNCHED(ctx);
     return AGRS_OK;
@@ -959,7 +1012,7 @@ int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const
     AGRS_CUDA(ctx, cudaFuncSetAttribute(k_conv1_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     ctx->func_attr_done |= 4u;
   }
-  k_conv1_fwd<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo, out);
+  k_conv1_fwd<<<unsigned(B < cap ? B : cap), 256, smem, ctx->stream>>>(im, filt, bias, int(B), int(H), int(W), int(k), int(c_out), int(stride), int(pad), Ho, Wo, out, act);
   AGRS_LAUNCHED(ctx);
   return AGRS_OK;
 }

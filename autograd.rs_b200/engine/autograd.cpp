@@ -398,6 +398,24 @@ Tensor forward_pair(const Operators& first, const Operators& second, std::vector
     attach_to_eager_graph(zs, y, second);
     return y;
   }
+  if (act && std::holds_alternative<Conv2D>(first) && xs.size() == 3 && xs[0].dev()->fuse_forward_activation &&
+      conv_implicit_ok(std::get<Conv2D>(first), xs[0], xs[1], xs[2])) {
+    // the implicit-GEMM Conv2D kernel streams its staged output out once: the same stream writes the activation next to it
+    const Conv2D& op = std::get<Conv2D>(first);
+    const Tensor &im = xs[0], &filters = xs[1], &bias = xs[2];
+    auto [h_out, w_out] = op.get_output_shape(im.shapei(2), im.shapei(3));
+    const Shape shape{im.shapei(0), h_out, w_out, op.out_channels};  // NHWC (operators.rs:383)
+    auto zs_ = std::make_shared<Storage>(im.dev(), shape);
+    auto ys_ = std::make_shared<Storage>(im.dev(), shape);
+    ys_->expect_magnitude_report();
+    im.dev()->check(agrs_conv2d_fwd_act_f32(im.dev()->ctx(), im.data->rptr(), filters.data->rptr(), bias.data->rptr(), im.shapei(0), im.shapei(2),
+                                            im.shapei(3), op.k_size, op.out_channels, op.stride, op.pad, zs_->buf->ptr, act, ys_->buf->ptr));
+    Tensor z(zs_), y(ys_);
+    attach_to_eager_graph(xs, z, first);
+    std::vector<Tensor> zs{z};
+    attach_to_eager_graph(zs, y, second);
+    return y;
+  }
   Tensor z = forward(first, std::move(xs));
   return forward(second, {z});
 }

@@ -47,8 +47,9 @@ struct Node {
 // (MeanSquaredError returns a single gradient: the target gets none, autograd.rs:73 zips to the shorter list).
 Tensor forward(const Operators& op, std::vector<Tensor> xs);
 std::vector<Tensor> backward(const Operators& op, const std::vector<Tensor>& xs, const Tensor& grad);
-// forward(second, {forward(first, xs)}) -- same nodes, same bits -- as one launch where the pair is Linear + ReLU / Sigmoid and the
-// device's fuse_forward_activation is on (the activation comes out of the GEMM's epilogue next to the pre-activation)
+// forward(second, {forward(first, xs)}) -- same nodes, same bits -- as one call where the pair is Linear or (single-channel,
+// implicit-GEMM) Conv2D + ReLU / Sigmoid and the device's fuse_forward_activation is on (the kernel that produces the
+// pre-activation writes the activation next to it where that pays)
 Tensor forward_pair(const Operators& first, const Operators& second, std::vector<Tensor> xs);
 void attach_to_eager_graph(std::vector<Tensor>& inputs, Tensor& op_output, const Operators& op);  // operators.rs:27-49
 

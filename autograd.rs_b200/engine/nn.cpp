@@ -12,8 +12,8 @@ Tensor Layer::forward_default(std::vector<Tensor> xs) const {
   Tensor res = xs.at(0).clone();
   const auto ops = get_op_subgraph();
   for (size_t i = 0; i < ops.size(); ++i) {
-    // a Linear operator feeding an activation inside one layer's subgraph goes out as one GEMM call (forward_pair decides)
-    if (i + 1 < ops.size() && std::holds_alternative<agrs::Linear>(ops[i]) &&
+    // a Linear / Conv2D operator feeding an activation inside one layer's subgraph goes out as one call (forward_pair decides)
+    if (i + 1 < ops.size() && (std::holds_alternative<agrs::Linear>(ops[i]) || std::holds_alternative<agrs::Conv2D>(ops[i])) &&
         (std::holds_alternative<agrs::ReLU>(ops[i + 1]) || std::holds_alternative<agrs::Sigmoid>(ops[i + 1]))) {
       res = agrs::forward_pair(ops[i], ops[i + 1], xs);
       ++i;

@@ -687,7 +687,7 @@ class nn:
             ops = self.get_op_subgraph()
             i = 0
             while i < len(ops):
-                if i + 1 < len(ops) and type(ops[i]) is Linear and type(ops[i + 1]) in (ReLU, Sigmoid):
+                if i + 1 < len(ops) and type(ops[i]) in (Linear, Conv2D) and type(ops[i + 1]) in (ReLU, Sigmoid):
                     res = ops[i].forward_then(ops[i + 1], xs)  # one GEMM call, two graph nodes
                     i += 2
                 else:
@@ -792,14 +792,14 @@ class nn:
             return self._params
 
         def forward(self, xs):
-            # a Linear layer followed by a ReLU / Sigmoid layer: both operators in one engine call (same graph, same bits; the
+            # a Linear / Conv2D layer followed by a ReLU / Sigmoid layer: both operators in one engine call (same graph, same bits; the
             # activation comes out of the GEMM's epilogue -- Operator.forward_then)
             t = xs[0]
             ls = self._layers
             i = 0
             while i < len(ls):
-                if i + 1 < len(ls) and type(ls[i]) is nn.Linear and type(ls[i + 1]) in (nn.ReLU, nn.Sigmoid):
-                    t = Linear().forward_then(ls[i + 1].get_op_subgraph()[0], [t] + ls[i].parameters())
+                if i + 1 < len(ls) and type(ls[i]) in (nn.Linear, nn.Conv2D) and type(ls[i + 1]) in (nn.ReLU, nn.Sigmoid):
+                    t = ls[i].get_op_subgraph()[0].forward_then(ls[i + 1].get_op_subgraph()[0], [t] + ls[i].parameters())
                     i += 2
                 else:
                     t = ls[i].forward([t])

@@ -263,6 +263,12 @@ AGRS_API int agrs_col2im_f32(agrs_ctx* ctx, const float* col, int64_t B, int64_t
 AGRS_API int agrs_conv2d_implicit_ok(int64_t B, int64_t C, int64_t H, int64_t W, int64_t k, int64_t c_out, int64_t stride, int64_t pad);
 AGRS_API int agrs_conv2d_fwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W,
                                  int64_t k, int64_t c_out, int64_t stride, int64_t pad, float* out);
+/* Conv2D::forward followed by ReLU / Sigmoid (layers.rs:24-43 feeding operators.rs:350-390 into :112-116 / :195-200) as one launch:
+ * out as agrs_conv2d_fwd_f32 writes it (the pre-activation, kept for the activation node's backward) and y = act(out), same layout,
+ * written by the same streaming stage of the kernel; `act` is an agrs_act.  Same bits as the two separate calls; honours
+ * agrs_next_output_absmax (reports on y). */
+AGRS_API int agrs_conv2d_fwd_act_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* bias, int64_t B, int64_t H, int64_t W,
+                                     int64_t k, int64_t c_out, int64_t stride, int64_t pad, float* out, int act, float* y);
 AGRS_API int agrs_conv2d_bwd_f32(agrs_ctx* ctx, const float* im, const float* filt, const float* grad, int64_t B, int64_t H, int64_t W,
                                  int64_t k, int64_t c_out, int64_t stride, int64_t pad, float* dx, float* dw, float* db);
 /* out[c*kk + r, o] = filt[r, o] for every c: the [k,k,Co] -> [Ci,k,k,Co] broadcast (storage.rs:114-120) */

@@ -890,3 +890,64 @@ def test_forward_pair_of_other_operators_is_two_forwards(dev):
     assert y.graph_info() == ("Sigmoid", 1, 1)
     want = O.sigmoid_fwd(O.relu_fwd(x))
     assert np.allclose(y.data(), want, rtol=4e-7)
+
+
+@pytest.mark.parametrize("act", ["relu", "sigmoid"])
+@pytest.mark.parametrize("B,H,Wd,co,k,s,p", [(64, 28, 28, 6, 5, 1, 0), (1026, 28, 28, 6, 5, 1, 0), (3, 9, 11, 8, 3, 1, 1), (5, 12, 10, 4, 3, 2, 1),
+                                                 (7, 16, 20, 8, 3, 1, 0), (9, 13, 12, 1, 3, 1, 0)])
+def test_conv2d_forward_fusion_is_bit_identical_and_keeps_the_graph(dev, act, B, H, Wd, co, k, s, p):
+    """Conv2D feeding ReLU / Sigmoid as one launch (agrs_conv2d_fwd_act_f32 through Operator.forward_then): the pre-activation, the
+    activation and the gradients that flow back through both nodes carry the bits of the two separate forwards -- register-tiled and
+    generic kernels, ragged last group of samples, stride / padding -- and both track the oracle (operators.rs:350-390 into :112-116)."""
+    rng = np.random.default_rng(B + H + k + p + co)
+    im = rng.standard_normal((B, 1, H, Wd)).astype(np.float32)
+    filt = rng.standard_normal((k, k, co)).astype(np.float32)
+    bias = rng.standard_normal((co,)).astype(np.float32)
+    act_op = {"relu": F.ReLU, "sigmoid": F.Sigmoid}[act]
+    res = {}
+    for fused in (True, False):
+        dev.set_forward_fusion(fused)
+        try:
+            X, Fl, Bi = T(dev, im), T(dev, filt), T(dev, bias)
+            n0 = dev.launches()
+            y = F.Conv2D(1, co, k, s, p).forward_then(act_op(), [X.clone(), Fl.clone(), Bi.clone()])
+            launches = dev.launches() - n0
+            assert y.graph_info() == ({"relu": "ReLU", "sigmoid": "Sigmoid"}[act], 1, 1)
+            F.Mean().forward([y]).backward()
+            res[fused] = (y.data(), X.grad().data(), Fl.grad().data(), Bi.grad().data(), launches)
+        finally:
+            dev.set_forward_fusion(True)
+    for a, b in zip(res[True][:4], res[False][:4]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert res[True][4] < res[False][4]
+    z, _ = O.conv2d_fwd(im, filt, bias, 1, k, s, p)
+    want = O.relu_fwd(z) if act == "relu" else O.sigmoid_fwd(z)
+    assert O.rel_err(res[True][0], want) < 1e-5
+
+
+def test_lenet_forward_fusion_trains_alike(dev):
+    """C3 in miniature: Conv2D + ReLU as one launch against two, three steps, identical losses and parameters"""
+    rng = np.random.default_rng(34)
+    B = 48
+    im = rng.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32)
+    t = rng.uniform(0, 1, (B, 10)).astype(np.float32)
+    filt = rng.uniform(-0.3, 0.3, (5, 5, 6)).astype(np.float32)
+    cb = rng.uniform(-0.1, 0.1, (6,)).astype(np.float32)
+    w = rng.uniform(-0.05, 0.05, (3456, 10)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (1, 10)).astype(np.float32)
+    runs = []
+    for fused in (True, False):
+        dev.set_forward_fusion(fused)
+        try:
+            net = W.build_lenet(dev, filt, cb, w, b)
+            tr = W.Trainer(net, 1e-3)
+            X, Tt = T(dev, im), T(dev, t)
+            Tt.requires_grad = False
+            n0 = dev.launches()
+            losses = [tr.step(X, Tt).item() for _ in range(3)]
+            runs.append((losses, [q.data() for q in net.parameters()], dev.launches() - n0))
+        finally:
+            dev.set_forward_fusion(True)
+    assert runs[0][0] == runs[1][0]
+    assert all(np.array_equal(a, b) for a, b in zip(runs[0][1], runs[1][1]))
+    assert runs[0][2] < runs[1][2]

@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--cpu", type=int, default=1)
     a = ap.parse_args()
     dev = F.Device(0)
+    if os.environ.get("AGRS_NO_FWD_FUSION"):  # A/B: Linear / Conv2D and the activation behind it as two calls
+        dev.set_forward_fusion(False)
     out = []
 
     def emit(r):
