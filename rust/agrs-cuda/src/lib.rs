@@ -90,6 +90,23 @@ impl CudaData {
         self.ctx.check(rc);
         out
     }
+    /// `dot` + bias followed by ReLU (act = 1) or Sigmoid (act = 2) as one call: returns (pre-activation, activation).  What
+    /// `Layer::forward_default` (layers.rs:24-43) can call when a Linear operator feeds an activation; the activation's node still
+    /// gets the pre-activation as its variable (operators.rs:120-129, :214-224).
+    pub fn dot_bias_act(&self, other: &CudaData, bias: &CudaData, act: i32) -> (CudaData, CudaData) {
+        assert!(self.ndim() <= 2 && other.ndim() <= 2, "Ndarray only supports 1d/2d matmul!");
+        let (m, k, n) = (self.shape[0] as i64, self.shape[1] as i64, other.shape[1] as i64);
+        assert_eq!(k, other.shape[0] as i64, "inputs are not compatible for matrix multiplication");
+        let z = CudaData::alloc(&self.ctx, &[m as usize, n as usize]);
+        let y = CudaData::alloc(&self.ctx, &[m as usize, n as usize]);
+        let (ta, tb) = (self.transposed as i32, other.transposed as i32);
+        let rc = unsafe {
+            sys::agrs_gemm_bias_act_f32(self.ctx.raw(), ta, tb, m, n, k, self.ptr, if self.transposed { m } else { k }, other.ptr,
+                                        if other.transposed { k } else { n }, z.ptr, n, bias.ptr as *const f32, act, y.ptr, n)
+        };
+        self.ctx.check(rc);
+        (z, y)
+    }
     /// operators.rs:115 (ReLU forward) and :103 (backward_dispatch)
     pub fn relu(&self) -> CudaData {
         let out = CudaData::alloc(&self.ctx, &self.shape);
