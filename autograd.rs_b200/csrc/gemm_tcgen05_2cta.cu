@@ -108,13 +108,6 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
                "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-// the other direction (forward activation in the epilogue: the folded partial sum of the earlier K chunks comes back as a piece)
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int32_t c0, int32_t c1, int32_t c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {  // at most N of this thread's bulk groups still read their shared-memory source
