@@ -22,3 +22,13 @@ def test_conv_tile_index_algebra():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.check() == []
+
+
+def test_activation_warps_decomposition_and_handover():
+    """Host model of the pair GEMM's activation warps (tools/act_warps_check.py): every 16-byte vector of a CTA's part of a tile is
+    visited exactly once on both index paths, fast-path accesses are 512 contiguous bytes, and the z_done / act_done mbarrier
+    hand-over neither deadlocks nor lets a barrier run two phases ahead of a waiter under randomised interleavings."""
+    spec = importlib.util.spec_from_file_location("act_warps_check", os.path.join(ROOT, "tools", "act_warps_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check() == []
