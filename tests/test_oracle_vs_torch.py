@@ -145,3 +145,22 @@ def test_training_loop_tracks_torch_autograd_step_for_step(act):
     assert max(abs(a - b) / abs(b) for a, b in zip(want, got)) < 1e-12
     for l, w, b in zip(layers, Ws, Bs):
         assert close(l.w.data, w.detach().numpy()) and close(l.b.data, b.detach().numpy())
+
+
+def test_conv2d_three_input_channels_share_the_filter():
+    """D5 (operators.rs:362-376): the [k, k, Co] filter is broadcast over the input channels -- a convolution whose weight is the same
+    for every channel; the forward, dx and db follow torch with that weight (dw keeps the reference's own [KK, C] regrouping, which
+    is a convolution gradient only for one channel and is pinned by shape in the reference's test_conv2d instead)"""
+    rng = np.random.default_rng(12)
+    B, C, H, W, co, k = 2, 3, 9, 8, 4, 3
+    im, filt, bias = rng.standard_normal((B, C, H, W)), rng.standard_normal((k, k, co)), rng.standard_normal((co,))
+    out, col2d = O.conv2d_fwd(im, filt, bias, C, k, 1, 0)
+    g = rng.standard_normal(out.shape)
+    dx, dw, db = O.conv2d_bwd(im, filt, col2d, g, C, k, 1, 0, literal=False)
+    IM, Bs = t64(im, True), t64(bias, True)
+    Wt = t64(np.broadcast_to(np.transpose(filt, (2, 0, 1))[:, None], (co, C, k, k)).copy())
+    Y = torch.nn.functional.conv2d(IM, Wt, Bs)
+    Y.backward(t64(np.transpose(g, (0, 3, 1, 2))))
+    assert close(out, np.transpose(Y.detach().numpy(), (0, 2, 3, 1)))
+    assert close(dx, IM.grad.numpy()) and close(db, Bs.grad.numpy())
+    assert dw.shape == (k, k, co)
