@@ -39,6 +39,10 @@ def main():
 
     img_b, out_b, col_b = B * H * H * 4, B * P * co * 4, B * P * kk * 4
     t_impl = timed("implicit forward (agrs_conv2d_fwd_f32)", lambda: ctx.call("agrs_conv2d_fwd_f32", im.ptr, filt.ptr, bias.ptr, B, H, H, k, co, 1, 0, out.ptr), img_b + out_b)
+    y = ctx.empty(B * P * co)
+    timed("implicit forward + ReLU in one launch (agrs_conv2d_fwd_act_f32)",
+          lambda: ctx.call("agrs_conv2d_fwd_act_f32", im.ptr, filt.ptr, bias.ptr, B, H, H, k, co, 1, 0, out.ptr, 1, y.ptr), img_b + 2 * out_b)
+    timed("ReLU forward on the conv output, its own launch (agrs_relu_fwd_f32)", lambda: ctx.call("agrs_relu_fwd_f32", out.ptr, y.ptr, B * P * co), 2 * out_b)
     t_impl += timed("implicit backward (agrs_conv2d_bwd_f32: dx, dw, db)", lambda: ctx.call("agrs_conv2d_bwd_f32", im.ptr, filt.ptr, g.ptr, B, H, H, k, co, 1, 0, dx.ptr, dw.ptr, db.ptr),
                     img_b + out_b + img_b)
     t_lit = timed("literal: im2col", lambda: ctx.call("agrs_im2col_f32", im.ptr, B, 1, H, H, k, 1, 0, col.ptr), img_b + col_b)
